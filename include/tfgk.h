@@ -1,0 +1,135 @@
+/*
+ * tfgk.h - C ABI of the B200 (sm_100a) message-passing kernel backend for tf_geometric's hot path.
+ *
+ * The reference (CrawlScript/tf_geometric @4539f11) has NO native FFI: its "operator API" for this path is a set
+ * of Python functions built on stock TensorFlow ops and the tf_sparse package.  Each entry point below therefore
+ * cites the reference Python interface (file:line, relative to /root/reference/tf_geometric) whose arithmetic it
+ * replaces; INTEGRATION.md shows the ctypes binding a tf_geometric maintainer would add at each of those sites.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch's allocator in this repo); the library never
+ *     allocates or frees device memory: scratch space is queried (`*_workspace_bytes`) and passed in;
+ *   - `stream` is a cudaStream_t cast to void* (NULL = default stream); all launches are asynchronous, except
+ *     tfgk_csr_build which synchronises `stream` once to report out-of-range node ids;
+ *   - outputs are fully overwritten; no global mutable state (calls on distinct streams are thread-safe);
+ *   - return value 0 = TFGK_OK, otherwise an error code with a thread-local message in tfgk_last_error();
+ *   - float data is IEEE fp32, node ids int32, edge offsets (rowptr) int64; one call handles < 2^31 edges;
+ *   - "row" = aggregation target (destination), "col" = neighbour (source): nn/kernel/map_reduce.py:60-70.
+ */
+#ifndef TFGK_H_
+#define TFGK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TFGK_ABI_VERSION 1
+
+enum tfgk_status {
+    TFGK_OK = 0,
+    TFGK_ERR_INVALID_ARGUMENT = 1,
+    TFGK_ERR_CUDA = 2,
+    TFGK_ERR_WORKSPACE = 3,
+    TFGK_ERR_UNSUPPORTED = 4,
+    TFGK_ERR_INDEX_OUT_OF_RANGE = 5
+};
+
+enum tfgk_reduce { TFGK_REDUCE_SUM = 0, TFGK_REDUCE_MEAN = 1, TFGK_REDUCE_MAX = 2 };
+enum tfgk_act { TFGK_ACT_NONE = 0, TFGK_ACT_RELU = 1 };
+enum tfgk_deg_power { TFGK_POW_INV_SQRT = 0, TFGK_POW_INV = 1 };
+
+int tfgk_version(void);
+const char *tfgk_last_error(void);
+/* SM count and compute capability of the current device (used by the host side to refuse non-sm_100 parts). */
+int tfgk_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---- integer edge preprocessing (bit-exact) ------------------------------------------------------------------ */
+
+/* utils/graph_utils.py:350-366 add_self_loop_edge: out[2,E+N] = concat(edge_index[2,E], [[0..N-1],[0..N-1]]). */
+int tfgk_self_loops_i32(const int32_t *edge_index, int64_t E, int32_t N, int32_t *out, void *stream);
+/* same function, weight half: out[E+N] = concat(w (ones if NULL), fill). */
+int tfgk_self_loop_weights_f32(const float *w, int64_t E, int32_t N, float fill, float *out, void *stream);
+/* nn/kernel/segment.py:36-40 segment_count: int32 histogram of ids (negative ids dropped like
+ * tf.math.unsorted_segment_sum; ids >= N are an error reported by tfgk_csr_build, ignored here). */
+int tfgk_segment_count_i32(const int32_t *ids, int64_t E, int32_t N, int32_t *out, void *stream);
+
+/* Destination-sorted CSR of a COO edge list: a STABLE sort by row, so that a left-to-right walk of a row
+ * visits its edges in input order (= tf.math.unsorted_segment_sum's CPU summation order).
+ *   rowptr[N+1] int64, col_sorted[E] = col[perm], perm[E] (position in the input list).
+ * Replaces the implicit scatter of tf.math.unsorted_segment_* (nn/kernel/map_reduce.py:16,28,41) and of
+ * tf_sparse.SparseMatrix.matmul (nn/conv/gcn.py:280, gat.py:89, appnp.py:86). */
+int tfgk_csr_workspace_bytes(int64_t E, int32_t N, size_t *out_bytes);
+int tfgk_csr_build(const int32_t *row, const int32_t *col, int64_t E, int32_t N_rows, int32_t N_cols,
+                   int64_t *rowptr, int32_t *col_sorted, int32_t *perm,
+                   void *workspace, size_t workspace_bytes, void *stream);
+
+/* dst[i*width + j] = src[perm[i]*width + j]   (COO order -> CSR order) and the inverse scatter. */
+int tfgk_permute_f32(const float *src, const int32_t *perm, int64_t E, int32_t width, float *dst, void *stream);
+int tfgk_unpermute_f32(const float *src, const int32_t *perm, int64_t E, int32_t width, float *dst, void *stream);
+
+/* ---- GCN normalisation (nn/conv/gcn.py:32-130, utils/graph_utils.py:914-943) -------------------------------- */
+
+/* SparseMatrix.segment_sum(axis=-1) on CSR-ordered values: out[r] = sum of w[rowptr[r]..rowptr[r+1]) in order. */
+int tfgk_csr_rowsum_f32(const int64_t *rowptr, const float *w_csr, int32_t N, float *out, void *stream);
+/* tf.pow(deg, -0.5 | -1) followed by _remove_inf_and_nan (gcn.py:23-29,81-82,104-105,114-115). */
+int tfgk_deg_inv_f32(const float *deg, int32_t N, int power, float *out, void *stream);
+/* (diags(dl) @ A) @ diags(dr) on the value array, COO order: out[e] = (dl[row[e]] * w[e]) * dr[col[e]];
+ * dl or dr may be NULL (gcn.py:94,109,119). */
+int tfgk_scale_edges_f32(const int32_t *row, const int32_t *col, const float *w, int64_t E,
+                         const float *dl, const float *dr, float *out, void *stream);
+
+/* ---- K1: gather - edge-apply - segment-reduce ---------------------------------------------------------------- */
+
+/* out[r,:] = epilogue( REDUCE_{e in row r} ( w[e] * h[col[e],:] ) )            r in [0, n_dst)
+ *   reduce = SUM  : tf.math.unsorted_segment_sum  (map_reduce.py:15-16), tf_sparse matmul (gcn.py:280)
+ *            MEAN : tf.math.unsorted_segment_mean (map_reduce.py:27-28; graph_sage.py:41), empty row -> 0
+ *            MAX  : tf.math.unsorted_segment_max  (map_reduce.py:38-42), empty row -> -FLT_MAX
+ *   w NULL = identity_mapper (map_reduce.py:7-8), else gcn_mapper (gcn.py:221-222); CSR order.
+ *   epilogue: v = agg*alpha + addend*beta (addend NULL -> v = agg; APPNP appnp.py:86-87, sum_updater
+ *   map_reduce.py:19-20), then + bias[D] (NULL ok), then activation  (gcn.py:284-288).
+ * Deterministic (no atomics); per-row accumulation is sequential in CSR order for rows of <= 1024 edges. */
+int tfgk_spmm_f32(const int64_t *rowptr, const int32_t *col, const float *w,
+                  const float *h, int64_t ldh, int32_t n_dst, int32_t D, int reduce,
+                  float alpha, const float *addend, int64_t ld_addend, float beta,
+                  const float *bias, int act,
+                  float *out, int64_t ldo, void *stream);
+
+/* ---- K3: edge softmax and fused GAT ------------------------------------------------------------------------- */
+
+/* nn/kernel/segment.py:26-33 segment_softmax over CSR segments, H interleaved score columns:
+ * score/out are [E, H] row-major in CSR order; per (segment, h): exp(s - max) / (sum + 1e-8). */
+int tfgk_segment_softmax_f32(const int64_t *rowptr, const float *score, int32_t n_seg, int32_t H,
+                             float *out, void *stream);
+
+/* nn/conv/gat.py:73-114 fused: per destination r and head h
+ *     s_e = <Q[r,h,:], K[col_e,h,:]> / scale  (scale = sqrt(dqk), gat.py:78-79) ;  a_e = softmax_e(s_e)  (gat.py:83-84,
+ *     segment.py:26-33) ;  out[r,h,:] = sum_e a_e V[col_e,h,:]  (gat.py:87-89)
+ * Q,K: [N, H*dqk]; V: [N, H*dv]. split_value_heads=1: out[N, H*dv] heads concatenated (gat.py:112);
+ * 0: out[N, dv] = mean over heads (gat.py:114).  Then + bias, activation (gat.py:116-120).
+ * att: [E, H] CSR order, REQUIRED scratch (raw scores, then exp(s - max)); with write_att != 0 it holds the
+ * attention coefficients a_e on return.  The CSR must already contain the self loops gat.py:43 appends. */
+int tfgk_gat_fused_f32(const int64_t *rowptr, const int32_t *col,
+                       const float *Q, int64_t ldq, const float *K, int64_t ldk, const float *V, int64_t ldv,
+                       int32_t N, int32_t H, int32_t dqk, int32_t dv, float scale, int split_value_heads,
+                       const float *bias, int act, float *att, int write_att, float *out, int64_t ldo,
+                       void *stream);
+
+/* ---- K4: dense projections (gcn.py:272, gat.py:52,61,70, graph_sage.py:43-44, appnp.py:69) ------------------- */
+
+/* C[M,N] = act( op(A) @ op(B) + bias[N] + beta * C ),  op = transpose when the flag is set (backward passes).
+ * fp32 in/out. workspace is needed only for split-K (tall-skinny reductions); NULL/0 disables split-K. */
+int tfgk_gemm_workspace_bytes(int32_t M, int32_t N, int32_t K, size_t *out_bytes);
+int tfgk_gemm_f32(const float *A, int64_t lda, int transA, const float *B, int64_t ldb, int transB,
+                  const float *bias, int act, float beta, int32_t M, int32_t N, int32_t K,
+                  float *C, int64_t ldc, void *workspace, size_t workspace_bytes, void *stream);
+
+/* tf.nn.l2_normalize(x, axis=-1) (graph_sage.py:57-58): out = x * rsqrt(max(sum(x^2), 1e-12)). */
+int tfgk_l2_normalize_f32(const float *x, int64_t ldx, int32_t N, int32_t D, float *out, int64_t ldo, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFGK_H_ */

@@ -1,0 +1,612 @@
+# coding=utf-8
+"""
+CPU ORACLE (numpy) for the tf_geometric message-passing hot path.
+
+  *** TEST INFRASTRUCTURE ONLY. ***  Nothing under ``tf_geometric_b200/`` may import this module.
+  Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of
+  ``bench.py`` use it, and only as the checker / the timed CPU arm.
+
+PARITY PINNING STATUS
+  The reference (/root/reference, CrawlScript/tf_geometric @4539f11) ships *no* tests and no golden vectors for
+  this path, and neither TensorFlow nor the un-vendored dependency ``tf_sparse`` (setup.py:25, ">= 0.0.17") can be
+  imported in the authoring container.  The oracle is pinned two ways (see tests/golden/README.md):
+    (1) tests/golden/ref_exec_*.npz - the reference's OWN Python functions (nn/kernel/*.py, nn/conv/{gcn,gat,
+        graph_sage,appnp}.py, utils/graph_utils.py) executed here over a numpy shim of the TF ops they call
+        (tools/gen_golden_from_reference.py).  That pins call order, quirks and the in-repo arithmetic; it does
+        NOT pin TensorFlow's kernels or tf_sparse themselves, whose semantics are restated from their public
+        documentation:  => "parity unpinned" for the TF/tf_sparse half.
+    (2) the tiny hard-coded fixtures of the reference's README/demos and the derived KAT of
+        SURVEY.md section 8c.
+
+TF op semantics restated here (TensorFlow 2.x CPU kernels):
+  * tf.gather(params, ids)                      -> params[ids]  (out-of-range raises on CPU)
+  * tf.math.unsorted_segment_sum(d, ids, n)     -> sequential float32 adds in input order, empty segment = 0,
+                                                   negative ids are dropped.
+  * tf.math.unsorted_segment_mean               -> unsorted_segment_sum / maximum(count, 1)
+  * tf.math.unsorted_segment_max / _min         -> empty segment = lowest()/max() of the dtype
+  * tf.unique                                   -> first-occurrence order, plus inverse index
+
+All floating point arithmetic is float32, indices int32 (data/graph.py:22-23,58-66).
+Every function cites the reference file:line it restates (paths relative to /root/reference/tf_geometric).
+"""
+import numpy as np
+
+F32 = np.float32
+I32 = np.int32
+FLT_LOWEST = np.finfo(np.float32).min
+FLT_MAX = np.finfo(np.float32).max
+
+
+# --------------------------------------------------------------------------------------------------------------
+# TensorFlow op semantics
+# --------------------------------------------------------------------------------------------------------------
+
+def _as_f32(a):
+    return np.ascontiguousarray(a, dtype=F32)
+
+
+def gather(params, ids):
+    """tf.gather on axis 0."""
+    ids = np.asarray(ids)
+    if ids.size and (ids.min() < 0 or ids.max() >= params.shape[0]):
+        raise IndexError("gather index out of range (TF-CPU raises InvalidArgument)")
+    return params[ids]
+
+
+def unsorted_segment_sum(data, segment_ids, num_segments):
+    """tf.math.unsorted_segment_sum, CPU kernel: out[ids[i]] += data[i] for i = 0..n-1 in order, fp32."""
+    data = np.asarray(data)
+    segment_ids = np.asarray(segment_ids)
+    out = np.zeros((int(num_segments),) + data.shape[1:], dtype=data.dtype)
+    keep = segment_ids >= 0
+    if not keep.all():
+        data, segment_ids = data[keep], segment_ids[keep]
+    if segment_ids.size and segment_ids.max() >= num_segments:
+        raise IndexError("segment id out of range")
+    np.add.at(out, segment_ids, data)  # unbuffered, applied in index order -> sequential fp32 rounding
+    return out
+
+
+def unsorted_segment_mean(data, segment_ids, num_segments):
+    """tf.math.unsorted_segment_mean = segment_sum(data) / maximum(segment_sum(ones), 1)."""
+    data = np.asarray(data)
+    s = unsorted_segment_sum(data, segment_ids, num_segments)
+    cnt = unsorted_segment_sum(np.ones(len(segment_ids), dtype=data.dtype), segment_ids, num_segments)
+    cnt = np.maximum(cnt, data.dtype.type(1))
+    return (s / cnt.reshape((-1,) + (1,) * (data.ndim - 1))).astype(data.dtype)
+
+
+def unsorted_segment_max(data, segment_ids, num_segments):
+    """tf.math.unsorted_segment_max: empty segment -> numeric_limits<T>::lowest()."""
+    data = np.asarray(data)
+    low = np.finfo(data.dtype).min if data.dtype.kind == "f" else np.iinfo(data.dtype).min
+    out = np.full((int(num_segments),) + data.shape[1:], low, dtype=data.dtype)
+    np.maximum.at(out, np.asarray(segment_ids), data)
+    return out
+
+
+def unsorted_segment_min(data, segment_ids, num_segments):
+    data = np.asarray(data)
+    high = np.finfo(data.dtype).max if data.dtype.kind == "f" else np.iinfo(data.dtype).max
+    out = np.full((int(num_segments),) + data.shape[1:], high, dtype=data.dtype)
+    np.minimum.at(out, np.asarray(segment_ids), data)
+    return out
+
+
+def tf_unique(x):
+    """tf.unique: values in first-occurrence order + index of each input element into them."""
+    x = np.asarray(x)
+    uniq_sorted, first_pos, inverse_sorted = np.unique(x, return_index=True, return_inverse=True)
+    order = np.argsort(first_pos, kind="stable")          # sorted-unique slot -> first-occurrence rank
+    rank_of_sorted_slot = np.empty_like(order)
+    rank_of_sorted_slot[order] = np.arange(len(order))
+    return uniq_sorted[order], rank_of_sorted_slot[inverse_sorted].astype(I32)
+
+
+def relu(x):
+    return np.maximum(x, F32(0))
+
+
+def l2_normalize(x, eps=1e-12):
+    """tf.nn.l2_normalize(x, axis=-1): x * rsqrt(max(sum(x^2), eps))."""
+    sq = np.sum(x * x, axis=-1, keepdims=True, dtype=F32)
+    return (x * (F32(1) / np.sqrt(np.maximum(sq, F32(eps))))).astype(F32)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# nn/kernel/map_reduce.py
+# --------------------------------------------------------------------------------------------------------------
+
+def identity_mapper(repeated_x, neighbor_x, edge_weight=None):          # map_reduce.py:7-8
+    return neighbor_x
+
+
+def neighbor_count_mapper(repeated_x, neighbor_x, edge_weight=None):    # map_reduce.py:11-12
+    return np.ones([neighbor_x.shape[0], 1], dtype=F32)
+
+
+def gcn_mapper(repeated_x, neighbor_x, edge_weight=None):               # nn/conv/gcn.py:221-222
+    return (neighbor_x * np.asarray(edge_weight, dtype=F32)[:, None]).astype(F32)
+
+
+def sum_reducer(neighbor_msg, node_index, num_nodes=None):              # map_reduce.py:15-16
+    return unsorted_segment_sum(neighbor_msg, node_index, num_nodes)
+
+
+def mean_reducer(neighbor_msg, node_index, num_nodes=None):             # map_reduce.py:27-28
+    return unsorted_segment_mean(neighbor_msg, node_index, num_nodes)
+
+
+def max_reducer(neighbor_msg, node_index, num_nodes=None):              # map_reduce.py:38-42 (TF2 branch)
+    if num_nodes is None:
+        num_nodes = int(np.max(node_index)) + 1
+    return unsorted_segment_max(neighbor_msg, node_index, num_nodes)
+
+
+def sum_updater(x, reduced_neighbor_msg):                               # map_reduce.py:19-20
+    return x + reduced_neighbor_msg
+
+
+def identity_updater(x, reduced_neighbor_msg):                          # map_reduce.py:23-24
+    return reduced_neighbor_msg
+
+
+def aggregate_neighbors(x, edge_index, edge_weight=None, mapper=identity_mapper,
+                        reducer=sum_reducer, updater=sum_updater, num_nodes=None):
+    """map_reduce.py:45-73.  Note `tf.shape(edge_index)[0] == 0` only triggers for a rank-1 empty tensor."""
+    edge_index = np.asarray(edge_index)
+    if edge_index.shape[0] == 0:                                        # :57-58
+        return x
+    row, col = edge_index[0], edge_index[1]                             # :60
+    repeated_x = gather(x, row)                                         # :62
+    neighbor_x = gather(x, col)                                         # :63
+    neighbor_msg = mapper(repeated_x, neighbor_x, edge_weight=edge_weight)  # :65
+    if num_nodes is None:
+        num_nodes = x.shape[0]                                          # :67-68
+    reduced_msg = reducer(neighbor_msg, row, num_nodes=num_nodes)       # :70
+    return updater(x, reduced_msg)                                      # :71
+
+
+# --------------------------------------------------------------------------------------------------------------
+# nn/kernel/segment.py
+# --------------------------------------------------------------------------------------------------------------
+
+def segment_softmax(data, segment_ids, num_segments):
+    """segment.py:26-33: max -> gather -> exp -> sum (+1e-8) -> gather -> divide."""
+    data = _as_f32(data)
+    max_values = unsorted_segment_max(data, segment_ids, num_segments)
+    e = np.exp(data - max_values[segment_ids]).astype(F32)
+    denominator = unsorted_segment_sum(e, segment_ids, num_segments) + F32(1e-8)
+    return (e / denominator[segment_ids]).astype(F32)
+
+
+def segment_count(index, num_segments=None):
+    """segment.py:36-40: histogram in the dtype of `index`."""
+    index = np.asarray(index)
+    if num_segments is None:
+        num_segments = int(index.max()) + 1
+    return unsorted_segment_sum(np.ones_like(index), index, num_segments)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# utils/graph_utils.py (integer edge preprocessing)
+# --------------------------------------------------------------------------------------------------------------
+
+def convert_edge_index_to_edge_hash(edge_index, num_nodes=None):
+    """graph_utils.py:14-43: hash = num_nodes * row + col in int64; num_nodes defaults to max id + 1."""
+    ei = np.asarray(edge_index).astype(np.int64)
+    if num_nodes is None:
+        num_nodes = int(ei.max()) + 1
+    return np.int64(num_nodes) * ei[0] + ei[1], int(num_nodes)
+
+
+def convert_edge_hash_to_edge_index(edge_hash, num_nodes):
+    """graph_utils.py:46-64."""
+    edge_hash = np.asarray(edge_hash, dtype=np.int64)
+    return np.stack([edge_hash // num_nodes, edge_hash % num_nodes], axis=0).astype(I32)
+
+
+def merge_duplicated_edge(edge_index, edge_props=None, merge_modes=None):
+    """graph_utils.py:67-125: tf.unique on the hash (first-occurrence order), props merged per unique slot."""
+    if edge_props is not None and len(edge_props) > 0 and merge_modes is None:
+        merge_modes = ["sum"] * len(edge_props)
+    edge_index = np.asarray(edge_index, dtype=I32)
+    edge_hash, hash_n = convert_edge_index_to_edge_hash(edge_index)
+    uniq_hash, uniq_idx = tf_unique(edge_hash)
+    uniq_edge_index = convert_edge_hash_to_edge_index(uniq_hash, hash_n)
+    if edge_props is None:
+        return uniq_edge_index, None
+    fn = {"min": unsorted_segment_min, "max": unsorted_segment_max,
+          "mean": unsorted_segment_mean, "sum": unsorted_segment_sum}
+    out = []
+    for prop, mode in zip(edge_props, merge_modes):
+        if prop is None:
+            out.append(None)
+        else:
+            if mode not in fn:
+                raise Exception("wrong merge mode: {}".format(mode))
+            out.append(fn[mode](np.asarray(prop), uniq_idx, len(uniq_hash)))
+    return uniq_edge_index, out
+
+
+def convert_edge_to_upper(edge_index, edge_props=None, merge_modes=None):
+    """graph_utils.py:128-151: (min(u,v), max(u,v)) then merge duplicates."""
+    edge_index = np.asarray(edge_index, dtype=I32)
+    upper = np.stack([edge_index.min(axis=0), edge_index.max(axis=0)], axis=0)
+    return merge_duplicated_edge(upper, edge_props, merge_modes)
+
+
+def convert_edge_to_directed(edge_index, edge_props=None, merge_modes=None):
+    """graph_utils.py:155-212: upper edges followed by the mirrored non-self-loop upper edges."""
+    edge_index = np.asarray(edge_index, dtype=I32)
+    if edge_props is not None and len(edge_props) > 0 and merge_modes is None:
+        merge_modes = ["sum"] * len(edge_props)
+    upper, upper_props = convert_edge_to_upper(edge_index, edge_props, merge_modes)
+    mask = upper[0] != upper[1]
+    if not mask.any():                                                  # :205-207
+        return edge_index, edge_props
+    lower = np.stack([upper[1][mask], upper[0][mask]], axis=0)
+    out_index = np.concatenate([upper, lower], axis=1)
+    if edge_props is None:
+        return out_index, None
+    out_props = []
+    for prop, up in zip(edge_props, upper_props):
+        out_props.append(None if prop is None else np.concatenate([up, up[mask]], axis=0))
+    return out_index, out_props
+
+
+def remove_self_loop_edge(edge_index, edge_weight=None):
+    """graph_utils.py:252-269."""
+    edge_index = np.asarray(edge_index)
+    mask = edge_index[0] != edge_index[1]
+    return edge_index[:, mask], (None if edge_weight is None else np.asarray(edge_weight)[mask])
+
+
+def add_self_loop_edge(edge_index, num_nodes, edge_weight=None, fill_weight=1.0):
+    """graph_utils.py:350-366: diagonal appended AFTER the existing edges, no dedup."""
+    edge_index = np.asarray(edge_index, dtype=I32).reshape(2, -1)
+    diag = np.arange(num_nodes, dtype=I32)
+    out_index = np.concatenate([edge_index, np.stack([diag, diag])], axis=1)
+    if edge_weight is None:
+        return out_index, None
+    out_w = np.concatenate([_as_f32(edge_weight), np.full([num_nodes], fill_weight, dtype=F32)])
+    return out_index, out_w
+
+
+def _remove_inf_and_nan(x):                                             # nn/conv/gcn.py:23-29
+    return np.where(np.isinf(x) | np.isnan(x), F32(0), x).astype(F32)
+
+
+def adj_norm_edge(edge_index, num_nodes, edge_weight=None, add_self_loop=False):
+    """graph_utils.py:914-943 (live, tf_sparse-free twin of gcn_norm_adj's default path)."""
+    edge_index = np.asarray(edge_index, dtype=I32)
+    if edge_weight is None:
+        edge_weight = np.ones([edge_index.shape[1]], dtype=F32)
+    if add_self_loop:
+        edge_index, edge_weight = add_self_loop_edge(edge_index, num_nodes, edge_weight, 1.0)
+    row, col = edge_index
+    deg = unsorted_segment_sum(_as_f32(edge_weight), row, num_nodes)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dis = _remove_inf_and_nan(np.power(deg, F32(-0.5)))
+    return edge_index, (dis[row] * _as_f32(edge_weight) * dis[col]).astype(F32)
+
+
+def csr_build(row, col, num_rows):
+    """Integer oracle for the destination-sorted CSR the backend caches: a STABLE sort by row.
+    Returns rowptr[int64, N+1], col_sorted[int32], perm[int32] with row[perm] non-decreasing and ties in input
+    order - so a per-row left-to-right sum reproduces unsorted_segment_sum's sequential rounding."""
+    row = np.asarray(row, dtype=I32)
+    perm = np.argsort(row, kind="stable").astype(I32)
+    counts = np.bincount(row, minlength=num_rows).astype(np.int64)
+    rowptr = np.zeros(num_rows + 1, dtype=np.int64)
+    np.cumsum(counts, out=rowptr[1:])
+    return rowptr, np.asarray(col, dtype=I32)[perm], perm
+
+
+# --------------------------------------------------------------------------------------------------------------
+# tf_sparse.SparseMatrix  [UNVERIFIED restatement - the package is not under /root/reference]
+# --------------------------------------------------------------------------------------------------------------
+
+class SparseMatrix(object):
+    """COO matrix with the subset of tf_sparse.SparseMatrix the reference calls.
+    index int32 [2, nnz] (row = aggregation target), value float32 [nnz] (ones if None), no sort, no merge."""
+
+    def __init__(self, index, value=None, shape=None):
+        self.index = np.asarray(index, dtype=I32).reshape(2, -1)
+        nnz = self.index.shape[1]
+        self.value = np.ones([nnz], dtype=F32) if value is None else _as_f32(value)
+        if shape is None:
+            n = int(self.index.max()) + 1 if nnz else 0
+            shape = [n, n]
+        self.shape = [int(shape[0]), int(shape[1])]
+
+    @property
+    def row(self):
+        return self.index[0]
+
+    @property
+    def col(self):
+        return self.index[1]
+
+    def segment_sum(self, axis=-1):
+        if axis in (-1, 1):
+            return unsorted_segment_sum(self.value, self.row, self.shape[0])
+        return unsorted_segment_sum(self.value, self.col, self.shape[1])
+
+    def segment_softmax(self, axis=-1):
+        ids, n = (self.row, self.shape[0]) if axis in (-1, 1) else (self.col, self.shape[1])
+        return SparseMatrix(self.index, segment_softmax(self.value, ids, n), self.shape)
+
+    def add_diag(self, w):
+        """A + diag(w): diagonal entries appended after the existing ones (same convention as
+        graph_utils.add_self_loop_edge, and as the commented-out legacy `add_self_loop` at gcn.py:78)."""
+        n = min(self.shape)
+        index, value = add_self_loop_edge(self.index, n, self.value, fill_weight=w)
+        return SparseMatrix(index, value, self.shape)
+
+    def scale_rows(self, d):      # diags(d) @ A
+        return SparseMatrix(self.index, (d[self.row] * self.value).astype(F32), self.shape)
+
+    def scale_cols(self, d):      # A @ diags(d)
+        return SparseMatrix(self.index, (self.value * d[self.col]).astype(F32), self.shape)
+
+    def dropout(self, rate, training=False):
+        if training and rate > 0.0:
+            raise NotImplementedError("edge dropout uses the TF RNG stream; parity is defined for inference only")
+        return self
+
+    def matmul(self, h, num_or_size_splits=None):
+        """A @ h = unsorted_segment_sum(gather(h, col) * value[:, None], row)  (legacy code kept in comments at
+        gat.py:91-109, gcn.py:175-176).  Column splitting does not change any output element."""
+        h = _as_f32(h)
+        msg = (h[self.col] * self.value[:, None]).astype(F32)
+        return unsorted_segment_sum(msg, self.row, self.shape[0])
+
+    def __matmul__(self, h):
+        return self.matmul(h)
+
+    def to_dense(self):
+        out = np.zeros(self.shape, dtype=F32)
+        np.add.at(out, (self.row, self.col), self.value)
+        return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# nn/conv/gcn.py
+# --------------------------------------------------------------------------------------------------------------
+
+def gcn_norm_adj(sparse_adj, norm="both", add_self_loop=True, sym=True, renorm=True, improved=False):
+    """nn/conv/gcn.py:32-130 (cache handling omitted: it only memoises the returned triple)."""
+    fill_weight = 2.0 if improved else 1.0                               # :62
+    if sparse_adj.shape[0] != sparse_adj.shape[1]:                       # :65-69
+        if add_self_loop:
+            raise Exception("cannot set add_self_loop=True for GCN when sparse_adj.shape[0] != sparse_adj.shape[1]")
+        if sym:
+            raise Exception("cannot set sym=True for GCN when sparse_adj.shape[0] != sparse_adj.shape[1]")
+    if add_self_loop and norm != "both":                                 # :71-72
+        sparse_adj = sparse_adj.add_diag(fill_weight)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if norm == "both":                                               # :75-98
+            if add_self_loop and renorm:
+                sparse_adj = sparse_adj.add_diag(fill_weight)
+            row_dis = _remove_inf_and_nan(np.power(sparse_adj.segment_sum(axis=-1), F32(-0.5)))
+            if sym:
+                col_dis = row_dis
+            else:
+                col_dis = _remove_inf_and_nan(np.power(sparse_adj.segment_sum(axis=0), F32(-0.5)))
+            normed = sparse_adj.scale_rows(row_dis).scale_cols(col_dis)  # (D^-1/2 A) D^-1/2, :94
+            if add_self_loop and not renorm:
+                normed = normed.add_diag(fill_weight)                    # :97-98
+        elif norm == "left":                                             # :101-109
+            row_inv = _remove_inf_and_nan(np.power(sparse_adj.segment_sum(axis=-1), F32(-1)))
+            normed = sparse_adj.scale_rows(row_inv)
+        elif norm == "right":                                            # :112-119 (row sums, sic)
+            col_inv = _remove_inf_and_nan(np.power(sparse_adj.segment_sum(axis=-1), F32(-1)))
+            normed = sparse_adj.scale_cols(col_inv)
+        else:
+            raise Exception("wrong GCN norm type: {}".format(norm))
+    return normed
+
+
+def gcn_norm_edge(edge_index, num_nodes, edge_weight=None, renorm=True, improved=False):
+    """nn/conv/gcn.py:180-196 (deprecated wrapper still used by gcn_graph_sage)."""
+    normed = gcn_norm_adj(SparseMatrix(edge_index, edge_weight, [num_nodes, num_nodes]),
+                          renorm=renorm, improved=improved)
+    return normed.index, normed.value
+
+
+def gcn(x, sparse_adj, kernel, bias=None, activation=None, norm="both", add_self_loop=True, sym=True,
+        renorm=True, improved=False):
+    """nn/conv/gcn.py:225-290 at inference (edge dropout inactive)."""
+    normed = gcn_norm_adj(sparse_adj, norm, add_self_loop, sym, renorm, improved)
+    h = _as_f32(x) if kernel is None else (_as_f32(x) @ _as_f32(kernel)).astype(F32)   # :266-272
+    h = normed.matmul(h)                                                 # :280
+    if bias is not None:
+        h = h + _as_f32(bias)
+    if activation is not None:
+        h = activation(h)
+    return h.astype(F32)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# nn/conv/gat.py
+# --------------------------------------------------------------------------------------------------------------
+
+def gat(x, edge_index, query_kernel, query_bias, query_activation, key_kernel, key_bias, key_activation,
+        kernel, bias=None, activation=None, num_heads=1, split_value_heads=True, return_attention=False):
+    """nn/conv/gat.py:13-122 at inference, op for op (including the H*N-node virtual graph)."""
+    x = _as_f32(x)
+    num_nodes = x.shape[0]
+    edge_index, _ = add_self_loop_edge(edge_index, num_nodes)            # :43
+    row, col = edge_index
+    Q = (x @ _as_f32(query_kernel)).astype(F32) + _as_f32(query_bias)    # :52-53
+    if query_activation is not None:
+        Q = query_activation(Q)
+    Q = Q[row]                                                           # :56
+    K = (x @ _as_f32(key_kernel)).astype(F32) + _as_f32(key_bias)        # :61-62
+    if key_activation is not None:
+        K = key_activation(K)
+    K = K[col]                                                           # :65
+    V = (x @ _as_f32(kernel)).astype(F32)                                # :70
+    Q_ = np.concatenate(np.split(Q, num_heads, axis=-1), axis=0)         # :73
+    K_ = np.concatenate(np.split(K, num_heads, axis=-1), axis=0)         # :74
+    qk_edge_index_ = np.concatenate([edge_index.astype(np.int64) + i * num_nodes for i in range(num_heads)], axis=1)
+    scale = np.sqrt(F32(Q_.shape[-1]))                                   # :78
+    att_score_ = (np.sum(Q_ * K_, axis=-1, dtype=F32) / scale).astype(F32)   # :79
+    num_nodes_ = num_nodes * num_heads
+    att = segment_softmax(att_score_, qk_edge_index_[0], num_nodes_)     # :83-84
+    V_ = np.concatenate(np.split(V, num_heads, axis=-1), axis=0)         # :87
+    msg = (V_[qk_edge_index_[1]] * att[:, None]).astype(F32)
+    h_ = unsorted_segment_sum(msg, qk_edge_index_[0], num_nodes_)        # :89
+    if split_value_heads:
+        h = np.concatenate(np.split(h_, num_heads, axis=0), axis=-1)     # :112
+    else:
+        parts = np.split(h_, num_heads, axis=0)
+        acc = parts[0]
+        for p in parts[1:]:                                              # tf.add_n, :114
+            acc = acc + p
+        h = acc / F32(num_heads)
+    if bias is not None:
+        h = h + _as_f32(bias)
+    if activation is not None:
+        h = activation(h)
+    h = h.astype(F32)
+    if return_attention:
+        return h, att.reshape(num_heads, -1).T.copy()                    # [E', H]
+    return h
+
+
+# --------------------------------------------------------------------------------------------------------------
+# nn/conv/graph_sage.py
+# --------------------------------------------------------------------------------------------------------------
+
+def _sage_tail(x_self, neighbor_msg, bias, activation, concat, normalize):
+    h = np.concatenate([x_self, neighbor_msg], axis=1) if concat else x_self + neighbor_msg
+    if bias is not None:
+        h = h + _as_f32(bias)
+    if activation is not None:
+        h = activation(h)
+    if normalize:
+        h = l2_normalize(h)
+    return h.astype(F32)
+
+
+def _sage_plain(reducer, x, edge_index, edge_weight, self_kernel, neighbor_kernel, bias, activation, concat,
+                normalize):
+    x = _as_f32(x)
+    num_nodes = x.shape[0]
+    row, col = np.asarray(edge_index, dtype=I32)
+    neighbor_x = x[col]                                                  # graph_sage.py:36
+    if edge_weight is not None:
+        neighbor_x = gcn_mapper(None, neighbor_x, edge_weight)           # :38-39
+    reduced = reducer(neighbor_x, row, num_nodes=num_nodes)              # :41 / :96
+    neighbor_msg = (reduced @ _as_f32(neighbor_kernel)).astype(F32)      # :43
+    x_self = (x @ _as_f32(self_kernel)).astype(F32)                      # :44
+    return _sage_tail(x_self, neighbor_msg, bias, activation, concat, normalize)
+
+
+def mean_graph_sage(x, edge_index, edge_weight, self_kernel, neighbor_kernel, bias=None, activation=None,
+                    concat=True, normalize=False):
+    """nn/conv/graph_sage.py:9-60."""
+    return _sage_plain(mean_reducer, x, edge_index, edge_weight, self_kernel, neighbor_kernel, bias, activation,
+                       concat, normalize)
+
+
+def sum_graph_sage(x, edge_index, edge_weight, self_kernel, neighbor_kernel, bias=None, activation=None,
+                   concat=True, normalize=False):
+    """nn/conv/graph_sage.py:64-115."""
+    return _sage_plain(sum_reducer, x, edge_index, edge_weight, self_kernel, neighbor_kernel, bias, activation,
+                       concat, normalize)
+
+
+def gcn_graph_sage(x, edge_index, edge_weight, kernel, bias=None, activation=None, normalize=False, cache=None):
+    """nn/conv/graph_sage.py:118-161.  Quirks restated literally: a provided edge_weight is replaced by ones
+    (:139-140) and `cache` is passed POSITIONALLY into gcn_norm_edge's `renorm` slot (:142), so
+    renorm = bool(cache): None or {} -> D^-1/2 A D^-1/2 + I ; non-empty dict -> renormalisation trick."""
+    x = _as_f32(x)
+    num_nodes = x.shape[0]
+    edge_index = np.asarray(edge_index, dtype=I32)
+    if edge_weight is not None:
+        edge_weight = np.ones([edge_index.shape[1]], dtype=F32)
+    upd_index, normed_w = gcn_norm_edge(edge_index, num_nodes, edge_weight, renorm=bool(cache))
+    row, col = upd_index
+    reduced = sum_reducer(gcn_mapper(None, x[col], normed_w), row, num_nodes=num_nodes)
+    h = (reduced @ _as_f32(kernel)).astype(F32)
+    if bias is not None:
+        h = h + _as_f32(bias)
+    if activation is not None:
+        h = activation(h)
+    if normalize:
+        h = l2_normalize(h)
+    return h.astype(F32)
+
+
+def _sage_pool(reducer, x, edge_index, edge_weight, self_kernel, neighbor_mlp_kernel, neighbor_kernel,
+               neighbor_mlp_bias, bias, activation, concat, normalize):
+    x = _as_f32(x)
+    num_nodes = x.shape[0]
+    edge_index = np.asarray(edge_index, dtype=I32)
+    if edge_weight is not None:                                          # :190-191 / :253-254
+        edge_weight = np.ones([edge_index.shape[1]], dtype=F32)
+    row, col = edge_index
+    neighbor_x = gcn_mapper(None, x[col], edge_weight)                   # crashes for None, like the reference
+    h = (neighbor_x @ _as_f32(neighbor_mlp_kernel)).astype(F32)          # per-EDGE dense layer
+    if neighbor_mlp_bias is not None:
+        h = h + _as_f32(neighbor_mlp_bias)
+    if activation is not None:
+        h = activation(h)
+    reduced = reducer(h.astype(F32), row, num_nodes=num_nodes)
+    from_neighbor = (reduced @ _as_f32(neighbor_kernel)).astype(F32)
+    from_x = (x @ _as_f32(self_kernel)).astype(F32)
+    return _sage_tail(from_x, from_neighbor, bias, activation, concat, normalize)
+
+
+def mean_pool_graph_sage(x, edge_index, edge_weight, self_kernel, neighbor_mlp_kernel, neighbor_kernel,
+                         neighbor_mlp_bias=None, bias=None, activation=None, concat=True, normalize=False):
+    """nn/conv/graph_sage.py:164-225."""
+    return _sage_pool(mean_reducer, x, edge_index, edge_weight, self_kernel, neighbor_mlp_kernel, neighbor_kernel,
+                      neighbor_mlp_bias, bias, activation, concat, normalize)
+
+
+def max_pool_graph_sage(x, edge_index, edge_weight, self_kernel, neighbor_mlp_kernel, neighbor_kernel,
+                        neighbor_mlp_bias=None, bias=None, activation=None, concat=True, normalize=False):
+    """nn/conv/graph_sage.py:228-287."""
+    return _sage_pool(max_reducer, x, edge_index, edge_weight, self_kernel, neighbor_mlp_kernel, neighbor_kernel,
+                      neighbor_mlp_bias, bias, activation, concat, normalize)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# nn/conv/appnp.py
+# --------------------------------------------------------------------------------------------------------------
+
+def appnp(x, edge_index, edge_weight, kernels, biases, dense_activation=relu, activation=None, k=10, alpha=0.1):
+    """nn/conv/appnp.py:11-92 at inference."""
+    x = _as_f32(x)
+    num_nodes = x.shape[0]
+    normed = gcn_norm_adj(SparseMatrix(edge_index, edge_weight, [num_nodes, num_nodes]))   # :51-53
+    h = x
+    n_dense = len(kernels)
+    for i, (kern, b) in enumerate(zip(kernels, biases)):                 # :64-81
+        h = (h @ _as_f32(kern)).astype(F32)
+        if b is not None:
+            h = h + _as_f32(b)
+        if i < n_dense - 1 and dense_activation is not None:
+            h = dense_activation(h)
+    h = h.astype(F32)
+    out = h
+    for _ in range(k):                                                   # :85-87
+        out = normed.matmul(out)
+        out = (out * F32(1.0 - alpha) + h * F32(alpha)).astype(F32)
+    if activation is not None:
+        out = activation(out)
+    return out.astype(F32)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# float64 dense model used by property tests (NOT a restatement: an independent cross-check of the oracle)
+# --------------------------------------------------------------------------------------------------------------
+
+def dense_spmm_f64(index, value, shape, h):
+    a = np.zeros(shape, dtype=np.float64)
+    np.add.at(a, (index[0], index[1]), np.asarray(value, dtype=np.float64))
+    return a @ np.asarray(h, dtype=np.float64)

@@ -1,0 +1,92 @@
+# coding=utf-8
+"""ctypes binding of include/tfgk.h (libtfgk.so, sm_100a).
+
+There is deliberately NO fallback: if the shared library is missing, or a call fails, an exception is raised.
+PyTorch is only the owner of device memory and streams; every pointer handed to the library is `tensor.data_ptr()`.
+"""
+import ctypes
+import os
+import threading
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtfgk.so")
+_lock = threading.Lock()
+_lib = None
+
+ABI_VERSION = 1
+
+OK = 0
+REDUCE_SUM, REDUCE_MEAN, REDUCE_MAX = 0, 1, 2
+ACT_NONE, ACT_RELU = 0, 1
+POW_INV_SQRT, POW_INV = 0, 1
+
+_i32, _i64, _f32, _int = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_int
+_ptr, _size = ctypes.c_void_p, ctypes.c_size_t
+
+# name -> argtypes, exactly as declared in include/tfgk.h (tests check every symbol is exported)
+SIGNATURES = {
+    "tfgk_version": [],
+    "tfgk_device_info": [ctypes.POINTER(_int)] * 3,
+    "tfgk_self_loops_i32": [_ptr, _i64, _i32, _ptr, _ptr],
+    "tfgk_self_loop_weights_f32": [_ptr, _i64, _i32, _f32, _ptr, _ptr],
+    "tfgk_segment_count_i32": [_ptr, _i64, _i32, _ptr, _ptr],
+    "tfgk_csr_workspace_bytes": [_i64, _i32, ctypes.POINTER(_size)],
+    "tfgk_csr_build": [_ptr, _ptr, _i64, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _size, _ptr],
+    "tfgk_permute_f32": [_ptr, _ptr, _i64, _i32, _ptr, _ptr],
+    "tfgk_unpermute_f32": [_ptr, _ptr, _i64, _i32, _ptr, _ptr],
+    "tfgk_csr_rowsum_f32": [_ptr, _ptr, _i32, _ptr, _ptr],
+    "tfgk_deg_inv_f32": [_ptr, _i32, _int, _ptr, _ptr],
+    "tfgk_scale_edges_f32": [_ptr, _ptr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr],
+    "tfgk_spmm_f32": [_ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _int, _f32, _ptr, _i64, _f32, _ptr, _int, _ptr, _i64,
+                      _ptr],
+    "tfgk_segment_softmax_f32": [_ptr, _ptr, _i32, _i32, _ptr, _ptr],
+    "tfgk_gat_fused_f32": [_ptr, _ptr, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _f32, _int, _ptr,
+                           _int, _ptr, _int, _ptr, _i64, _ptr],
+    "tfgk_gemm_workspace_bytes": [_i32, _i32, _i32, ctypes.POINTER(_size)],
+    "tfgk_gemm_f32": [_ptr, _i64, _int, _ptr, _i64, _int, _ptr, _int, _f32, _i32, _i32, _i32, _ptr, _i64, _ptr, _size,
+                      _ptr],
+    "tfgk_l2_normalize_f32": [_ptr, _i64, _i32, _i32, _ptr, _i64, _ptr],
+}
+
+
+class TfgkError(RuntimeError):
+    """A tfgk_* entry point returned a non-zero status."""
+
+    def __init__(self, fn, code, message):
+        super().__init__("{} failed with status {}: {}".format(fn, code, message))
+        self.code = code
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def lib():
+    """Load libtfgk.so once.  Raises ImportError (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(_LIB_PATH):
+                raise ImportError(
+                    "tf_geometric_b200: {} is missing - build it with `python -c 'import __graft_entry__ as g; "
+                    "g.build()'` or `make -C tf_geometric_b200/csrc`. There is no CPU/PyTorch fallback.".format(_LIB_PATH))
+            handle = ctypes.CDLL(_LIB_PATH)
+            for name, argtypes in SIGNATURES.items():
+                fn = getattr(handle, name)
+                fn.argtypes = argtypes
+                fn.restype = _int
+            handle.tfgk_last_error.argtypes = []
+            handle.tfgk_last_error.restype = ctypes.c_char_p
+            if handle.tfgk_version() != ABI_VERSION:
+                raise ImportError("libtfgk.so ABI version {} != expected {}".format(handle.tfgk_version(), ABI_VERSION))
+            _lib = handle
+    return _lib
+
+
+def call(name, *args):
+    handle = lib()
+    rc = getattr(handle, name)(*args)
+    if rc != OK:
+        raise TfgkError(name, rc, handle.tfgk_last_error().decode("utf-8", "replace"))
+    return rc

@@ -1,0 +1,381 @@
+// K3: edge softmax (tfgk_segment_softmax_f32) and the fused GAT aggregation (tfgk_gat_fused_f32).
+//
+// One warp owns one destination row r of the self-looped CSR and runs three phases without leaving the SM:
+//   A   stream the K rows of the neighbours (one coalesced 4*A-byte request per edge), dot them with Q[r] per head,
+//       write the raw scores s[e,h] to the [E,H] attention buffer and keep the exact per-head maximum;
+//   B1  walk the row's H*deg scores flat and coalesced: p = exp(s - max), accumulate the per-head denominators;
+//   B2  stream the V rows of the neighbours and accumulate  a_e * V[col_e]  in CSR (= reference) order, with
+//       a_e = p_e / (sum + 1e-8)  exactly as nn/kernel/segment.py:26-33 computes it.
+// K and V are each read once per edge, Q and the output once per node: 4*(A+U)+4 bytes per edge - the HBM
+// roofline of the reference's 5-pass segment_softmax + two [E,A] gathers + SpMM pipeline.
+// No tensor cores: the per-edge dot products are 16-wide and the kernel is bound by the gathers.
+#include "common.cuh"
+
+namespace tfgk {
+
+constexpr int kGatThreads = 256;
+constexpr int kGatWarps = kGatThreads / 32;
+constexpr int kMaxHeadsFast = 32;
+
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+struct GatParams {
+    const int64_t *rowptr;
+    const int32_t *col;
+    const float *Q; int64_t ldq;
+    const float *K; int64_t ldk;
+    const float *V; int64_t ldv;
+    int32_t N, H, dqk, dv;
+    float scale;
+    int split;
+    const float *bias;
+    int act;
+    float *att;          // NOT restrict/const: written and re-read by the same warp
+    int write_att;
+    float *out; int64_t ldo;
+};
+
+// ---- fast path: float4 lanes, H | 32, dqk/4 a power of two, heads concatenated ---------------------------------
+template <int NCK, int NCV, int U>
+__global__ void __launch_bounds__(kGatThreads) gat_fast_kernel(const GatParams p) {
+    __shared__ float s_max[kGatWarps][kMaxHeadsFast];
+    __shared__ float s_den[kGatWarps][kMaxHeadsFast];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r = (int64_t)blockIdx.x * kGatWarps + warp;
+    if (r >= p.N) return;   // warp-uniform
+    const int H = p.H;
+    const int A = H * p.dqk, VW = H * p.dv;
+    const int lanes_per_head = p.dqk >> 2;
+    const int64_t start = p.rowptr[r];
+    const int deg = (int)(p.rowptr[r + 1] - start);
+    float *att = p.att + start * H;
+
+    // ---------------- phase A: scores ----------------
+    int kcol[NCK];
+    bool kok[NCK];
+    float4 q[NCK];
+    float mx[NCK];
+#pragma unroll
+    for (int k = 0; k < NCK; ++k) {
+        kcol[k] = (lane + 32 * k) * 4;
+        kok[k] = kcol[k] < A;
+        q[k] = kok[k] ? ldg4(p.Q + r * p.ldq + kcol[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        mx[k] = -FLT_MAX;
+    }
+    for (int t = 0; t < deg; t += 32) {
+        const int e = t + lane;
+        const int my_c = e < deg ? ld_stream_i32(p.col + start + e) : 0;
+        const int nb = min(32, deg - t);
+        for (int j = 0; j < nb; j += U) {
+            float4 kk[U][NCK];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int c = __shfl_sync(0xffffffffu, my_c, j + u);
+                const float *rowp = p.K + (int64_t)c * p.ldk;
+#pragma unroll
+                for (int k = 0; k < NCK; ++k)
+                    if (j + u < nb && kok[k]) kk[u][k] = ldg4(rowp + kcol[k]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool ok = j + u < nb;   // warp-uniform
+#pragma unroll
+                for (int k = 0; k < NCK; ++k) {
+                    float d = 0.0f;
+                    if (ok && kok[k])
+                        d = q[k].x * kk[u][k].x + q[k].y * kk[u][k].y + q[k].z * kk[u][k].z + q[k].w * kk[u][k].w;
+                    for (int off = 1; off < lanes_per_head; off <<= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+                    if (ok && kok[k]) {
+                        const float s = __fdiv_rn(d, p.scale);
+                        mx[k] = fmaxf(mx[k], s);
+                        if ((lane & (lanes_per_head - 1)) == 0) att[(int64_t)(t + j + u) * H + kcol[k] / p.dqk] = s;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NCK; ++k)
+        if (kok[k] && (lane & (lanes_per_head - 1)) == 0) s_max[warp][kcol[k] / p.dqk] = mx[k];
+    __syncwarp();
+
+    // ---------------- phase B1: exp and denominators (flat, coalesced; head of a lane = lane % H) -------------
+    {
+        const float m = s_max[warp][lane & (H - 1)];
+        float part = 0.0f;
+        const int total = deg * H;
+        for (int f = 0; f < total; f += 32) {
+            const int idx = f + lane;
+            if (idx < total) {
+                const float pexp = expf(att[idx] - m);
+                att[idx] = pexp;
+                part += pexp;
+            }
+        }
+        for (int off = 16; off >= H; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+        s_den[warp][lane & (H - 1)] = part + 1e-8f;
+    }
+    __syncwarp();
+
+    // ---------------- phase B2: weighted aggregation of V ----------------
+    int vcol[NCV], vhead[NCV];
+    bool vok[NCV];
+    float den[NCV];
+    float acc[NCV][4];
+#pragma unroll
+    for (int k = 0; k < NCV; ++k) {
+        vcol[k] = (lane + 32 * k) * 4;
+        vok[k] = vcol[k] < VW;
+        vhead[k] = vok[k] ? vcol[k] / p.dv : 0;
+        den[k] = s_den[warp][vhead[k]];
+        acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.0f;
+    }
+    for (int t = 0; t < deg; t += 32) {
+        const int e = t + lane;
+        const int my_c = e < deg ? __ldg(p.col + start + e) : 0;
+        const int nb = min(32, deg - t);
+        for (int j = 0; j < nb; j += U) {
+            float4 vv[U][NCV];
+            float pe[U][NCV];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int c = __shfl_sync(0xffffffffu, my_c, j + u);
+                const float *rowp = p.V + (int64_t)c * p.ldv;
+#pragma unroll
+                for (int k = 0; k < NCV; ++k)
+                    if (j + u < nb && vok[k]) {
+                        vv[u][k] = ldg4(rowp + vcol[k]);
+                        pe[u][k] = att[(int64_t)(t + j + u) * H + vhead[k]];
+                    }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (j + u < nb) {
+#pragma unroll
+                    for (int k = 0; k < NCV; ++k) {
+                        if (vok[k]) {
+                            const float a = __fdiv_rn(pe[u][k], den[k]);
+                            acc[k][0] = __fadd_rn(acc[k][0], __fmul_rn(vv[u][k].x, a));
+                            acc[k][1] = __fadd_rn(acc[k][1], __fmul_rn(vv[u][k].y, a));
+                            acc[k][2] = __fadd_rn(acc[k][2], __fmul_rn(vv[u][k].z, a));
+                            acc[k][3] = __fadd_rn(acc[k][3], __fmul_rn(vv[u][k].w, a));
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NCV; ++k) {
+        if (!vok[k]) continue;
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) b = ldg4(p.bias + vcol[k]);
+        float4 o;
+        o.x = apply_act(acc[k][0] + b.x, p.act);
+        o.y = apply_act(acc[k][1] + b.y, p.act);
+        o.z = apply_act(acc[k][2] + b.z, p.act);
+        o.w = apply_act(acc[k][3] + b.w, p.act);
+        *reinterpret_cast<float4 *>(p.out + r * p.ldo + vcol[k]) = o;
+    }
+    if (p.write_att) {
+        __syncwarp();
+        const float dn = s_den[warp][lane & (H - 1)];
+        const int total = deg * H;
+        for (int f = 0; f < total; f += 32) {
+            const int idx = f + lane;
+            if (idx < total) att[idx] = __fdiv_rn(att[idx], dn);
+        }
+    }
+}
+
+// ---- generic path: any H / dqk / dv, split or averaged heads (correctness first) --------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+
+__global__ void __launch_bounds__(kGatThreads) gat_generic_kernel(const GatParams p) {
+    extern __shared__ float smem[];   // [warps][2][H]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r = (int64_t)blockIdx.x * kGatWarps + warp;
+    if (r >= p.N) return;
+    const int H = p.H;
+    float *s_max = smem + (size_t)warp * 2 * H;
+    float *s_den = s_max + H;
+    const int64_t start = p.rowptr[r];
+    const int deg = (int)(p.rowptr[r + 1] - start);
+    float *att = p.att + start * H;
+    const int32_t *col = p.col + start;
+
+    for (int h = lane; h < H; h += 32) s_max[h] = -FLT_MAX;
+    __syncwarp();
+    for (int e = 0; e < deg; ++e) {
+        const float *krow = p.K + (int64_t)col[e] * p.ldk;
+        const float *qrow = p.Q + r * p.ldq;
+        for (int h = 0; h < H; ++h) {
+            float d = 0.0f;
+            for (int j = lane; j < p.dqk; j += 32) d += qrow[h * p.dqk + j] * krow[h * p.dqk + j];
+            d = warp_sum(d);
+            if (lane == 0) {
+                const float s = __fdiv_rn(d, p.scale);
+                att[(int64_t)e * H + h] = s;
+                s_max[h] = fmaxf(s_max[h], s);
+            }
+        }
+    }
+    __syncwarp();
+    for (int h = 0; h < H; ++h) {
+        const float m = s_max[h];
+        float part = 0.0f;
+        for (int e = lane; e < deg; e += 32) {
+            const float pexp = expf(att[(int64_t)e * H + h] - m);
+            att[(int64_t)e * H + h] = pexp;
+            part += pexp;
+        }
+        part = warp_sum(part);
+        if (lane == 0) s_den[h] = part + 1e-8f;
+    }
+    __syncwarp();
+    if (p.split) {
+        for (int c = lane; c < H * p.dv; c += 32) {
+            const int hv = c / p.dv;
+            const float dn = s_den[hv];
+            float acc = 0.0f;
+            for (int e = 0; e < deg; ++e) {
+                const float a = __fdiv_rn(att[(int64_t)e * H + hv], dn);
+                acc = __fadd_rn(acc, __fmul_rn(p.V[(int64_t)col[e] * p.ldv + c], a));
+            }
+            if (p.bias) acc += p.bias[c];
+            p.out[r * p.ldo + c] = apply_act(acc, p.act);
+        }
+    } else {
+        for (int u = lane; u < p.dv; u += 32) {
+            float tot = 0.0f;
+            for (int h = 0; h < H; ++h) {
+                const float dn = s_den[h];
+                float acc = 0.0f;
+                for (int e = 0; e < deg; ++e) {
+                    const float a = __fdiv_rn(att[(int64_t)e * H + h], dn);
+                    acc = __fadd_rn(acc, __fmul_rn(p.V[(int64_t)col[e] * p.ldv + h * p.dv + u], a));
+                }
+                tot = h == 0 ? acc : __fadd_rn(tot, acc);     // tf.add_n over heads
+            }
+            tot = __fdiv_rn(tot, (float)H);
+            if (p.bias) tot += p.bias[u];
+            p.out[r * p.ldo + u] = apply_act(tot, p.act);
+        }
+    }
+    if (p.write_att) {
+        __syncwarp();
+        for (int idx = lane; idx < deg * H; idx += 32) att[idx] = __fdiv_rn(att[idx], s_den[idx % H]);
+    }
+}
+
+// ---- stand-alone segment softmax over CSR segments ------------------------------------------------------------
+__global__ void __launch_bounds__(kGatThreads) segment_softmax_kernel(const int64_t *__restrict__ rowptr,
+                                                                      const float *__restrict__ score, int32_t n_seg,
+                                                                      int32_t H, float *__restrict__ out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r = (int64_t)blockIdx.x * kGatWarps + warp;
+    if (r >= n_seg) return;
+    const int64_t start = rowptr[r];
+    const int deg = (int)(rowptr[r + 1] - start);
+    const float *s = score + start * H;
+    float *o = out + start * H;
+    for (int h = 0; h < H; ++h) {
+        float m = -FLT_MAX;
+        for (int e = lane; e < deg; e += 32) m = fmaxf(m, s[(int64_t)e * H + h]);
+        m = warp_max(m);
+        float part = 0.0f;
+        for (int e = lane; e < deg; e += 32) {
+            const float pexp = expf(s[(int64_t)e * H + h] - m);
+            o[(int64_t)e * H + h] = pexp;
+            part += pexp;
+        }
+        const float den = warp_sum(part) + 1e-8f;
+        for (int e = lane; e < deg; e += 32) o[(int64_t)e * H + h] = __fdiv_rn(o[(int64_t)e * H + h], den);
+    }
+}
+
+static inline bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+template <int NCK, int NCV>
+static int launch_gat_fast(const GatParams &p, cudaStream_t st) {
+    constexpr int U = (NCK + NCV <= 2) ? 4 : 2;
+    const unsigned blocks = (unsigned)ceil_div64(p.N, kGatWarps);
+    gat_fast_kernel<NCK, NCV, U><<<blocks, kGatThreads, 0, st>>>(p);
+    TFGK_LAUNCH_CHECK();
+    return TFGK_OK;
+}
+
+template <int NCK>
+static int dispatch_gat_v(const GatParams &p, int ncv, cudaStream_t st) {
+    switch (ncv) {
+        case 1: return launch_gat_fast<NCK, 1>(p, st);
+        case 2: return launch_gat_fast<NCK, 2>(p, st);
+        case 3: return launch_gat_fast<NCK, 3>(p, st);
+        default: return launch_gat_fast<NCK, 4>(p, st);
+    }
+}
+
+}  // namespace tfgk
+
+using namespace tfgk;
+
+extern "C" int tfgk_segment_softmax_f32(const int64_t *rowptr, const float *score, int32_t n_seg, int32_t H,
+                                        float *out, void *stream) {
+    TFGK_CHECK_ARG(n_seg >= 0 && H >= 1, "segment_softmax: bad size (n_seg=%d, H=%d)", n_seg, H);
+    if (n_seg == 0) return TFGK_OK;
+    TFGK_CHECK_ARG(rowptr && out, "segment_softmax: null pointer");
+    segment_softmax_kernel<<<(unsigned)ceil_div64(n_seg, kGatWarps), kGatThreads, 0, as_stream(stream)>>>(
+        rowptr, score, n_seg, H, out);
+    TFGK_LAUNCH_CHECK();
+    return TFGK_OK;
+}
+
+extern "C" int tfgk_gat_fused_f32(const int64_t *rowptr, const int32_t *col,
+                                  const float *Q, int64_t ldq, const float *K, int64_t ldk, const float *V, int64_t ldv,
+                                  int32_t N, int32_t H, int32_t dqk, int32_t dv, float scale, int split_value_heads,
+                                  const float *bias, int act, float *att, int write_att, float *out, int64_t ldo,
+                                  void *stream) {
+    TFGK_CHECK_ARG(N >= 0 && H >= 1 && dqk >= 1 && dv >= 1, "gat: bad size (N=%d H=%d dqk=%d dv=%d)", N, H, dqk, dv);
+    TFGK_CHECK_ARG(act == TFGK_ACT_NONE || act == TFGK_ACT_RELU, "gat: unknown activation %d", act);
+    TFGK_CHECK_ARG(scale > 0.0f, "gat: scale must be positive");
+    if (N == 0) return TFGK_OK;
+    TFGK_CHECK_ARG(rowptr && col && Q && K && V && att && out, "gat: null pointer");
+    const int A = H * dqk, VW = H * dv;
+    const int out_w = split_value_heads ? VW : dv;
+    TFGK_CHECK_ARG(ldq >= A && ldk >= A && ldv >= VW && ldo >= out_w, "gat: leading dimension too small");
+
+    GatParams p;
+    p.rowptr = rowptr; p.col = col;
+    p.Q = Q; p.ldq = ldq; p.K = K; p.ldk = ldk; p.V = V; p.ldv = ldv;
+    p.N = N; p.H = H; p.dqk = dqk; p.dv = dv; p.scale = scale; p.split = split_value_heads;
+    p.bias = bias; p.act = act; p.att = att; p.write_att = write_att; p.out = out; p.ldo = ldo;
+    cudaStream_t st = as_stream(stream);
+
+    const bool fast = split_value_heads && is_pow2(H) && H <= kMaxHeadsFast && dqk % 4 == 0 && is_pow2(dqk / 4) &&
+                      dqk <= 128 && dv % 4 == 0 && A <= 512 && VW <= 512 && ldq % 4 == 0 && ldk % 4 == 0 &&
+                      ldv % 4 == 0 && ldo % 4 == 0 && aligned16(Q) && aligned16(K) && aligned16(V) && aligned16(out) &&
+                      (!bias || aligned16(bias));
+    if (fast) {
+        const int nck = (A + 127) / 128, ncv = (VW + 127) / 128;
+        switch (nck) {
+            case 1: return dispatch_gat_v<1>(p, ncv, st);
+            case 2: return dispatch_gat_v<2>(p, ncv, st);
+            case 3: return dispatch_gat_v<3>(p, ncv, st);
+            default: return dispatch_gat_v<4>(p, ncv, st);
+        }
+    }
+    const size_t smem = (size_t)kGatWarps * 2 * H * sizeof(float);
+    TFGK_CHECK_ARG(smem <= 48 * 1024, "gat: too many heads for the generic path (H=%d)", H);
+    gat_generic_kernel<<<(unsigned)ceil_div64(N, kGatWarps), kGatThreads, smem, st>>>(p);
+    TFGK_LAUNCH_CHECK();
+    return TFGK_OK;
+}

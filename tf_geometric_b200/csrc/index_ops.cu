@@ -1,0 +1,495 @@
+// Integer edge preprocessing, destination-sorted CSR build (stable LSD radix sort), GCN normalisation helpers.
+// Everything here is HBM-bound integer/byte work: coalesced streaming loads, shared-memory staging for the
+// radix ranks, no tensor cores.  Results are bit-exact with the numpy oracle (oracle/tfg_oracle.py).
+#include "common.cuh"
+#include <string.h>
+
+namespace tfgk {
+
+static thread_local char g_error[512] = "";
+
+char *error_buffer() { return g_error; }
+
+int set_error(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// small elementwise kernels
+// ------------------------------------------------------------------------------------------------------------
+
+__global__ void self_loops_kernel(const int32_t *__restrict__ ei, int64_t E, int32_t N, int32_t *__restrict__ out) {
+    // out is [2, E+N] row-major; ei is [2, E] row-major.
+    const int64_t Ep = E + N;
+    const int64_t total = 2 * Ep;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i >= Ep ? 1 : 0;
+        const int64_t j = i - r * Ep;
+        out[i] = j < E ? ei[r * E + j] : (int32_t)(j - E);
+    }
+}
+
+__global__ void self_loop_weights_kernel(const float *__restrict__ w, int64_t E, int32_t N, float fill,
+                                         float *__restrict__ out) {
+    const int64_t total = E + N;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = i < E ? (w ? w[i] : 1.0f) : fill;
+}
+
+__global__ void count_kernel(const int32_t *__restrict__ ids, int64_t E, int32_t N, int32_t *__restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < E; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t r = ids[i];
+        if (r >= 0 && r < N) atomicAdd(&out[r], 1);   // integer atomics: order-independent, deterministic
+    }
+}
+
+__global__ void validate_kernel(const int32_t *__restrict__ ids, int64_t E, int32_t N, int32_t *__restrict__ bad) {
+    int local = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < E; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t r = ids[i];
+        local |= (r < 0 || r >= N);
+    }
+    if (__any_sync(0xffffffffu, local) && (threadIdx.x & 31) == 0) atomicOr(bad, 1);
+}
+
+__global__ void gather_i32_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ perm, int64_t E,
+                                  int32_t *__restrict__ dst) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < E; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = src[perm[i]];
+}
+
+__global__ void permute_f32_kernel(const float *__restrict__ src, const int32_t *__restrict__ perm, int64_t E,
+                                   int32_t width, float *__restrict__ dst, bool inverse) {
+    const int64_t total = E * width;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i / width;
+        const int32_t j = (int32_t)(i - e * width);
+        const int64_t p = perm[e];
+        if (inverse) dst[p * width + j] = src[i];
+        else         dst[i] = src[p * width + j];
+    }
+}
+
+__global__ void csr_rowsum_kernel(const int64_t *__restrict__ rowptr, const float *__restrict__ w, int32_t N,
+                                  float *__restrict__ out) {
+    // one thread per row, strictly left-to-right: reproduces unsorted_segment_sum's fp32 rounding sequence
+    const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    float acc = 0.0f;
+    for (int64_t e = rowptr[r]; e < rowptr[r + 1]; ++e) acc = __fadd_rn(acc, w[e]);
+    out[r] = acc;
+}
+
+__global__ void deg_inv_kernel(const float *__restrict__ deg, int32_t N, int power, float *__restrict__ out) {
+    const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    const float d = deg[r];
+    // pow(d, -0.5) / pow(d, -1) correctly rounded; inf and nan -> 0 (gcn.py:23-29)
+    float v = power == TFGK_POW_INV_SQRT ? __frsqrt_rn(d) : __frcp_rn(d);
+    if (isinf(v) || isnan(v)) v = 0.0f;
+    out[r] = v;
+}
+
+__global__ void scale_edges_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col,
+                                   const float *__restrict__ w, int64_t E, const float *__restrict__ dl,
+                                   const float *__restrict__ dr, float *__restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < E; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = w ? w[i] : 1.0f;
+        if (dl) v = __fmul_rn(dl[row[i]], v);
+        if (dr) v = __fmul_rn(v, dr[col[i]]);
+        out[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// exclusive scan (tile scan -> scan of tile sums -> add), used for the radix histograms and rowptr
+// ------------------------------------------------------------------------------------------------------------
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(kScanThreads) scan_tile_kernel(const TIn *in, int64_t n_in, int64_t n_out,
+                                                                 TOut *out, TOut *__restrict__ tile_sums) {
+    // thread t owns items [t*kScanItems, (t+1)*kScanItems) of the tile (blocked arrangement)
+    __shared__ TOut warp_tot[kScanThreads / 32];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    TOut v[kScanItems];
+    TOut sum = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        const int64_t idx = base + i;
+        const TOut x = idx < n_in ? (TOut)in[idx] : (TOut)0;
+        v[i] = sum;      // exclusive within the thread
+        sum += x;
+    }
+    // inclusive warp scan of the thread sums
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    TOut incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const TOut y = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += y;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    TOut warp_off = 0;
+    for (int w = 0; w < warp; ++w) warp_off += warp_tot[w];
+    const TOut thread_off = warp_off + incl - sum;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        const int64_t idx = base + i;
+        if (idx < n_out) out[idx] = v[i] + thread_off;
+    }
+    if (threadIdx.x == kScanThreads - 1) tile_sums[blockIdx.x] = thread_off + sum;
+}
+
+template <typename TOut>
+__global__ void __launch_bounds__(1024) scan_sums_kernel(TOut *__restrict__ tile_sums, int64_t n_tiles) {
+    // single block: exclusive scan of the tile sums in chunks of 1024 with a running carry
+    __shared__ TOut warp_tot[32];
+    __shared__ TOut carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t base = 0; base < n_tiles; base += 1024) {
+        const int64_t idx = base + threadIdx.x;
+        const TOut x = idx < n_tiles ? tile_sums[idx] : (TOut)0;
+        TOut incl = x;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const TOut y = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += y;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        TOut warp_off = 0;
+        for (int w = 0; w < warp; ++w) warp_off += warp_tot[w];
+        const TOut carry = carry_s;
+        if (idx < n_tiles) tile_sums[idx] = carry + warp_off + incl - x;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + warp_off + incl;
+        __syncthreads();
+    }
+}
+
+template <typename TOut>
+__global__ void __launch_bounds__(kScanThreads) scan_add_kernel(TOut *__restrict__ out, int64_t n_out,
+                                                                const TOut *__restrict__ tile_sums) {
+    const TOut off = tile_sums[blockIdx.x];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile;
+    for (int i = threadIdx.x; i < kScanTile; i += kScanThreads) {
+        const int64_t idx = base + i;
+        if (idx < n_out) out[idx] += off;
+    }
+}
+
+// out[0..n_out) = exclusive scan of in[0..n_in) (elements beyond n_in count as 0; n_out may be n_in + 1)
+template <typename TIn, typename TOut>
+static int exclusive_scan(const TIn *in, int64_t n_in, int64_t n_out, TOut *out, TOut *tile_sums, cudaStream_t st) {
+    const int64_t n_tiles = ceil_div64(n_out, kScanTile);
+    if (n_tiles == 0) return TFGK_OK;
+    scan_tile_kernel<TIn, TOut><<<(unsigned)n_tiles, kScanThreads, 0, st>>>(in, n_in, n_out, out, tile_sums);
+    TFGK_LAUNCH_CHECK();
+    if (n_tiles > 1) {
+        scan_sums_kernel<TOut><<<1, 1024, 0, st>>>(tile_sums, n_tiles);
+        TFGK_LAUNCH_CHECK();
+        scan_add_kernel<TOut><<<(unsigned)n_tiles, kScanThreads, 0, st>>>(out, n_out, tile_sums);
+        TFGK_LAUNCH_CHECK();
+    }
+    return TFGK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// stable LSD radix sort of (row -> edge position), 8 bits per pass
+// ------------------------------------------------------------------------------------------------------------
+
+constexpr int kRsThreads = 256;
+constexpr int kRsWarps = kRsThreads / 32;
+constexpr int kRsItems = 16;                       // rounds per warp
+constexpr int kRsTile = kRsThreads * kRsItems;     // 4096 keys per block
+constexpr int kRadix = 256;
+
+__global__ void __launch_bounds__(kRsThreads) rs_hist_kernel(const int32_t *__restrict__ keys, int64_t E, int shift,
+                                                             uint32_t *__restrict__ hist, int nblk) {
+    __shared__ uint32_t sh[kRadix];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kRsTile;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < kRsTile; i += kRsThreads) {
+        const int64_t idx = base + i;
+        if (idx < E) atomicAdd(&sh[(keys[idx] >> shift) & (kRadix - 1)], 1u);
+    }
+    __syncthreads();
+    hist[(int64_t)threadIdx.x * nblk + blockIdx.x] = sh[threadIdx.x];   // digit-major for the global scan
+}
+
+__global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const int32_t *__restrict__ kin,
+                                                                const int32_t *__restrict__ vin, int64_t E, int shift,
+                                                                const uint32_t *__restrict__ hist_scanned, int nblk,
+                                                                int32_t *__restrict__ kout, int32_t *__restrict__ vout) {
+    __shared__ uint32_t warp_cnt[kRsWarps][kRadix];
+    __shared__ uint32_t digit_base[kRadix];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int w = 0; w < kRsWarps; ++w) warp_cnt[w][threadIdx.x] = 0;
+    digit_base[threadIdx.x] = hist_scanned[(int64_t)threadIdx.x * nblk + blockIdx.x];
+    __syncthreads();
+
+    // warp w owns the contiguous sub-tile [w*32*kRsItems, (w+1)*32*kRsItems); round i covers 32 consecutive keys.
+    const int64_t base = (int64_t)blockIdx.x * kRsTile + (int64_t)warp * (32 * kRsItems);
+    int32_t key[kRsItems];
+    uint32_t rank[kRsItems];
+#pragma unroll
+    for (int i = 0; i < kRsItems; ++i) {
+        const int64_t idx = base + i * 32 + lane;
+        const bool valid = idx < E;
+        key[i] = valid ? kin[idx] : 0;
+        const uint32_t d = (uint32_t)(key[i] >> shift) & (kRadix - 1);
+        // invalid tail lanes form their own group and never touch the counters
+        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0x100u);
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (lane == leader && valid) {
+            old = warp_cnt[warp][d];
+            warp_cnt[warp][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[i] = old + __popc(peers & ((1u << lane) - 1u));   // same-digit keys earlier in (round, lane) order
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // exclusive prefix over warps, per digit (thread t = digit t)
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < kRsWarps; ++w) {
+            const uint32_t c = warp_cnt[w][threadIdx.x];
+            warp_cnt[w][threadIdx.x] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kRsItems; ++i) {
+        const int64_t idx = base + i * 32 + lane;
+        if (idx < E) {
+            const uint32_t d = (uint32_t)(key[i] >> shift) & (kRadix - 1);
+            const uint32_t dst = digit_base[d] + warp_cnt[warp][d] + rank[i];
+            if (kout) kout[dst] = key[i];
+            vout[dst] = vin ? vin[idx] : (int32_t)idx;
+        }
+    }
+}
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct CsrWorkspace {
+    size_t off_flag, off_keys_a, off_keys_b, off_vals_b, off_hist, off_sums, off_counts, total;
+    int nblk;
+    CsrWorkspace(int64_t E, int32_t N) {
+        nblk = (int)ceil_div64(E > 0 ? E : 1, kRsTile);
+        const int64_t n_hist = (int64_t)kRadix * nblk;
+        const int64_t n_sums = ceil_div64((n_hist > (int64_t)N + 1 ? n_hist : (int64_t)N + 1), kScanTile) + 1;
+        size_t o = 0;
+        off_flag = o;   o += align_up(sizeof(int32_t));
+        off_keys_a = o; o += align_up((size_t)E * 4);
+        off_keys_b = o; o += align_up((size_t)E * 4);
+        off_vals_b = o; o += align_up((size_t)E * 4);
+        off_hist = o;   o += align_up((size_t)n_hist * 4);
+        off_sums = o;   o += align_up((size_t)n_sums * 8);
+        off_counts = o; o += align_up(((size_t)N + 1) * 4);
+        total = o;
+    }
+};
+
+static inline unsigned grid_for(int64_t n, int threads = 256) {
+    int64_t b = ceil_div64(n, threads);
+    if (b < 1) b = 1;
+    if (b > 148 * 32) b = 148 * 32;   // grid-stride loops: 32 CTAs of 256 threads per SM is plenty
+    return (unsigned)b;
+}
+
+}  // namespace tfgk
+
+using namespace tfgk;
+
+extern "C" {
+
+int tfgk_version(void) { return TFGK_ABI_VERSION; }
+
+const char *tfgk_last_error(void) { return error_buffer(); }
+
+int tfgk_device_info(int *sm_count, int *cc_major, int *cc_minor) {
+    int dev = 0;
+    TFGK_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    TFGK_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return TFGK_OK;
+}
+
+int tfgk_self_loops_i32(const int32_t *edge_index, int64_t E, int32_t N, int32_t *out, void *stream) {
+    TFGK_CHECK_ARG(E >= 0 && N >= 0, "self_loops: negative size (E=%lld, N=%d)", (long long)E, N);
+    TFGK_CHECK_ARG(E + N < (1ll << 31), "self_loops: E + N must be < 2^31");
+    if (E + N == 0) return TFGK_OK;
+    TFGK_CHECK_ARG(out != nullptr && (E == 0 || edge_index != nullptr), "self_loops: null pointer");
+    self_loops_kernel<<<grid_for(2 * (E + N)), 256, 0, as_stream(stream)>>>(edge_index, E, N, out);
+    TFGK_LAUNCH_CHECK();
+    return TFGK_OK;
+}
+
+int tfgk_self_loop_weights_f32(const float *w, int64_t E, int32_t N, float fill, float *out, void *stream) {
+    TFGK_CHECK_ARG(E >= 0 && N >= 0, "self_loop_weights: negative size");
+    if (E + N == 0) return TFGK_OK;
+    TFGK_CHECK_ARG(out != nullptr, "self_loop_weights: null output");
+    self_loop_weights_kernel<<<grid_for(E + N), 256, 0, as_stream(stream)>>>(w, E, N, fill, out);
+    TFGK_LAUNCH_CHECK();
+    return TFGK_OK;
+}
+
+int tfgk_segment_count_i32(const int32_t *ids, int64_t E, int32_t N, int32_t *out, void *stream) {
+    TFGK_CHECK_ARG(E >= 0 && N >= 0, "segment_count: negative size");
+    if (N == 0) return TFGK_OK;
+    TFGK_CHECK_ARG(out != nullptr && (E == 0 || ids != nullptr), "segment_count: null pointer");
+    TFGK_CUDA(cudaMemsetAsync(out, 0, (size_t)N * 4, as_stream(stream)));
+    if (E > 0) {
+        count_kernel<<<grid_for(E), 256, 0, as_stream(stream)>>>(ids, E, N, out);
+        TFGK_LAUNCH_CHECK();
+    }
+    return TFGK_OK;
+}
+
+int tfgk_csr_workspace_bytes(int64_t E, int32_t N, size_t *out_bytes) {
+    TFGK_CHECK_ARG(out_bytes != nullptr, "csr_workspace_bytes: null output");
+    TFGK_CHECK_ARG(E >= 0 && N >= 0 && E < (1ll << 31), "csr_workspace_bytes: need 0 <= E < 2^31, N >= 0");
+    *out_bytes = CsrWorkspace(E, N).total;
+    return TFGK_OK;
+}
+
+int tfgk_csr_build(const int32_t *row, const int32_t *col, int64_t E, int32_t N_rows, int32_t N_cols,
+                   int64_t *rowptr, int32_t *col_sorted, int32_t *perm,
+                   void *workspace, size_t workspace_bytes, void *stream) {
+    TFGK_CHECK_ARG(E >= 0 && E < (1ll << 31), "csr_build: need 0 <= E < 2^31 (got %lld)", (long long)E);
+    TFGK_CHECK_ARG(N_rows >= 0 && N_cols >= 0, "csr_build: negative node count");
+    TFGK_CHECK_ARG(rowptr != nullptr, "csr_build: null rowptr");
+    cudaStream_t st = as_stream(stream);
+    if (E == 0) {
+        TFGK_CUDA(cudaMemsetAsync(rowptr, 0, ((size_t)N_rows + 1) * 8, st));
+        return TFGK_OK;
+    }
+    TFGK_CHECK_ARG(row && col && col_sorted && perm, "csr_build: null pointer");
+    const CsrWorkspace L(E, N_rows);
+    if (workspace == nullptr || workspace_bytes < L.total)
+        return set_error(TFGK_ERR_WORKSPACE, "csr_build: workspace too small (%zu < %zu bytes)", workspace_bytes, L.total);
+    char *ws = static_cast<char *>(workspace);
+    int32_t *flag = reinterpret_cast<int32_t *>(ws + L.off_flag);
+    int32_t *keys_a = reinterpret_cast<int32_t *>(ws + L.off_keys_a);
+    int32_t *keys_b = reinterpret_cast<int32_t *>(ws + L.off_keys_b);
+    int32_t *vals_b = reinterpret_cast<int32_t *>(ws + L.off_vals_b);
+    uint32_t *hist = reinterpret_cast<uint32_t *>(ws + L.off_hist);
+    void *sums = ws + L.off_sums;
+    int32_t *counts = reinterpret_cast<int32_t *>(ws + L.off_counts);
+
+    // 1. validate ids (TF-CPU's gather / segment ops raise on out-of-range ids)
+    TFGK_CUDA(cudaMemsetAsync(flag, 0, 4, st));
+    validate_kernel<<<grid_for(E), 256, 0, st>>>(row, E, N_rows, flag);
+    TFGK_LAUNCH_CHECK();
+    validate_kernel<<<grid_for(E), 256, 0, st>>>(col, E, N_cols, flag);
+    TFGK_LAUNCH_CHECK();
+    int32_t bad = 0;
+    TFGK_CUDA(cudaMemcpyAsync(&bad, flag, 4, cudaMemcpyDeviceToHost, st));
+    TFGK_CUDA(cudaStreamSynchronize(st));
+    if (bad) return set_error(TFGK_ERR_INDEX_OUT_OF_RANGE, "csr_build: edge_index holds node ids outside [0, N)");
+
+    // 2. rowptr = exclusive scan of the per-row edge counts
+    TFGK_CUDA(cudaMemsetAsync(counts, 0, ((size_t)N_rows + 1) * 4, st));
+    count_kernel<<<grid_for(E), 256, 0, st>>>(row, E, N_rows, counts);
+    TFGK_LAUNCH_CHECK();
+    int rc = exclusive_scan<int32_t, int64_t>(counts, N_rows, (int64_t)N_rows + 1, rowptr,
+                                              reinterpret_cast<int64_t *>(sums), st);
+    if (rc != TFGK_OK) return rc;
+
+    // 3. stable LSD radix sort of (row, position); the last pass lands in `perm`
+    int bits = 1;
+    while (bits < 31 && (1ll << bits) < (int64_t)N_rows) ++bits;
+    const int passes = (bits + 7) / 8;
+    const int32_t *kin = row;
+    const int32_t *vin = nullptr;   // implicit iota
+    for (int p = 1; p <= passes; ++p) {
+        const bool to_x = ((passes - p) % 2) == 0;        // X = (keys_a, perm), Y = (keys_b, vals_b)
+        int32_t *kout = to_x ? keys_a : keys_b;
+        int32_t *vout = to_x ? perm : vals_b;
+        const int shift = (p - 1) * 8;
+        rs_hist_kernel<<<L.nblk, kRsThreads, 0, st>>>(kin, E, shift, hist, L.nblk);
+        TFGK_LAUNCH_CHECK();
+        const int64_t n_hist = (int64_t)kRadix * L.nblk;
+        rc = exclusive_scan<uint32_t, uint32_t>(hist, n_hist, n_hist, hist, reinterpret_cast<uint32_t *>(sums), st);
+        if (rc != TFGK_OK) return rc;
+        rs_scatter_kernel<<<L.nblk, kRsThreads, 0, st>>>(kin, vin, E, shift, hist, L.nblk,
+                                                         p == passes ? nullptr : kout, vout);
+        TFGK_LAUNCH_CHECK();
+        kin = kout;
+        vin = vout;
+    }
+    // 4. col_sorted = col[perm]
+    gather_i32_kernel<<<grid_for(E), 256, 0, st>>>(col, perm, E, col_sorted);
+    TFGK_LAUNCH_CHECK();
+    return TFGK_OK;
+}
+
+int tfgk_permute_f32(const float *src, const int32_t *perm, int64_t E, int32_t width, float *dst, void *stream) {
+    TFGK_CHECK_ARG(E >= 0 && width >= 1, "permute: bad size");
+    if (E == 0) return TFGK_OK;
+    TFGK_CHECK_ARG(src && perm && dst, "permute: null pointer");
+    permute_f32_kernel<<<grid_for(E * width), 256, 0, as_stream(stream)>>>(src, perm, E, width, dst, false);
+    TFGK_LAUNCH_CHECK();
+    return TFGK_OK;
+}
+
+int tfgk_unpermute_f32(const float *src, const int32_t *perm, int64_t E, int32_t width, float *dst, void *stream) {
+    TFGK_CHECK_ARG(E >= 0 && width >= 1, "unpermute: bad size");
+    if (E == 0) return TFGK_OK;
+    TFGK_CHECK_ARG(src && perm && dst, "unpermute: null pointer");
+    permute_f32_kernel<<<grid_for(E * width), 256, 0, as_stream(stream)>>>(src, perm, E, width, dst, true);
+    TFGK_LAUNCH_CHECK();
+    return TFGK_OK;
+}
+
+int tfgk_csr_rowsum_f32(const int64_t *rowptr, const float *w_csr, int32_t N, float *out, void *stream) {
+    TFGK_CHECK_ARG(N >= 0, "csr_rowsum: negative N");
+    if (N == 0) return TFGK_OK;
+    TFGK_CHECK_ARG(rowptr && out, "csr_rowsum: null pointer");
+    csr_rowsum_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, as_stream(stream)>>>(rowptr, w_csr, N, out);
+    TFGK_LAUNCH_CHECK();
+    return TFGK_OK;
+}
+
+int tfgk_deg_inv_f32(const float *deg, int32_t N, int power, float *out, void *stream) {
+    TFGK_CHECK_ARG(N >= 0, "deg_inv: negative N");
+    TFGK_CHECK_ARG(power == TFGK_POW_INV_SQRT || power == TFGK_POW_INV, "deg_inv: unknown power %d", power);
+    if (N == 0) return TFGK_OK;
+    TFGK_CHECK_ARG(deg && out, "deg_inv: null pointer");
+    deg_inv_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, as_stream(stream)>>>(deg, N, power, out);
+    TFGK_LAUNCH_CHECK();
+    return TFGK_OK;
+}
+
+int tfgk_scale_edges_f32(const int32_t *row, const int32_t *col, const float *w, int64_t E,
+                         const float *dl, const float *dr, float *out, void *stream) {
+    TFGK_CHECK_ARG(E >= 0, "scale_edges: negative E");
+    if (E == 0) return TFGK_OK;
+    TFGK_CHECK_ARG(out && (!dl || row) && (!dr || col), "scale_edges: null pointer");
+    scale_edges_kernel<<<grid_for(E), 256, 0, as_stream(stream)>>>(row, col, w, E, dl, dr, out);
+    TFGK_LAUNCH_CHECK();
+    return TFGK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,6 @@
+# coding=utf-8
+"""OOP API (the subset of tf_geometric.layers on the message-passing hot path)."""
+from .conv.gcn import GCN
+from .conv.gat import GAT
+from .conv.graph_sage import MeanGraphSage, SumGraphSage, GCNGraphSage, MeanPoolGraphSage, MaxPoolGraphSage
+from .conv.appnp import APPNP

@@ -1,0 +1,49 @@
+# coding=utf-8
+"""Minimal stand-in for tf.keras.Model as the reference's layers use it: weights are created lazily from the first
+input (Keras `build`), named exactly like the reference's `add_weight` calls so that a state dict maps 1:1
+(kernel, bias, query_kernel, key_kernel, self_kernel, neighbor_kernel, kernel_i, bias_i ...), initialised with
+glorot_uniform / zeros, and the layer is invoked as `layer(inputs, cache=..., training=...)`."""
+import math
+
+import torch
+
+
+class Layer(torch.nn.Module):
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        self.built = False
+        self._seed = kwargs.pop("seed", None)
+
+    def add_weight(self, name, shape, initializer="glorot_uniform", regularizer=None, device=None):
+        shape = [int(s) for s in shape]
+        w = torch.empty(shape, dtype=torch.float32, device=device)
+        if initializer == "zeros":
+            w.zero_()
+        elif initializer == "glorot_uniform":
+            fan_in, fan_out = (shape[0], shape[1]) if len(shape) == 2 else (shape[0], shape[0])
+            limit = math.sqrt(6.0 / (fan_in + fan_out))
+            gen = None
+            if self._seed is not None:
+                gen = torch.Generator(device="cpu")
+                gen.manual_seed(self._seed + sum(ord(c) for c in name))
+            w.copy_((torch.rand(shape, generator=gen, dtype=torch.float32) * 2.0 - 1.0) * limit)
+        else:
+            raise ValueError("unknown initializer {}".format(initializer))
+        param = torch.nn.Parameter(w, requires_grad=False)
+        self.register_parameter(name, param)
+        return param
+
+    def build(self, input_shapes, device=None):
+        raise NotImplementedError
+
+    def _maybe_build(self, inputs):
+        if not self.built:
+            x = inputs[0]
+            device = x.device if torch.is_tensor(x) and x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+            self.build([tuple(x.shape)], device=device)
+            self.built = True
+
+    def forward(self, inputs, **kwargs):
+        self._maybe_build(inputs)
+        return self.call(inputs, **kwargs)

@@ -1,0 +1,58 @@
+# coding=utf-8
+"""Multi-head graph attention with the reference's functional signature (tf_geometric/nn/conv/gat.py:13-122).
+
+The reference materialises Q[row] and K[col] ([E', A] each), builds a virtual graph of H*N nodes, runs a 5-pass
+segment_softmax over H*E' scores and finally a SpMM.  Here: three dense projections, then ONE fused kernel
+(tfgk_gat_fused_f32) that streams K and V rows once per edge.
+"""
+import torch
+
+from ... import ops, _structure
+
+
+def gat(x, edge_index,
+        query_kernel, query_bias, query_activation,
+        key_kernel, key_bias, key_activation,
+        kernel, bias=None, activation=None, num_heads=1,
+        split_value_heads=True, edge_drop_rate=0.0, training=False, cache=None, return_attention=False):
+    """
+    :param x: [num_nodes, num_features]
+    :param edge_index: [2, num_edges]; self loops are appended (never de-duplicated), reference gat.py:43
+    :param query_kernel/key_kernel: [num_features, attention_units]; query_bias/key_bias: [attention_units]
+    :param kernel: [num_features, units] (or [num_features, units * num_heads] when split_value_heads=False)
+    :param num_heads: heads; attention_units (and units when splitting) must be divisible by it
+    :param split_value_heads: True: heads own slices of V and are concatenated; False: every head sees a full V and
+        the head outputs are averaged
+    :param cache: optional dict (e.g. graph.cache) memoising the self-looped CSR; an extension of the reference API
+    :return: [num_nodes, units]
+    """
+    if training and edge_drop_rate > 0.0:
+        raise NotImplementedError("attention dropout (TF RNG stream) is outside the forward hot path of this backend")
+    edge_index = ops.as_device(edge_index, torch.int32)
+    dev = edge_index.device
+    x = ops.as_device(x, torch.float32, device=dev)
+    num_nodes = x.shape[0]
+    csr, _ = _structure.csr_for_edge_index(edge_index, num_nodes, add_self_loop=True, cache=cache)
+
+    q_act, q_left = ops.activation_code(query_activation)
+    k_act, k_left = ops.activation_code(key_activation)
+    Q = ops.gemm(x, ops.as_device(query_kernel, torch.float32, device=dev),
+                 bias=ops.as_device(query_bias, torch.float32, device=dev), act=q_act)
+    if q_left is not None:
+        Q = q_left(Q)
+    K = ops.gemm(x, ops.as_device(key_kernel, torch.float32, device=dev),
+                 bias=ops.as_device(key_bias, torch.float32, device=dev), act=k_act)
+    if k_left is not None:
+        K = k_left(K)
+    V = ops.gemm(x, ops.as_device(kernel, torch.float32, device=dev))
+
+    act_code, leftover = ops.activation_code(activation)
+    bias = None if bias is None else ops.as_device(bias, torch.float32, device=dev)
+    res = ops.gat_fused(csr, Q, K, V, num_heads, split_value_heads=split_value_heads, bias=bias, act=act_code,
+                        return_attention=return_attention)
+    h, att = res if return_attention else (res, None)
+    if leftover is not None:
+        h = leftover(h)
+    if return_attention:
+        return h, ops.permute(att, csr.perm, inverse=True)     # [E', H] in edge_index-with-self-loops order
+    return h

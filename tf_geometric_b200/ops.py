@@ -1,0 +1,278 @@
+# coding=utf-8
+"""Typed wrappers over the C ABI (include/tfgk.h): torch CUDA tensors in, torch CUDA tensors out.
+
+Nothing here computes with PyTorch: tensors are allocated with torch.empty and handed to libtfgk.so by pointer on
+the current CUDA stream.  Every function requires CUDA tensors and raises otherwise (no CPU path).
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _ffi
+from ._ffi import (REDUCE_SUM, REDUCE_MEAN, REDUCE_MAX, ACT_NONE, ACT_RELU, POW_INV_SQRT, POW_INV)  # noqa: F401
+
+_REDUCE_CODES = {"sum": REDUCE_SUM, "mean": REDUCE_MEAN, "max": REDUCE_MAX}
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("tf_geometric_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback")
+
+
+def as_device(x, dtype=None, device=None):
+    """numpy / list / torch (any device) -> contiguous CUDA tensor of `dtype` (reference casting rules are applied
+    by the callers: int32 edge_index, float32 weights/features; data/graph.py:58-86)."""
+    if x is None:
+        return None
+    _require_cuda()
+    if not torch.is_tensor(x):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    if device is None:
+        device = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    if dtype is not None and x.dtype != dtype:
+        x = x.to(dtype)
+    if x.device != device:
+        x = x.to(device, non_blocking=True)
+    return x.contiguous()
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _check(t, dtype, name):
+    if not (torch.is_tensor(t) and t.is_cuda):
+        raise TypeError("{} must be a CUDA tensor (got {})".format(name, type(t)))
+    if t.dtype != dtype:
+        raise TypeError("{} must be {} (got {})".format(name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("{} must be contiguous".format(name))
+
+
+def _row_major_2d(t, name):
+    """Accept [N, D] tensors whose rows are contiguous (stride(1) == 1); returns the leading dimension."""
+    if t.dim() != 2:
+        raise ValueError("{} must be 2-D".format(name))
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        raise ValueError("{} rows must be contiguous".format(name))
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+
+
+class CSR(object):
+    """Destination-sorted CSR of a COO edge list (stable by row): rowptr int64 [n_rows+1], col int32 [nnz],
+    perm int32 [nnz] (position of each CSR slot in the original edge list)."""
+
+    __slots__ = ("rowptr", "col", "perm", "n_rows", "n_cols", "nnz")
+
+    def __init__(self, rowptr, col, perm, n_rows, n_cols):
+        self.rowptr, self.col, self.perm = rowptr, col, perm
+        self.n_rows, self.n_cols = int(n_rows), int(n_cols)
+        self.nnz = int(col.shape[0])
+
+    def degree_i64(self):
+        return self.rowptr[1:] - self.rowptr[:-1]
+
+
+# ---- integer edge preprocessing ---------------------------------------------------------------------------------
+
+def self_loops(edge_index, num_nodes):
+    _check(edge_index, torch.int32, "edge_index")
+    E = edge_index.shape[1] if edge_index.dim() == 2 else 0
+    out = torch.empty((2, E + num_nodes), dtype=torch.int32, device=edge_index.device)
+    _ffi.call("tfgk_self_loops_i32", _p(edge_index), E, num_nodes, _p(out), _stream(out))
+    return out
+
+
+def self_loop_weights(edge_weight, num_edges, num_nodes, fill_weight, device):
+    if edge_weight is not None:
+        _check(edge_weight, torch.float32, "edge_weight")
+    out = torch.empty((num_edges + num_nodes,), dtype=torch.float32, device=device)
+    _ffi.call("tfgk_self_loop_weights_f32", _p(edge_weight), num_edges, num_nodes, float(fill_weight), _p(out),
+              _stream(out))
+    return out
+
+
+def segment_count(ids, num_segments):
+    _check(ids, torch.int32, "index")
+    out = torch.empty((num_segments,), dtype=torch.int32, device=ids.device)
+    _ffi.call("tfgk_segment_count_i32", _p(ids), ids.numel(), num_segments, _p(out), _stream(out))
+    return out
+
+
+def csr_build(row, col, n_rows, n_cols=None):
+    _check(row, torch.int32, "row")
+    _check(col, torch.int32, "col")
+    n_cols = n_rows if n_cols is None else n_cols
+    E = row.numel()
+    dev = row.device
+    need = ctypes.c_size_t()
+    _ffi.call("tfgk_csr_workspace_bytes", E, n_rows, ctypes.byref(need))
+    ws = torch.empty((max(need.value, 1),), dtype=torch.uint8, device=dev)
+    rowptr = torch.empty((n_rows + 1,), dtype=torch.int64, device=dev)
+    col_sorted = torch.empty((E,), dtype=torch.int32, device=dev)
+    perm = torch.empty((E,), dtype=torch.int32, device=dev)
+    _ffi.call("tfgk_csr_build", _p(row), _p(col), E, n_rows, n_cols, _p(rowptr), _p(col_sorted), _p(perm),
+              _p(ws), need.value, _stream(row))
+    return CSR(rowptr, col_sorted, perm, n_rows, n_cols)
+
+
+def permute(src, perm, inverse=False):
+    """COO-order values -> CSR order (dst[i] = src[perm[i]]), or back with inverse=True.  src: [E] or [E, W]."""
+    _check(src, torch.float32, "src")
+    _check(perm, torch.int32, "perm")
+    width = 1 if src.dim() == 1 else src.shape[1]
+    dst = torch.empty_like(src)
+    _ffi.call("tfgk_unpermute_f32" if inverse else "tfgk_permute_f32", _p(src), _p(perm), perm.numel(), width, _p(dst),
+              _stream(src))
+    return dst
+
+
+def csr_rowsum(csr, w_csr):
+    _check(w_csr, torch.float32, "w_csr")
+    out = torch.empty((csr.n_rows,), dtype=torch.float32, device=w_csr.device)
+    _ffi.call("tfgk_csr_rowsum_f32", _p(csr.rowptr), _p(w_csr), csr.n_rows, _p(out), _stream(out))
+    return out
+
+
+def deg_inv(deg, power):
+    _check(deg, torch.float32, "deg")
+    out = torch.empty_like(deg)
+    _ffi.call("tfgk_deg_inv_f32", _p(deg), deg.numel(), power, _p(out), _stream(out))
+    return out
+
+
+def scale_edges(row, col, w, dl=None, dr=None):
+    _check(w, torch.float32, "value")
+    out = torch.empty_like(w)
+    _ffi.call("tfgk_scale_edges_f32", _p(row), _p(col), _p(w), w.numel(), _p(dl), _p(dr), _p(out), _stream(out))
+    return out
+
+
+# ---- K1 ----------------------------------------------------------------------------------------------------------
+
+def spmm(csr, w_csr, h, reduce="sum", alpha=1.0, addend=None, beta=0.0, bias=None, act=ACT_NONE, out=None, col=None):
+    """out = epilogue(REDUCE_{e in row} w[e] * h[col[e]]); see tfgk_spmm_f32.  `col` overrides csr.col (used by the
+    generic reducers, which gather message rows through csr.perm)."""
+    if h.dtype != torch.float32 or not h.is_cuda:
+        raise TypeError("h must be a float32 CUDA tensor")
+    ldh = _row_major_2d(h, "h")
+    n_dst, D = csr.n_rows, h.shape[1]
+    if out is None:
+        out = torch.empty((n_dst, D), dtype=torch.float32, device=h.device)
+    ldo = _row_major_2d(out, "out")
+    lda = 0
+    if addend is not None:
+        lda = _row_major_2d(addend, "addend")
+    if w_csr is not None:
+        _check(w_csr, torch.float32, "w_csr")
+    if bias is not None:
+        _check(bias, torch.float32, "bias")
+    code = _REDUCE_CODES[reduce] if isinstance(reduce, str) else reduce
+    _ffi.call("tfgk_spmm_f32", _p(csr.rowptr), _p(csr.col if col is None else col), _p(w_csr), _p(h), ldh, n_dst, D,
+              code, float(alpha), _p(addend), lda, float(beta), _p(bias), act, _p(out), ldo, _stream(h))
+    return out
+
+
+# ---- K3 ----------------------------------------------------------------------------------------------------------
+
+def segment_softmax_csr(csr, score_csr):
+    """score_csr: [E] or [E, H] in CSR order."""
+    _check(score_csr, torch.float32, "score")
+    H = 1 if score_csr.dim() == 1 else score_csr.shape[1]
+    out = torch.empty_like(score_csr)
+    _ffi.call("tfgk_segment_softmax_f32", _p(csr.rowptr), _p(score_csr), csr.n_rows, H, _p(out), _stream(out))
+    return out
+
+
+def gat_fused(csr, Q, K, V, num_heads, split_value_heads=True, bias=None, act=ACT_NONE, return_attention=False,
+              att_buffer=None, out=None):
+    for t, n in ((Q, "Q"), (K, "K"), (V, "V")):
+        if not (t.is_cuda and t.dtype == torch.float32):
+            raise TypeError("{} must be a float32 CUDA tensor".format(n))
+    N = csr.n_rows
+    H = int(num_heads)
+    A, VW = Q.shape[1], V.shape[1]
+    if A % H or VW % H or K.shape[1] != A:
+        raise ValueError("attention units ({}) and value units ({}) must be divisible by num_heads ({})".format(A, VW, H))
+    dqk, dv = A // H, VW // H
+    out_w = VW if split_value_heads else dv
+    if out is None:
+        out = torch.empty((N, out_w), dtype=torch.float32, device=Q.device)
+    att = att_buffer
+    if att is None or att.numel() < csr.nnz * H:
+        att = torch.empty((csr.nnz, H), dtype=torch.float32, device=Q.device)
+    if bias is not None:
+        _check(bias, torch.float32, "bias")
+    # gat.py:78  scale = sqrt(cast(shape(Q_)[-1], float32))
+    scale = float(np.sqrt(np.float32(dqk)))
+    _ffi.call("tfgk_gat_fused_f32", _p(csr.rowptr), _p(csr.col), _p(Q), _row_major_2d(Q, "Q"), _p(K),
+              _row_major_2d(K, "K"), _p(V), _row_major_2d(V, "V"), N, H, dqk, dv, scale, 1 if split_value_heads else 0,
+              _p(bias), act, _p(att), 1 if return_attention else 0, _p(out), _row_major_2d(out, "out"), _stream(Q))
+    if return_attention:
+        return out, att[:csr.nnz]
+    return out
+
+
+# ---- K4 ----------------------------------------------------------------------------------------------------------
+
+def gemm(a, b, bias=None, act=ACT_NONE, trans_a=False, trans_b=False, beta=0.0, out=None):
+    """act(op(a) @ op(b) + bias + beta*out) in fp32."""
+    for t, n in ((a, "a"), (b, "b")):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2):
+            raise TypeError("{} must be a 2-D float32 CUDA tensor".format(n))
+    M = a.shape[1] if trans_a else a.shape[0]
+    Ka = a.shape[0] if trans_a else a.shape[1]
+    Kb = b.shape[1] if trans_b else b.shape[0]
+    N = b.shape[0] if trans_b else b.shape[1]
+    if Ka != Kb:
+        raise ValueError("gemm: inner dimensions differ ({} vs {})".format(Ka, Kb))
+    if out is None:
+        if beta != 0.0:
+            raise ValueError("gemm: beta != 0 needs `out`")
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    if bias is not None:
+        _check(bias, torch.float32, "bias")
+    need = ctypes.c_size_t()
+    _ffi.call("tfgk_gemm_workspace_bytes", M, N, Ka, ctypes.byref(need))
+    ws = torch.empty((need.value,), dtype=torch.uint8, device=a.device) if need.value else None
+    _ffi.call("tfgk_gemm_f32", _p(a), _row_major_2d(a, "a"), int(trans_a), _p(b), _row_major_2d(b, "b"), int(trans_b),
+              _p(bias), act, float(beta), M, N, Ka, _p(out), _row_major_2d(out, "out"), _p(ws), need.value, _stream(a))
+    return out
+
+
+def l2_normalize(x, out=None):
+    if out is None:
+        out = torch.empty_like(x)
+    _ffi.call("tfgk_l2_normalize_f32", _p(x), _row_major_2d(x, "x"), x.shape[0], x.shape[1], _p(out),
+              _row_major_2d(out, "out"), _stream(x))
+    return out
+
+
+def device_info():
+    sm, major, minor = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _ffi.call("tfgk_device_info", ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor))
+    return {"sm_count": sm.value, "cc": (major.value, minor.value)}
+
+
+def activation_code(activation):
+    """Map an activation callable to a fused epilogue code; returns (code, leftover_callable)."""
+    if activation is None:
+        return ACT_NONE, None
+    if activation in (torch.relu, torch.nn.functional.relu) or getattr(activation, "_tfgk_act", None) == "relu" \
+            or isinstance(activation, torch.nn.ReLU):
+        return ACT_RELU, None
+    return ACT_NONE, activation
+
+
+def relu(x):
+    """Stand-in for tf.nn.relu in the reference's layer defaults (layers/conv/gat.py:15-16, graph_sage.py:13)."""
+    return torch.relu(x)
+
+
+relu._tfgk_act = "relu"
