@@ -1,0 +1,130 @@
+# coding=utf-8
+"""TEST DOUBLE for the kernel layer: replaces the thin wrappers of tf_geometric_b200.ops with the CPU oracle so the
+HOST logic (argument plumbing, caching, quirks, layer wiring) can be exercised in a GPU-less container.
+It lives under tests/ and is injected with monkeypatch; the product has no such path."""
+import numpy as np
+import torch
+
+from oracle import tfg_oracle as o
+from oracle import c_oracle
+
+
+def _np(t):
+    return None if t is None else t.detach().cpu().numpy()
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def install(monkeypatch):
+    from tf_geometric_b200 import ops, _structure
+    _structure.clear()
+    cpu = torch.device("cpu")
+    monkeypatch.setattr(ops, "_require_cuda", lambda: None)
+    monkeypatch.setattr(ops, "default_device", lambda: cpu)
+
+    def as_device(x, dtype=None, device=None):
+        if x is None:
+            return None
+        if not torch.is_tensor(x):
+            x = torch.from_numpy(np.ascontiguousarray(x))
+        if dtype is not None and x.dtype != dtype:
+            x = x.to(dtype)
+        return x.contiguous()
+    monkeypatch.setattr(ops, "as_device", as_device)
+
+    def self_loops(edge_index, num_nodes):
+        return _t(o.add_self_loop_edge(_np(edge_index), num_nodes)[0])
+
+    def self_loop_weights(w, num_edges, num_nodes, fill, device):
+        base = np.ones(num_edges, np.float32) if w is None else _np(w)
+        return _t(np.concatenate([base, np.full(num_nodes, fill, np.float32)]))
+
+    def segment_count(ids, n):
+        return _t(np.bincount(_np(ids), minlength=n).astype(np.int32))
+
+    def csr_build(row, col, n_rows, n_cols=None):
+        rowptr, cs, perm = c_oracle.csr_build(_np(row), _np(col), n_rows)
+        return ops.CSR(_t(rowptr), _t(cs), _t(perm), n_rows, n_rows if n_cols is None else n_cols)
+
+    def permute(src, perm, inverse=False):
+        s, p = _np(src), _np(perm)
+        if inverse:
+            out = np.empty_like(s)
+            out[p] = s
+            return _t(out)
+        return _t(s[p])
+
+    def csr_rowsum(csr, w):
+        ids = np.repeat(np.arange(csr.n_rows), np.diff(_np(csr.rowptr)))
+        return _t(o.unsorted_segment_sum(_np(w), ids, csr.n_rows))
+
+    def deg_inv(deg, power):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return _t(o._remove_inf_and_nan(np.power(_np(deg), np.float32(-0.5 if power == ops.POW_INV_SQRT else -1))))
+
+    def scale_edges(row, col, w, dl=None, dr=None):
+        v = _np(w)
+        if dl is not None:
+            v = _np(dl)[_np(row)] * v
+        if dr is not None:
+            v = v * _np(dr)[_np(col)]
+        return _t(v.astype(np.float32))
+
+    def spmm(csr, w_csr, h, reduce="sum", alpha=1.0, addend=None, beta=0.0, bias=None, act=0, out=None, col=None):
+        ids = np.repeat(np.arange(csr.n_rows), np.diff(_np(csr.rowptr))).astype(np.int32)
+        cols = _np(csr.col if col is None else col)
+        agg = c_oracle.aggregate(ids, cols, _np(w_csr), _np(h), csr.n_rows, reduce if isinstance(reduce, str)
+                                 else ["sum", "mean", "max"][reduce])
+        if addend is not None:
+            agg = agg * np.float32(alpha) + _np(addend) * np.float32(beta)
+        elif alpha != 1.0:
+            agg = agg * np.float32(alpha)
+        if bias is not None:
+            agg = agg + _np(bias)
+        if act == ops.ACT_RELU:
+            agg = np.maximum(agg, 0)
+        res = _t(agg.astype(np.float32))
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+
+    def segment_softmax_csr(csr, score):
+        ids = np.repeat(np.arange(csr.n_rows), np.diff(_np(csr.rowptr))).astype(np.int32)
+        return _t(c_oracle.segment_softmax(_np(score), ids, csr.n_rows))
+
+    def gat_fused(csr, Q, K, V, num_heads, split_value_heads=True, bias=None, act=0, return_attention=False,
+                  att_buffer=None, out=None):
+        ids = np.repeat(np.arange(csr.n_rows), np.diff(_np(csr.rowptr))).astype(np.int32)
+        res, att = c_oracle.gat_core(ids, _np(csr.col), _np(Q), _np(K), _np(V), num_heads, split_value_heads, True)
+        if bias is not None:
+            res = res + _np(bias)
+        if act == ops.ACT_RELU:
+            res = np.maximum(res, 0)
+        return (_t(res), _t(att)) if return_attention else _t(res)
+
+    def gemm(a, b, bias=None, act=0, trans_a=False, trans_b=False, beta=0.0, out=None):
+        an, bn = _np(a), _np(b)
+        r = (an.T if trans_a else an) @ (bn.T if trans_b else bn)
+        if beta != 0.0:
+            r = r + np.float32(beta) * _np(out)
+        if bias is not None:
+            r = r + _np(bias)
+        if act == ops.ACT_RELU:
+            r = np.maximum(r, 0)
+        res = _t(r.astype(np.float32))
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+
+    def l2_normalize(x, out=None):
+        return _t(o.l2_normalize(_np(x)))
+
+    for name, fn in dict(self_loops=self_loops, self_loop_weights=self_loop_weights, segment_count=segment_count,
+                         csr_build=csr_build, permute=permute, csr_rowsum=csr_rowsum, deg_inv=deg_inv,
+                         scale_edges=scale_edges, spmm=spmm, segment_softmax_csr=segment_softmax_csr,
+                         gat_fused=gat_fused, gemm=gemm, l2_normalize=l2_normalize).items():
+        monkeypatch.setattr(ops, name, fn)

@@ -1,0 +1,158 @@
+# coding=utf-8
+"""GPU parity for the callers of the hot path: gcn / graph_sage / appnp (functional + layer API) and the dense GEMM."""
+import numpy as np
+import pytest
+import torch
+
+import tf_geometric_b200 as tfg
+from tf_geometric_b200 import ops
+from oracle import tfg_oracle as o
+from conftest import random_graph, assert_close, glorot
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a, dtype=None):
+    return ops.as_device(a, dtype)
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("m,n,k,ta,tb", [
+    (1, 1, 1, False, False), (100, 128, 100, False, False), (257, 16, 1433, False, False), (300, 7, 16, False, False),
+    (513, 130, 77, False, False), (64, 200, 300, True, False), (64, 200, 300, False, True), (90, 33, 65, True, True),
+    (100, 128, 50000, True, False),      # weight-gradient shape -> split-K
+    (2000, 256, 128, False, False)])
+def test_gemm(m, n, k, ta, tb):
+    rs = np.random.RandomState(m + n + k)
+    a = rs.randn(*((k, m) if ta else (m, k))).astype(np.float32)
+    b = rs.randn(*((n, k) if tb else (k, n))).astype(np.float32)
+    bias = rs.randn(n).astype(np.float32)
+    want = (a.T if ta else a).astype(np.float64) @ (b.T if tb else b).astype(np.float64)
+    got = ops.gemm(dev(a), dev(b), trans_a=ta, trans_b=tb)
+    assert_close(host(got), want, rtol=1e-4, atol_scale=2e-6, what="gemm")
+    got = ops.gemm(dev(a), dev(b), bias=dev(bias), act=ops.ACT_RELU, trans_a=ta, trans_b=tb)
+    assert_close(host(got), np.maximum(want + bias, 0), rtol=1e-4, atol_scale=2e-6, what="gemm+bias+relu")
+    c0 = rs.randn(m, n).astype(np.float32)
+    out = dev(c0.copy())
+    ops.gemm(dev(a), dev(b), trans_a=ta, trans_b=tb, beta=1.0, out=out)
+    assert_close(host(out), want + c0, rtol=1e-4, atol_scale=2e-6, what="gemm beta")
+
+
+@pytest.mark.parametrize("norm,loop,sym,renorm,improved,act", [
+    ("both", True, True, True, False, "relu"), ("both", True, True, False, False, None),
+    ("both", True, False, True, True, "relu"), ("left", True, False, True, False, None),
+    ("right", False, False, True, False, "relu")])
+def test_gcn_functional(norm, loop, sym, renorm, improved, act):
+    rs = np.random.RandomState(1)
+    n, f, u = 2500, 60, 32
+    ei = random_graph(n, 30000, seed=2, symmetric=sym, isolated=4)
+    w = (rs.rand(ei.shape[1]) + .1).astype(np.float32)
+    x = rs.randn(n, f).astype(np.float32)
+    k, b = glorot(rs, f, u), rs.randn(u).astype(np.float32)
+    want = o.gcn(x, o.SparseMatrix(ei, w, [n, n]), k, b, o.relu if act else None, norm, loop, sym, renorm, improved)
+    got = tfg.nn.gcn(dev(x), tfg.SparseMatrix(ei, w, [n, n]), dev(k), dev(b), tfg.nn.relu if act else None,
+                     norm=norm, add_self_loop=loop, sym=sym, renorm=renorm, improved=improved)
+    assert_close(host(got), want, what="gcn")
+    # kernel=None propagates x itself; a non-relu activation goes through the generic callable route
+    want = o.gcn(x, o.SparseMatrix(ei, w, [n, n]), None, None, np.tanh, norm, loop, sym, renorm, improved)
+    got = tfg.nn.gcn(dev(x), tfg.SparseMatrix(ei, w, [n, n]), None, None, torch.tanh, norm=norm, add_self_loop=loop,
+                     sym=sym, renorm=renorm, improved=improved)
+    assert_close(host(got), want, what="gcn no kernel tanh")
+
+
+def test_gcn_two_layer_cora_shaped_model_with_cache():
+    """BASELINE config 1 wiring (demo/demo_gcn.py:18-47): GCN(16, relu) -> GCN(7), cache pre-built, numpy inputs."""
+    rs = np.random.RandomState(0)
+    n, f = 2708, 1433
+    pairs = rs.randint(0, n, (2, 5278)).astype(np.int32)
+    x = (rs.rand(n, f) < 0.0126).astype(np.float32)
+    x = x / np.maximum(x.sum(1, keepdims=True), 1)
+    g = tfg.Graph(x, pairs).to_directed()
+    want_ei, _ = o.convert_edge_to_directed(pairs)
+    np.testing.assert_array_equal(np.asarray(g.edge_index), want_ei)
+    gd = g.to_device()
+    l0, l1 = tfg.layers.GCN(16, activation=tfg.nn.relu, seed=3), tfg.layers.GCN(7, seed=4)
+    l0.build_cache_for_graph(gd)
+    h = l0([gd.x, gd.edge_index, gd.edge_weight], cache=gd.cache)
+    logits = l1([h, gd.edge_index, gd.edge_weight], cache=gd.cache)
+    assert len(gd.cache) == 1
+    k0, b0, k1, b1 = (host(p) for p in (l0.kernel, l0.bias, l1.kernel, l1.bias))
+    adj = o.SparseMatrix(want_ei, np.ones(want_ei.shape[1], np.float32), [n, n])
+    want = o.gcn(o.gcn(x, adj, k0, b0, o.relu), adj, k1, b1)
+    assert_close(host(logits), want, what="2-layer GCN")
+    assert sorted(k for k, _ in l0.named_parameters()) == ["bias", "kernel"]
+
+
+@pytest.mark.parametrize("concat", [True, False])
+@pytest.mark.parametrize("weighted", [True, False])
+@pytest.mark.parametrize("kind", ["mean", "sum"])
+def test_plain_graph_sage(kind, weighted, concat):
+    rs = np.random.RandomState(5)
+    n, f, u = 2000, 100, 32
+    ei = random_graph(n, 25000, seed=7, isolated=5)
+    w = rs.rand(ei.shape[1]).astype(np.float32) if weighted else None
+    x = rs.randn(n, f).astype(np.float32)
+    ws, wn = glorot(rs, f, u), glorot(rs, f, u)
+    b = rs.randn(2 * u if concat else u).astype(np.float32)
+    fo = {"mean": o.mean_graph_sage, "sum": o.sum_graph_sage}[kind]
+    fg = {"mean": tfg.nn.mean_graph_sage, "sum": tfg.nn.sum_graph_sage}[kind]
+    want = fo(x, ei, w, ws, wn, b, o.relu, concat=concat, normalize=True)
+    got = fg(dev(x), dev(ei), dev(w), dev(ws), dev(wn), dev(b), tfg.nn.relu, concat=concat, normalize=True)
+    assert_close(host(got), want, what=kind + "_graph_sage")
+
+
+def test_pool_and_gcn_graph_sage_and_layers():
+    rs = np.random.RandomState(6)
+    n, f, units = 1500, 40, 32
+    ei = random_graph(n, 20000, seed=8, symmetric=True)          # every node has in-edges: max-pool stays finite
+    w = rs.rand(ei.shape[1]).astype(np.float32)
+    x = rs.randn(n, f).astype(np.float32)
+    for cls, fo in ((tfg.layers.MeanPoolGraphSage, o.mean_pool_graph_sage), (tfg.layers.MaxPoolGraphSage, o.max_pool_graph_sage)):
+        layer = cls(units, seed=11)
+        out = layer([dev(x), dev(ei), dev(w)])
+        p = {k: host(v) for k, v in layer.named_parameters()}
+        mk, mb, nk = layer._names
+        want = fo(x, ei, w, p["self_kernel"], p[mk], p[nk], p[mb], p["bias"], o.relu)
+        assert_close(host(out), want, what=cls.__name__)
+        with pytest.raises(TypeError):
+            layer([dev(x), dev(ei)])                               # edge_weight=None crashes in the reference too
+    assert sorted(tfg.layers.MaxPoolGraphSage._names) == ["mlp_bias", "mlp_kernel", "neighs_kernel"]
+    layer = tfg.layers.GCNGraphSage(units, seed=12)
+    p_out = layer([dev(x), dev(ei), dev(w)])
+    p = {k: host(v) for k, v in layer.named_parameters()}
+    assert_close(host(p_out), o.gcn_graph_sage(x, ei, w, p["kernel"], p["bias"], o.relu), what="GCNGraphSage")
+    assert_close(host(layer([dev(x), dev(ei), dev(w)], cache={"warm": 1})),
+                 o.gcn_graph_sage(x, ei, w, p["kernel"], p["bias"], o.relu, cache={"warm": 1}), what="GCNGraphSage cache quirk")
+    layer = tfg.layers.MeanGraphSage(units, seed=13)
+    out = layer([dev(x), dev(ei)])
+    p = {k: host(v) for k, v in layer.named_parameters()}
+    assert_close(host(out), o.mean_graph_sage(x, ei, None, p["self_kernel"], p["neighbor_kernel"], p["bias"], o.relu),
+                 what="MeanGraphSage")
+    with pytest.raises(Exception):
+        tfg.layers.SumGraphSage(33)
+
+
+@pytest.mark.parametrize("k,alpha", [(10, 0.1), (1, 0.5), (0, 0.1)])
+def test_appnp(k, alpha):
+    rs = np.random.RandomState(8)
+    n, f = 2000, 50
+    ei = random_graph(n, 24000, seed=9, symmetric=True)
+    w = (rs.rand(ei.shape[1]) + .2).astype(np.float32)
+    x = rs.randn(n, f).astype(np.float32)
+    kernels = [glorot(rs, f, 64), glorot(rs, 64, 7)]
+    biases = [rs.randn(64).astype(np.float32), rs.randn(7).astype(np.float32)]
+    want = o.appnp(x, ei, w, kernels, biases, o.relu, o.relu, k=k, alpha=alpha)
+    got = tfg.nn.appnp(dev(x), dev(ei), dev(w), [dev(a) for a in kernels], [dev(a) for a in biases], tfg.nn.relu,
+                       tfg.nn.relu, k=k, alpha=alpha)
+    assert_close(host(got), want, what="appnp")
+    layer = tfg.layers.APPNP([64, 7], k=k, alpha=alpha, seed=2)
+    g = tfg.Graph(x, ei, edge_weight=w).to_device()
+    out = layer([g.x, g.edge_index, g.edge_weight], cache=g.cache)
+    p = {kk: host(v) for kk, v in layer.named_parameters()}
+    assert sorted(p) == ["bias_0", "bias_1", "kernel_0", "kernel_1"]
+    want = o.appnp(x, ei, w, [p["kernel_0"], p["kernel_1"]], [p["bias_0"], p["bias_1"]], o.relu, None, k=k, alpha=alpha)
+    assert_close(host(out), want, what="APPNP layer")
+    assert "gcn_normed_adj_both_True_True_True_False" in g.cache

@@ -1,0 +1,88 @@
+# coding=utf-8
+"""Host-side logic of the reference-facing API, exercised on CPU through a test double of the kernel layer
+(tests/fake_backend.py): argument plumbing, graph.cache, quirks, layer wiring, weight names, casting rules.
+The SAME test bodies run against the real kernels in the test_gpu_*.py modules on the B200."""
+import numpy as np
+import pytest
+import torch
+
+import tf_geometric_b200 as tfg
+import fake_backend
+import test_gpu_index
+import test_gpu_spmm
+import test_gpu_gat
+import test_gpu_models
+
+
+@pytest.fixture
+def fake(monkeypatch):
+    fake_backend.install(monkeypatch)
+    yield
+    from tf_geometric_b200 import _structure
+    _structure.clear()
+
+
+def test_graph_casting_rules():
+    """data/graph.py:58-91: list/ndarray edge_index -> int32, weights -> float32, float64 features -> float32."""
+    g = tfg.Graph(np.random.randn(5, 3), [[0, 0, 1, 3], [1, 2, 2, 1]])
+    assert g.x.dtype == np.float32 and g.edge_index.dtype == np.int32 and g.edge_weight.dtype == np.float32
+    assert g.edge_weight.tolist() == [1, 1, 1, 1] and g.num_nodes == 5 and g.num_edges == 4 and g.num_features == 3
+    assert g.cache == {} and "x => (5, 3)" in str(g)
+    g = tfg.Graph(np.zeros((2, 1), np.float16), np.array([[0], [1]], np.int64), edge_weight=[2])
+    assert g.x.dtype == np.float16 and g.edge_index.dtype == np.int32 and g.edge_weight.dtype == np.float32
+    g = tfg.Graph(torch.zeros(3, 2, dtype=torch.float64), torch.tensor([[0, 1], [1, 2]]))
+    assert g.x.dtype == torch.float32 and g.edge_index.dtype == torch.int32 and torch.is_tensor(g.edge_weight)
+    assert tfg.Graph(np.zeros((3, 2)), np.zeros((2, 0))).num_edges == 0
+
+
+def test_compute_num_or_size_splits():
+    f = tfg.utils.compute_num_or_size_splits
+    assert f(128, None) is None and f(128, 1) is None and f(128, 4) == 4
+    assert f(10, 3) == [4, 4, 2]
+    with pytest.raises(Exception):
+        f(10, 4)      # ceil(10/4)=3 -> [3,3,3,1] has 4 parts: valid; use a truly invalid one below
+        f(5, 4)
+
+
+def test_cache_key_format():
+    assert tfg.nn.compute_cache_key("both", True, True, True, False) == "gcn_normed_adj_both_True_True_True_False"
+
+
+# ---- the GPU test bodies, replayed on the fake backend -------------------------------------------------------------
+
+def test_index_paths(fake):
+    test_gpu_index.test_add_self_loop_edge(1000, 20000)
+    test_gpu_index.test_segment_count(6, 9)
+    test_gpu_index.test_gcn_norm_derived_kat_and_cache()
+    test_gpu_index.test_to_directed_and_merge_match_oracle()
+    for args in (("both", True, True, True, False), ("both", True, True, False, False), ("both", True, False, True, True),
+                 ("left", True, False, True, False), ("right", True, False, True, False)):
+        test_gpu_index.test_gcn_norm_adj_index_bit_exact_values_close(*args)
+
+
+def test_aggregate_paths(fake):
+    test_gpu_spmm.test_aggregate_sum_bit_exact_all_widths(7, True)
+    test_gpu_spmm.test_aggregate_sum_bit_exact_all_widths(16, False)
+    test_gpu_spmm.test_aggregate_mean_max(7, "mean")
+    test_gpu_spmm.test_aggregate_mean_max(16, "max")
+    test_gpu_spmm.test_aggregate_defaults_sum_updater_and_empty_edge_index()
+    test_gpu_spmm.test_generic_mapper_route_and_standalone_reducers()
+
+
+def test_gat_paths(fake):
+    test_gpu_gat.test_segment_softmax(None)
+    test_gpu_gat.test_segment_softmax(3)
+    test_gpu_gat.test_gat_forward_matches_oracle(24, 64, 64, 8, True)
+    test_gpu_gat.test_gat_forward_matches_oracle(16, 48, 40, 4, False)
+    test_gpu_gat.test_gat_layer_defaults_and_weight_names()
+
+
+def test_model_paths(fake):
+    test_gpu_models.test_gcn_functional("both", True, True, True, False, "relu")
+    test_gpu_models.test_gcn_functional("right", False, False, True, False, "relu")
+    test_gpu_models.test_gcn_two_layer_cora_shaped_model_with_cache()
+    test_gpu_models.test_plain_graph_sage("mean", True, True)
+    test_gpu_models.test_plain_graph_sage("sum", False, False)
+    test_gpu_models.test_pool_and_gcn_graph_sage_and_layers()
+    test_gpu_models.test_appnp(10, 0.1)
+    test_gpu_models.test_appnp(0, 0.1)

@@ -84,9 +84,47 @@ def lib():
     return _lib
 
 
+class CallTrace(object):
+    """Optional instrumentation used by bench.py: counts ABI calls by name and, for the names in `timed`, brackets the
+    call with CUDA events on the launching stream (torch.cuda.Event on torch's current stream, which is the stream
+    handed to the library)."""
+
+    def __init__(self, timed=()):
+        self.counts = {}
+        self.timed = set(timed)
+        self.events = {name: [] for name in self.timed}
+
+    def elapsed_ms(self, name):
+        """Per-call device durations (ms); call after synchronising."""
+        return [a.elapsed_time(b) for a, b in self.events.get(name, [])]
+
+
+_trace = None
+
+
+def set_trace(trace):
+    """Install (or remove, with None) a CallTrace; returns the previous one."""
+    global _trace
+    prev, _trace = _trace, trace
+    return prev
+
+
 def call(name, *args):
     handle = lib()
-    rc = getattr(handle, name)(*args)
+    trace = _trace
+    if trace is None:
+        rc = getattr(handle, name)(*args)
+    else:
+        trace.counts[name] = trace.counts.get(name, 0) + 1
+        if name in trace.timed:
+            import torch
+            start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            start.record()
+            rc = getattr(handle, name)(*args)
+            end.record()
+            trace.events[name].append((start, end))
+        else:
+            rc = getattr(handle, name)(*args)
     if rc != OK:
         raise TfgkError(name, rc, handle.tfgk_last_error().decode("utf-8", "replace"))
     return rc

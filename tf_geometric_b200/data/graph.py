@@ -108,7 +108,7 @@ class Graph(object):
     def to_device(self, device=None, inplace=False):
         """All graph data as CUDA tensors (the analogue of the reference's convert_data_to_tensor, :212-233)."""
         g = self if inplace else Graph(self._x, self.edge_index, y=self.y, edge_weight=self.edge_weight)
-        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        dev = device if device is not None else ops.default_device()
         g._x = ops.as_device(g.x, torch.float32, device=dev) if not isinstance(g._x, types.FunctionType) else g._x
         g.edge_index = ops.as_device(g.edge_index, torch.int32, device=dev)
         g.edge_weight = ops.as_device(g.edge_weight, torch.float32, device=dev)

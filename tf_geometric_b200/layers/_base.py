@@ -7,6 +7,8 @@ import math
 
 import torch
 
+from .. import ops
+
 
 class Layer(torch.nn.Module):
 
@@ -31,6 +33,7 @@ class Layer(torch.nn.Module):
         else:
             raise ValueError("unknown initializer {}".format(initializer))
         param = torch.nn.Parameter(w, requires_grad=False)
+        self.__dict__.pop(name, None)       # __init__ pre-declares the slot as None, like the reference's layers
         self.register_parameter(name, param)
         return param
 
@@ -40,7 +43,7 @@ class Layer(torch.nn.Module):
     def _maybe_build(self, inputs):
         if not self.built:
             x = inputs[0]
-            device = x.device if torch.is_tensor(x) and x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+            device = x.device if torch.is_tensor(x) and x.is_cuda else ops.default_device()
             self.build([tuple(x.shape)], device=device)
             self.built = True
 

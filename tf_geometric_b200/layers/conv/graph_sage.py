@@ -98,9 +98,6 @@ class _PoolSage(Layer):
         self.kernel_regularizer = kernel_regularizer
         self.bias_regularizer = bias_regularizer
         self.self_kernel = None
-        self.neighbor_mlp_kernel = None
-        self.neighbor_mlp_bias = None
-        self.neighbor_kernel = None
         self.bias = None
 
     def build(self, input_shapes, device=None):
@@ -108,19 +105,19 @@ class _PoolSage(Layer):
         kernel_units = self.units // 2 if self.concat else self.units
         mlp_k, mlp_b, neigh_k = self._names
         self.self_kernel = self.add_weight("self_kernel", [num_features, kernel_units], device=device)
-        self._mlp_kernel = self.add_weight(mlp_k, [num_features, kernel_units * 4], device=device)
-        self._mlp_bias = self.add_weight(mlp_b, [kernel_units * 4], "zeros", device=device) if self.use_bias else None
-        self._neigh_kernel = self.add_weight(neigh_k, [kernel_units * 4, kernel_units], device=device)
-        self.neighbor_mlp_kernel, self.neighbor_mlp_bias, self.neighbor_kernel = \
-            self._mlp_kernel, self._mlp_bias, self._neigh_kernel
+        self.add_weight(mlp_k, [num_features, kernel_units * 4], device=device)
+        if self.use_bias:
+            self.add_weight(mlp_b, [kernel_units * 4], "zeros", device=device)
+        self.add_weight(neigh_k, [kernel_units * 4, kernel_units], device=device)
         if self.use_bias:
             self.bias = self.add_weight("bias", [self.units], "zeros", device=device)
 
     def call(self, inputs, cache=None, training=None, mask=None):
         x, edge_index, edge_weight = _unpack(inputs)
-        return type(self)._fn(x, edge_index, edge_weight, self.self_kernel, self._mlp_kernel, self._neigh_kernel,
-                              neighbor_mlp_bias=self._mlp_bias, bias=self.bias, activation=self.activation,
-                              concat=self.concat, normalize=self.normalize)
+        mlp_k, mlp_b, neigh_k = self._names
+        return type(self)._fn(x, edge_index, edge_weight, self.self_kernel, getattr(self, mlp_k), getattr(self, neigh_k),
+                              neighbor_mlp_bias=getattr(self, mlp_b) if self.use_bias else None, bias=self.bias,
+                              activation=self.activation, concat=self.concat, normalize=self.normalize)
 
 
 class MeanPoolGraphSage(_PoolSage):

@@ -21,16 +21,20 @@ def _require_cuda():
         raise RuntimeError("tf_geometric_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback")
 
 
+def default_device():
+    _require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
 def as_device(x, dtype=None, device=None):
     """numpy / list / torch (any device) -> contiguous CUDA tensor of `dtype` (reference casting rules are applied
     by the callers: int32 edge_index, float32 weights/features; data/graph.py:58-86)."""
     if x is None:
         return None
-    _require_cuda()
     if not torch.is_tensor(x):
         x = torch.from_numpy(np.ascontiguousarray(x))
     if device is None:
-        device = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        device = x.device if x.is_cuda else default_device()
     if dtype is not None and x.dtype != dtype:
         x = x.to(dtype)
     if x.device != device:
