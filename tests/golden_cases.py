@@ -1,0 +1,188 @@
+# coding=utf-8
+"""Replays tests/golden/ref_exec_*.npz (outputs of the reference's own Python code, see tools/gen_golden_from_reference.py)
+against (a) the CPU oracle and (b) the CUDA product through its public API."""
+import numpy as np
+
+from conftest import assert_close
+
+EXACT = dict(rtol=0, atol=0)
+
+
+def _eq(a, b, what):
+    np.testing.assert_array_equal(np.asarray(a), np.asarray(b), err_msg=what)
+
+
+def _close(a, b, what, rtol=1e-4, atol_scale=1e-4):
+    assert_close(np.asarray(a), np.asarray(b), rtol=rtol, atol_scale=atol_scale, what=what)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# generic driver: `api` is a small adapter with the same function names for the oracle and for the product
+# ------------------------------------------------------------------------------------------------------------------
+
+class OracleApi(object):
+    exact_float = True
+
+    def __init__(self):
+        from oracle import tfg_oracle as o
+        self.o = o
+        self.relu = o.relu
+
+    def arr(self, a):
+        return a
+
+    def out(self, a):
+        return np.asarray(a)
+
+    def __getattr__(self, name):
+        return getattr(self.o, name)
+
+    def sparse(self, ei, w, n):
+        return self.o.SparseMatrix(ei, w, [n, n])
+
+    def gcn_norm(self, adj, norm, loop, sym, renorm, improved):
+        m = self.o.gcn_norm_adj(adj, norm, loop, sym, renorm, improved)
+        return m.index, m.value
+
+    def gcn_graph_sage(self, *a, **k):
+        return self.o.gcn_graph_sage(*a, **k)
+
+
+class ProductApi(object):
+    exact_float = False
+
+    def __init__(self):
+        import torch
+        import tf_geometric_b200 as tfg
+        self.tfg, self.torch = tfg, torch
+        self.relu = tfg.nn.relu
+        for name in ("aggregate_neighbors", "identity_mapper", "gcn_mapper", "neighbor_count_mapper", "sum_reducer",
+                     "mean_reducer", "max_reducer", "sum_updater", "identity_updater", "segment_softmax", "segment_count",
+                     "gcn", "gat", "mean_graph_sage", "sum_graph_sage", "gcn_graph_sage", "mean_pool_graph_sage",
+                     "max_pool_graph_sage", "appnp"):
+            setattr(self, name, getattr(tfg.nn, name))
+        for name in ("convert_edge_to_directed", "merge_duplicated_edge", "add_self_loop_edge", "remove_self_loop_edge",
+                     "adj_norm_edge"):
+            setattr(self, name, getattr(tfg.utils, name))
+
+    def arr(self, a):
+        if a is None:
+            return None
+        a = np.asarray(a)
+        return self.tfg.ops.as_device(a, {"i": self.torch.int32, "f": self.torch.float32}[a.dtype.kind])
+
+    def out(self, a):
+        return a.detach().cpu().numpy() if self.torch.is_tensor(a) else np.asarray(a)
+
+    def sparse(self, ei, w, n):
+        return self.tfg.SparseMatrix(ei, w, [n, n])
+
+    def gcn_norm(self, adj, norm, loop, sym, renorm, improved):
+        m = self.tfg.nn.gcn_norm_adj(adj, norm, loop, sym, renorm, improved)
+        return m.index, m.value
+
+
+def replay(fname, data, api):
+    kind = fname[len("ref_exec_"):-len(".npz")]
+    globals()["_replay_" + kind](data, api)
+
+
+def replay_with_oracle(fname, data):
+    replay(fname, data, OracleApi())
+
+
+def _replay_graph_utils(d, api):
+    A, O = api.arr, api.out
+    i, (w,) = api.convert_edge_to_directed(A(d["readme_ei"]), [A(d["readme_w"])], ["sum"])
+    _eq(O(i), d["readme_directed_index"], "readme to_directed index")
+    _eq(O(w), d["readme_directed_w"], "readme to_directed weight")
+    for mode in ("sum", "min", "max", "mean"):
+        i, (w,) = api.merge_duplicated_edge(A(d["multi_ei"]), [A(d["multi_w"])], [mode])
+        _eq(O(i), d["merge_{}_index".format(mode)], "merge index " + mode)
+        _eq(O(w), d["merge_{}_w".format(mode)], "merge weight " + mode)
+        i, (w,) = api.convert_edge_to_directed(A(d["multi_ei"]), [A(d["multi_w"])], [mode])
+        _eq(O(i), d["directed_{}_index".format(mode)], "directed index " + mode)
+        _eq(O(w), d["directed_{}_w".format(mode)], "directed weight " + mode)
+    i, w = api.add_self_loop_edge(A(d["multi_ei"]), 12, A(d["multi_w"]), fill_weight=2.0)
+    _eq(O(i), d["self_loop_index"], "self loop index")
+    _eq(O(w), d["self_loop_w"], "self loop weight")
+    i, w = api.remove_self_loop_edge(A(d["multi_ei"]), A(d["multi_w"]))
+    _eq(O(i), d["no_loop_index"], "remove loop index")
+    _eq(O(w), d["no_loop_w"], "remove loop weight")
+    i, w = api.adj_norm_edge(A(d["multi_ei"]), 12, A(d["multi_w"]), add_self_loop=True)
+    _eq(O(i), d["adj_norm_index"], "adj_norm index")
+    _close(O(w), d["adj_norm_w"], "adj_norm weight", rtol=3e-7, atol_scale=0)
+
+
+def _replay_kernel(d, api):
+    A, O = api.arr, api.out
+    n = int(d["n"])
+    ei, x, w = d["ei"], d["x"], d["w"]
+    _close(O(api.segment_softmax(A(d["scores"]), A(ei[0]), n)), d["segment_softmax"], "segment_softmax", rtol=2e-5,
+           atol_scale=1e-7)
+    cnt = O(api.segment_count(A(ei[0]), n))
+    _eq(cnt, d["segment_count"], "segment_count")
+    assert cnt.dtype == np.int32
+    red = {"sum": api.sum_reducer, "mean": api.mean_reducer, "max": api.max_reducer}
+    for rname, fn in red.items():
+        got = api.aggregate_neighbors(A(x), A(ei), None, api.identity_mapper, fn, api.sum_updater, num_nodes=n)
+        _eq(O(got), d["agg_identity_{}_sumupd".format(rname)], "aggregate identity/" + rname)
+        got = api.aggregate_neighbors(A(x), A(ei), A(w), api.gcn_mapper, fn, api.identity_updater, num_nodes=n)
+        _eq(O(got), d["agg_gcn_{}_idupd".format(rname)], "aggregate gcn_mapper/" + rname)
+    got = api.aggregate_neighbors(A(x), A(ei), None, api.neighbor_count_mapper, api.sum_reducer, api.identity_updater,
+                                  num_nodes=n)
+    _eq(O(got), d["agg_count"], "neighbor count")
+
+
+def _replay_gcn(d, api):
+    A, O = api.arr, api.out
+    n = int(d["n"])
+    for i, cfg in enumerate(d["configs"]):
+        norm, loop, sym, renorm, improved = str(cfg).split("|")
+        loop, sym, renorm, improved = (v == "True" for v in (loop, sym, renorm, improved))
+        ei, w = (d["ei_sym"], d["w_sym"]) if sym else (d["ei_dir"], d["w_dir"])
+        index, value = api.gcn_norm(api.sparse(ei, w, n), norm, loop, sym, renorm, improved)
+        _eq(O(index), d["norm{}_index".format(i)], "gcn_norm index " + str(cfg))          # bit-exact integers
+        _close(O(value), d["norm{}_value".format(i)], "gcn_norm value " + str(cfg), rtol=0 if api.exact_float else 3e-7,
+               atol_scale=0)
+        got = api.gcn(A(d["x"]), api.sparse(ei, w, n), A(d["kernel"]), A(d["bias"]), api.relu, norm, loop, sym, renorm,
+                      improved)
+        _close(O(got), d["gcn{}_out".format(i)], "gcn out " + str(cfg), rtol=0 if api.exact_float else 1e-4,
+               atol_scale=0 if api.exact_float else 1e-4)
+    got = api.gcn(A(d["x"]), api.sparse(d["ei_sym"], d["w_sym"], n), None, None)
+    _close(O(got), d["gcn_no_kernel"], "gcn no kernel", rtol=0 if api.exact_float else 1e-5, atol_scale=0 if api.exact_float else 1e-6)
+
+
+def _replay_gat(d, api):
+    A, O = api.arr, api.out
+    for tag in ("h8", "h4avg", "h1", "demo"):
+        g = lambda k: d[tag + "_" + k]
+        got = api.gat(A(d["x"]), A(d["ei"]), A(g("wq")), A(g("bq")), api.relu, A(g("wk")), A(g("bk")), api.relu,
+                      A(g("wv")), A(g("b")), api.relu, num_heads=int(g("heads")), split_value_heads=bool(g("split")))
+        _close(O(got), g("out"), "gat " + tag, rtol=0 if api.exact_float else 1e-4, atol_scale=0 if api.exact_float else 1e-4)
+
+
+def _replay_graph_sage(d, api):
+    A, O = api.arr, api.out
+    x, ei, w = A(d["x"]), A(d["ei"]), A(d["w"])
+    ws, wn, b2, b1 = A(d["ws"]), A(d["wn"]), A(d["b2"]), A(d["b1"])
+    wm, bm, wnk, kernel = A(d["wm"]), A(d["bm"]), A(d["wnk"]), A(d["kernel"])
+    tol = dict(rtol=0, atol_scale=0) if api.exact_float else dict(rtol=1e-4, atol_scale=1e-4)
+    _close(O(api.mean_graph_sage(x, ei, w, ws, wn, b2, api.relu, True, True)), d["mean_w_concat_norm"], "mean sage",
+           **(dict(rtol=1e-6, atol_scale=1e-7) if api.exact_float else tol))
+    _close(O(api.mean_graph_sage(x, ei, None, ws, wn, b1, api.relu, False, False)), d["mean_now_add"], "mean sage add", **tol)
+    _close(O(api.sum_graph_sage(x, ei, w, ws, wn, b2, None, True, False)), d["sum_w_concat"], "sum sage", **tol)
+    _close(O(api.gcn_graph_sage(x, ei, w, kernel, b1, api.relu, False, cache=None)), d["gcn_sage_nocache"], "gcn sage", **tol)
+    _close(O(api.gcn_graph_sage(x, ei, w, kernel, b1, api.relu, True, cache={"k": 1})), d["gcn_sage_cache"],
+           "gcn sage (cache quirk)", **(dict(rtol=1e-6, atol_scale=1e-7) if api.exact_float else tol))
+    _close(O(api.mean_pool_graph_sage(x, ei, w, ws, wm, wnk, bm, b2, api.relu)), d["mean_pool"], "mean pool", **tol)
+    _close(O(api.max_pool_graph_sage(x, ei, w, ws, wm, wnk, bm, b2, api.relu)), d["max_pool"], "max pool", **tol)
+
+
+def _replay_appnp(d, api):
+    A, O = api.arr, api.out
+    tol = dict(rtol=0, atol_scale=0) if api.exact_float else dict(rtol=1e-4, atol_scale=1e-4)
+    ks, bs = [A(d["k0"]), A(d["k1"])], [A(d["b0"]), A(d["b1"])]
+    _close(O(api.appnp(A(d["x"]), A(d["ei"]), A(d["w"]), ks, bs, k=10, alpha=0.1)), d["k10"], "appnp k=10", **tol)
+    _close(O(api.appnp(A(d["x"]), A(d["ei"]), A(d["w"]), ks, bs, activation=api.relu, k=2, alpha=0.3)), d["k2_relu"],
+           "appnp k=2 relu", **tol)

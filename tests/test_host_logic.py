@@ -86,3 +86,14 @@ def test_model_paths(fake):
     test_gpu_models.test_pool_and_gcn_graph_sage_and_layers()
     test_gpu_models.test_appnp(10, 0.1)
     test_gpu_models.test_appnp(0, 0.1)
+
+
+def test_golden_fixtures_through_public_api(fake):
+    """The committed reference-execution fixtures replayed through the product's host logic (fake kernels)."""
+    import os
+    import golden_cases
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    files = sorted(f for f in os.listdir(golden) if f.startswith("ref_exec_"))
+    assert len(files) >= 6
+    for f in files:
+        golden_cases.replay(f, np.load(os.path.join(golden, f), allow_pickle=False), golden_cases.ProductApi())

@@ -1,0 +1,179 @@
+#!/usr/bin/env python
+# coding=utf-8
+"""Generate tests/golden/ref_exec_*.npz by EXECUTING the reference's own Python (read-only /root/reference) over the
+numpy shims in tools/ref_shim.  Runs only in the authoring container (the reference does not travel to the GPU box);
+the resulting small fixtures are committed.  Re-run:  python tools/gen_golden_from_reference.py
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+REFERENCE = os.environ.get("TFG_REFERENCE", "/root/reference")
+OUT = os.path.join(ROOT, "tests", "golden")
+
+import ref_shim  # noqa: E402
+
+T = ref_shim.install(REFERENCE)
+tf = sys.modules["tensorflow"]
+tfs = sys.modules["tf_sparse"]
+seg = importlib.import_module("tf_geometric.nn.kernel.segment")
+mr = importlib.import_module("tf_geometric.nn.kernel.map_reduce")
+gu = importlib.import_module("tf_geometric.utils.graph_utils")
+gcn_m = importlib.import_module("tf_geometric.nn.conv.gcn")
+gat_m = importlib.import_module("tf_geometric.nn.conv.gat")
+sage_m = importlib.import_module("tf_geometric.nn.conv.graph_sage")
+appnp_m = importlib.import_module("tf_geometric.nn.conv.appnp")
+
+
+def glorot(rs, a, b):
+    lim = np.sqrt(6.0 / (a + b))
+    return rs.uniform(-lim, lim, (a, b)).astype(np.float32)
+
+
+def graph(n, e, seed, symmetric):
+    rs = np.random.RandomState(seed)
+    if symmetric:
+        u, v = rs.randint(0, n, e // 2), rs.randint(0, n, e // 2)
+        keep = u != v
+        u, v = u[keep], v[keep]
+        return np.stack([np.concatenate([u, v]), np.concatenate([v, u])]).astype(np.int32)
+    ei = rs.randint(0, n, (2, e)).astype(np.int32)
+    ei[0][ei[0] < 3] = 3            # nodes 0..2 have no in-edges (empty segments)
+    return ei
+
+
+def save(name, **arrays):
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, "ref_exec_{}.npz".format(name)),
+                        **{k: np.asarray(v) for k, v in arrays.items() if v is not None})
+    print("wrote ref_exec_{}.npz: {}".format(name, ", ".join(sorted(arrays))))
+
+
+def main():
+    rs = np.random.RandomState(1234)
+
+    # ---- README fixture (README.md:31-35) + a random multigraph through the integer preprocessing -----------------
+    readme_ei = np.array([[0, 0, 1, 3], [1, 2, 2, 1]], np.int32)
+    readme_w = np.array([0.9, 0.8, 0.1, 0.2], np.float32)
+    d_i, (d_w,) = gu.convert_edge_to_directed(T(readme_ei), [T(readme_w)], merge_modes=["sum"])
+    multi = rs.randint(0, 12, (2, 80)).astype(np.int32)
+    multi_w = rs.rand(80).astype(np.float32)
+    out = {"readme_ei": readme_ei, "readme_w": readme_w, "readme_directed_index": d_i, "readme_directed_w": d_w,
+           "multi_ei": multi, "multi_w": multi_w}
+    for mode in ("sum", "min", "max", "mean"):
+        m_i, (m_w,) = gu.merge_duplicated_edge(T(multi), [T(multi_w)], merge_modes=[mode])
+        dd_i, (dd_w,) = gu.convert_edge_to_directed(T(multi), [T(multi_w)], merge_modes=[mode])
+        out["merge_{}_index".format(mode)], out["merge_{}_w".format(mode)] = m_i, m_w
+        out["directed_{}_index".format(mode)], out["directed_{}_w".format(mode)] = dd_i, dd_w
+    sl_i, sl_w = gu.add_self_loop_edge(T(multi), 12, T(multi_w), fill_weight=2.0)
+    rm_i, rm_w = gu.remove_self_loop_edge(T(multi), T(multi_w))
+    an_i, an_w = gu.adj_norm_edge(T(multi), 12, T(multi_w), add_self_loop=True)
+    out.update(self_loop_index=sl_i, self_loop_w=sl_w, no_loop_index=rm_i, no_loop_w=rm_w, adj_norm_index=an_i,
+               adj_norm_w=an_w)
+    save("graph_utils", **out)
+
+    # ---- segment ops + aggregate_neighbors -----------------------------------------------------------------------------
+    n, e, d = 60, 700, 9
+    ei = graph(n, e, 5, False)
+    x = rs.randn(n, d).astype(np.float32)
+    w = rs.rand(ei.shape[1]).astype(np.float32)
+    scores = (rs.randn(ei.shape[1]) * 3).astype(np.float32)
+    out = {"ei": ei, "x": x, "w": w, "scores": scores, "n": n,
+           "segment_softmax": seg.segment_softmax(T(scores), T(ei[0]), n),
+           "segment_count": seg.segment_count(T(ei[0]), n)}
+    reducers = {"sum": mr.sum_reducer, "mean": mr.mean_reducer, "max": mr.max_reducer}
+    for rname, red in reducers.items():
+        out["agg_identity_{}_sumupd".format(rname)] = mr.aggregate_neighbors(T(x), T(ei), None, mr.identity_mapper, red,
+                                                                             mr.sum_updater, num_nodes=n)
+        out["agg_gcn_{}_idupd".format(rname)] = mr.aggregate_neighbors(T(x), T(ei), T(w), gcn_m.gcn_mapper, red,
+                                                                        mr.identity_updater, num_nodes=n)
+    out["agg_count"] = mr.aggregate_neighbors(T(x), T(ei), None, mr.neighbor_count_mapper, mr.sum_reducer,
+                                              mr.identity_updater, num_nodes=n)
+    save("kernel", **out)
+
+    # ---- gcn_norm_adj variants and gcn ---------------------------------------------------------------------------------
+    n, f, u = 50, 14, 6
+    ei_sym, ei_dir = graph(n, 500, 7, True), graph(n, 500, 8, False)
+    w_sym = rs.rand(ei_sym.shape[1]).astype(np.float32) + 0.1
+    # symmetric weights: mirror halves share a weight
+    half = ei_sym.shape[1] // 2
+    w_sym[half:] = w_sym[:half]
+    w_dir = rs.rand(ei_dir.shape[1]).astype(np.float32) + 0.1
+    x = rs.randn(n, f).astype(np.float32)
+    kernel, bias = glorot(rs, f, u), rs.randn(u).astype(np.float32)
+    out = {"n": n, "ei_sym": ei_sym, "w_sym": w_sym, "ei_dir": ei_dir, "w_dir": w_dir, "x": x, "kernel": kernel, "bias": bias}
+    configs = [("both", True, True, True, False), ("both", True, True, True, True), ("both", True, True, False, False),
+               ("both", True, False, True, False), ("both", False, False, True, False), ("left", True, False, True, False),
+               ("right", True, False, True, False), ("left", False, False, True, False)]
+    out["configs"] = np.array(["{}|{}|{}|{}|{}".format(*c) for c in configs])
+    for i, (norm, loop, sym, renorm, improved) in enumerate(configs):
+        ei_, w_ = (ei_sym, w_sym) if sym else (ei_dir, w_dir)
+        adj = tfs.SparseMatrix(T(ei_), T(w_), [n, n])
+        cache = {}
+        normed = gcn_m.gcn_norm_adj(adj, norm, loop, sym, renorm, improved, cache=cache)
+        key = gcn_m.compute_cache_key(norm, loop, sym, renorm, improved)
+        assert list(cache.keys()) == [key]
+        out["norm{}_index".format(i)], out["norm{}_value".format(i)] = normed.index, normed.value
+        out["norm{}_cache_key".format(i)] = np.array(key)
+        out["gcn{}_out".format(i)] = gcn_m.gcn(T(x), adj, T(kernel), T(bias), activation=tf.nn.relu, norm=norm,
+                                                add_self_loop=loop, sym=sym, renorm=renorm, improved=improved)
+    out["gcn_no_kernel"] = gcn_m.gcn(T(x), tfs.SparseMatrix(T(ei_sym), T(w_sym), [n, n]), None, None)
+    save("gcn", **out)
+
+    # ---- gat -----------------------------------------------------------------------------------------------------------
+    n, f = 40, 10
+    ei = graph(n, 300, 9, False)
+    ei = np.concatenate([ei, np.array([[5, 5], [5, 5]], np.int32)], axis=1)     # pre-existing self loop, twice
+    x = rs.randn(n, f).astype(np.float32)
+    out = {"n": n, "ei": ei, "x": x}
+    for tag, a, u, heads, split in (("h8", 32, 16, 8, True), ("h4avg", 16, 12, 4, False), ("h1", 8, 8, 1, True),
+                                    ("demo", 8, 64, 8, True)):
+        wq, wk = glorot(rs, f, a), glorot(rs, f, a)
+        wv = glorot(rs, f, u if split else u * heads)
+        bq, bk, b = (rs.randn(a) * .1).astype(np.float32), (rs.randn(a) * .1).astype(np.float32), rs.randn(u).astype(np.float32)
+        res = gat_m.gat(T(x), T(ei), T(wq), T(bq), tf.nn.relu, T(wk), T(bk), tf.nn.relu, T(wv), T(b), tf.nn.relu,
+                        num_heads=heads, split_value_heads=split)
+        out.update({tag + "_wq": wq, tag + "_wk": wk, tag + "_wv": wv, tag + "_bq": bq, tag + "_bk": bk, tag + "_b": b,
+                    tag + "_heads": heads, tag + "_split": int(split), tag + "_out": res})
+    save("gat", **out)
+
+    # ---- graph_sage ----------------------------------------------------------------------------------------------------
+    n, f, u = 45, 12, 8
+    ei = graph(n, 400, 10, True)
+    w = rs.rand(ei.shape[1]).astype(np.float32) + 0.2
+    x = rs.randn(n, f).astype(np.float32)
+    ws, wn = glorot(rs, f, u), glorot(rs, f, u)
+    b2, b1 = rs.randn(2 * u).astype(np.float32), rs.randn(u).astype(np.float32)
+    wm, bm, wnk = glorot(rs, f, 4 * u), rs.randn(4 * u).astype(np.float32), glorot(rs, 4 * u, u)
+    kernel = glorot(rs, f, u)
+    out = {"n": n, "ei": ei, "w": w, "x": x, "ws": ws, "wn": wn, "b2": b2, "b1": b1, "wm": wm, "bm": bm, "wnk": wnk,
+           "kernel": kernel}
+    out["mean_w_concat_norm"] = sage_m.mean_graph_sage(T(x), T(ei), T(w), T(ws), T(wn), T(b2), tf.nn.relu, True, True)
+    out["mean_now_add"] = sage_m.mean_graph_sage(T(x), T(ei), None, T(ws), T(wn), T(b1), tf.nn.relu, False, False)
+    out["sum_w_concat"] = sage_m.sum_graph_sage(T(x), T(ei), T(w), T(ws), T(wn), T(b2), None, True, False)
+    out["gcn_sage_nocache"] = sage_m.gcn_graph_sage(T(x), T(ei), T(w), T(kernel), T(b1), tf.nn.relu, False, cache=None)
+    out["gcn_sage_cache"] = sage_m.gcn_graph_sage(T(x), T(ei), T(w), T(kernel), T(b1), tf.nn.relu, True, cache={"k": 1})
+    out["mean_pool"] = sage_m.mean_pool_graph_sage(T(x), T(ei), T(w), T(ws), T(wm), T(wnk), T(bm), T(b2), tf.nn.relu)
+    out["max_pool"] = sage_m.max_pool_graph_sage(T(x), T(ei), T(w), T(ws), T(wm), T(wnk), T(bm), T(b2), tf.nn.relu)
+    save("graph_sage", **out)
+
+    # ---- appnp ---------------------------------------------------------------------------------------------------------
+    n, f = 40, 11
+    ei = graph(n, 360, 11, True)
+    w = np.ones(ei.shape[1], np.float32)
+    x = rs.randn(n, f).astype(np.float32)
+    k0, k1 = glorot(rs, f, 16), glorot(rs, 16, 5)
+    b0, b1 = rs.randn(16).astype(np.float32), rs.randn(5).astype(np.float32)
+    out = {"n": n, "ei": ei, "w": w, "x": x, "k0": k0, "k1": k1, "b0": b0, "b1": b1}
+    out["k10"] = appnp_m.appnp(T(x), T(ei), T(w), [T(k0), T(k1)], [T(b0), T(b1)], k=10, alpha=0.1)
+    out["k2_relu"] = appnp_m.appnp(T(x), T(ei), T(w), [T(k0), T(k1)], [T(b0), T(b1)], activation=tf.nn.relu, k=2, alpha=0.3)
+    save("appnp", **out)
+
+
+if __name__ == "__main__":
+    main()

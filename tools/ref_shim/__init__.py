@@ -1,0 +1,202 @@
+# coding=utf-8
+"""numpy stand-ins for `tensorflow` and `tf_sparse`, just large enough to EXECUTE the reference's own Python files
+for the message-passing hot path (nn/kernel/*.py, nn/conv/{gcn,gat,graph_sage,appnp}.py, utils/graph_utils.py)
+in a container that has neither package.  Used ONLY by tools/gen_golden_from_reference.py to produce
+tests/golden/ref_exec_*.npz.  What this pins: the reference's control flow, call order, quirks and in-repo arithmetic.
+What it cannot pin: TensorFlow's / tf_sparse's own kernels - their semantics are restated here from the public docs
+(and, for tf_sparse, from the commented-out legacy code in the reference)."""
+import sys
+import types
+
+import numpy as np
+
+from oracle import tfg_oracle as _o
+
+
+class Tensor(np.ndarray):
+    """An eager tensor: an ndarray that also answers .numpy()."""
+
+    def numpy(self):
+        return np.asarray(self)
+
+
+def T(a, dtype=None):
+    return np.asarray(a, dtype=dtype).view(Tensor)
+
+
+def _unsupported(name):
+    def fn(*a, **k):
+        raise NotImplementedError("tensorflow shim: {} is not implemented".format(name))
+    return fn
+
+
+def build_tensorflow():
+    tf = types.ModuleType("tensorflow")
+    tf.__version__ = "2.15.0"
+    tf.float32, tf.float64, tf.int32, tf.int64, tf.bool = np.float32, np.float64, np.int32, np.int64, np.bool_
+    tf.is_tensor = lambda x: isinstance(x, Tensor)
+    tf.executing_eagerly = lambda: True
+    tf.function = lambda f=None, **k: (f if f is not None else (lambda g: g))
+    tf.convert_to_tensor = lambda x, dtype=None: T(x, dtype)
+    tf.cast = lambda x, dtype: (T(np.asarray(x).astype(dtype)) if np.ndim(x) else dtype(x))
+    tf.shape = lambda x: T(np.array(np.shape(x), dtype=np.int32))
+    tf.range = lambda *a, dtype=np.int32: T(np.arange(*[int(v) for v in a], dtype=dtype))
+    tf.ones = lambda shape, dtype=np.float32: T(np.ones([int(s) for s in shape], dtype=dtype))
+    tf.zeros = lambda shape, dtype=np.float32: T(np.zeros([int(s) for s in shape], dtype=dtype))
+    tf.fill = lambda shape, v: T(np.full([int(s) for s in shape], v))
+    tf.ones_like = lambda x: T(np.ones_like(np.asarray(x)))
+    tf.zeros_like = lambda x: T(np.zeros_like(np.asarray(x)))
+    tf.stack = lambda xs, axis=0: T(np.stack([np.asarray(x) for x in xs], axis=axis))
+    tf.concat = lambda xs, axis=0: T(np.concatenate([np.asarray(x) for x in xs], axis=axis))
+    tf.split = lambda x, n, axis=0: [T(p) for p in np.split(np.asarray(x), n, axis=axis)]
+    tf.reshape = lambda x, shape: T(np.reshape(np.asarray(x), shape))
+    tf.expand_dims = lambda x, axis: T(np.expand_dims(np.asarray(x), axis))
+    tf.where = lambda c, a, b: T(np.where(np.asarray(c), np.asarray(a), np.asarray(b)))
+    tf.boolean_mask = lambda t, m, axis=None: T(np.compress(np.asarray(m), np.asarray(t), axis=0 if axis is None else axis))
+    tf.not_equal = lambda a, b: T(np.not_equal(np.asarray(a), np.asarray(b)))
+    tf.less = lambda a, b: T(np.less(np.asarray(a), np.asarray(b)))
+    tf.maximum = lambda a, b: T(np.maximum(np.asarray(a), np.asarray(b)))
+    tf.pow = lambda x, p: T(_pow(np.asarray(x), p))
+    tf.exp = lambda x: T(np.exp(np.asarray(x)))
+    tf.stop_gradient = lambda x: x
+    tf.add_n = lambda xs: T(_add_n(xs))
+    tf.reduce_sum = lambda x, axis=None: _red(np.sum, x, axis)
+    tf.reduce_mean = lambda x, axis=None: _red(np.mean, x, axis)
+    tf.reduce_max = lambda x, axis=None: _red(np.max, x, axis)
+    tf.reduce_any = lambda x, axis=None: bool(np.any(np.asarray(x)))
+
+    def gather(params, indices, axis=0):
+        return T(_o.gather(np.asarray(params), np.asarray(indices)))
+    tf.gather = gather
+
+    def unique(x):
+        vals, idx = _o.tf_unique(np.asarray(x))
+        return T(vals), T(idx)
+    tf.unique = unique
+
+    math = types.ModuleType("tensorflow.math")
+    math.unsorted_segment_sum = lambda d, i, num_segments: T(_o.unsorted_segment_sum(np.asarray(d), np.asarray(i), int(num_segments)))
+    math.unsorted_segment_mean = lambda d, i, num_segments: T(_o.unsorted_segment_mean(np.asarray(d), np.asarray(i), int(num_segments)))
+    math.unsorted_segment_max = lambda d, i, num_segments: T(_o.unsorted_segment_max(np.asarray(d), np.asarray(i), int(num_segments)))
+    math.unsorted_segment_min = lambda d, i, num_segments: T(_o.unsorted_segment_min(np.asarray(d), np.asarray(i), int(num_segments)))
+    math.logical_or = lambda a, b: T(np.logical_or(np.asarray(a), np.asarray(b)))
+    math.logical_and = lambda a, b: T(np.logical_and(np.asarray(a), np.asarray(b)))
+    math.is_inf = lambda x: T(np.isinf(np.asarray(x)))
+    math.is_nan = lambda x: T(np.isnan(np.asarray(x)))
+    math.sqrt = lambda x: (T(np.sqrt(np.asarray(x))) if np.ndim(x) else np.sqrt(np.float32(x)))
+    math.floordiv = lambda a, b: T(np.asarray(a) // np.asarray(b))
+    math.floormod = lambda a, b: T(np.asarray(a) % np.asarray(b))
+    math.reduce_min = lambda x, axis=None: _red(np.min, x, axis)
+    math.reduce_max = lambda x, axis=None: _red(np.max, x, axis)
+    math.__getattr__ = lambda name: _unsupported("tf.math." + name)
+    tf.math = math
+
+    nn = types.ModuleType("tensorflow.nn")
+    nn.relu = lambda x: T(np.maximum(np.asarray(x), np.float32(0)))
+    nn.l2_normalize = lambda x, axis=-1: T(_o.l2_normalize(np.asarray(x)))
+    nn.__getattr__ = lambda name: _unsupported("tf.nn." + name)
+    tf.nn = nn
+
+    sparse = types.ModuleType("tensorflow.sparse")
+
+    class SparseTensor(object):
+        pass
+    sparse.SparseTensor = SparseTensor
+    sparse.__getattr__ = lambda name: _unsupported("tf.sparse." + name)
+    tf.sparse = sparse
+    tf.__getattr__ = lambda name: _unsupported("tf." + name)
+    return tf
+
+
+def _pow(x, p):
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.power(x, x.dtype.type(p))
+
+
+def _add_n(xs):
+    acc = np.asarray(xs[0])
+    for x in xs[1:]:
+        acc = acc + np.asarray(x)
+    return acc
+
+
+def _red(fn, x, axis):
+    r = fn(np.asarray(x), axis=axis)
+    return T(r) if np.ndim(r) else r
+
+
+def build_tf_sparse():
+    """tf_sparse >= 0.0.17 [UNVERIFIED restatement]: COO, no sort, no merge; add_diag appends the diagonal."""
+    tfs = types.ModuleType("tf_sparse")
+
+    class DiagMatrix(object):
+        def __init__(self, d):
+            self.d = np.asarray(d)
+
+        def __matmul__(self, other):                      # diags(d) @ A : scale rows
+            return SparseMatrix(other.index, T(self.d[np.asarray(other.index[0])] * np.asarray(other.value)), other.shape)
+
+    class SparseMatrix(object):
+        def __init__(self, index, value=None, shape=None, merge=False):
+            self.index = T(np.asarray(index, dtype=np.int32).reshape(2, -1))
+            nnz = self.index.shape[1]
+            self.value = T(np.ones([nnz], np.float32)) if value is None else T(np.asarray(value, dtype=np.float32))
+            if shape is None:
+                n = int(np.max(self.index)) + 1
+                shape = [n, n]
+            self._shape = T(np.array([int(s) for s in np.asarray(shape)], dtype=np.int64))
+
+        @property
+        def shape(self):
+            return [int(s) for s in self._shape]
+
+        def add_diag(self, w):
+            m = _o.SparseMatrix(np.asarray(self.index), np.asarray(self.value), self.shape).add_diag(w)
+            return SparseMatrix(m.index, m.value, m.shape)
+
+        def segment_sum(self, axis=-1):
+            m = _o.SparseMatrix(np.asarray(self.index), np.asarray(self.value), self.shape)
+            return T(m.segment_sum(axis))
+
+        def segment_softmax(self, axis=-1):
+            m = _o.SparseMatrix(np.asarray(self.index), np.asarray(self.value), self.shape).segment_softmax(axis)
+            return SparseMatrix(m.index, m.value, m.shape)
+
+        def dropout(self, rate, training=False):
+            assert not (training and rate > 0.0)
+            return self
+
+        def matmul(self, h, num_or_size_splits=None):
+            m = _o.SparseMatrix(np.asarray(self.index), np.asarray(self.value), self.shape)
+            return T(m.matmul(np.asarray(h)))
+
+        def __matmul__(self, other):
+            if isinstance(other, DiagMatrix):             # A @ diags(d) : scale columns
+                return SparseMatrix(self.index, T(np.asarray(self.value) * other.d[np.asarray(self.index[1])]), self.shape)
+            return self.matmul(other)
+
+    tfs.SparseMatrix = SparseMatrix
+    tfs.diags = lambda d: DiagMatrix(d)
+    tfs.shape = lambda x: list(np.shape(x)) if not isinstance(x, SparseMatrix) else x.shape
+    tfs.__getattr__ = lambda name: _unsupported("tf_sparse." + name)
+    return tfs
+
+
+def install(reference_root):
+    """Put the shims and stub packages into sys.modules so individual reference files can be imported without
+    running tf_geometric/__init__.py (which pulls in keras layers, datasets and downloads)."""
+    import os
+    sys.modules["tensorflow"] = build_tensorflow()
+    sys.modules["tf_sparse"] = build_tf_sparse()
+    pkg_root = os.path.join(reference_root, "tf_geometric")
+    for name, sub in (("tf_geometric", ""), ("tf_geometric.nn", "nn"), ("tf_geometric.nn.kernel", "nn/kernel"),
+                      ("tf_geometric.nn.conv", "nn/conv"), ("tf_geometric.utils", "utils")):
+        mod = types.ModuleType(name)
+        mod.__path__ = [os.path.join(pkg_root, sub)]
+        sys.modules[name] = mod
+    import importlib
+    mr = importlib.import_module("tf_geometric.nn.kernel.map_reduce")
+    for n in ("mean_reducer", "max_reducer", "sum_reducer", "identity_mapper", "neighbor_count_mapper", "sum_updater",
+              "identity_updater", "aggregate_neighbors"):
+        setattr(sys.modules["tf_geometric.nn"], n, getattr(mr, n))
+    return T
