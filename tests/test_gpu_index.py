@@ -92,7 +92,7 @@ def test_gcn_norm_adj_index_bit_exact_values_close(norm, loop, sym, renorm, impr
     got = tfg.nn.gcn_norm_adj(tfg.SparseMatrix(ei, w, [n, n]), norm, loop, sym, renorm, improved)
     np.testing.assert_array_equal(host(got.index), want.index)                 # bit-exact integers
     assert got.index.dtype == torch.int32
-    np.testing.assert_allclose(host(got.value), want.value, rtol=3e-7, atol=0)  # fp32, <= 2 ulp
+    np.testing.assert_allclose(host(got.value), want.value, rtol=6e-7, atol=0)  # fp32: two correctly rounded rsqrt + two products, <= 4 ulp
     # the CSR the kernels will use is the stable sort of exactly that index
     rowptr, col, perm = o.csr_build(want.index[0], want.index[1], n)
     np.testing.assert_array_equal(host(got.csr.rowptr), rowptr)
@@ -112,7 +112,7 @@ def test_gcn_norm_derived_kat_and_cache():
     assert host(normed.index).tolist() == [[0, 0, 1, 1, 1, 2, 2, 3, 0, 1, 2, 3, 4], [1, 2, 2, 3, 0, 0, 1, 1, 0, 1, 2, 3, 4]]
     want = [0.36927447, 0.3532086, 0.0489116, 0.1230915, 0.36927447, 0.3532086, 0.0489116, 0.1230915, 0.37037033,
             0.45454547, 0.52631575, 0.8333334, 1.0]
-    np.testing.assert_allclose(host(normed.value), np.array(want, np.float32), rtol=3e-7)
+    np.testing.assert_allclose(host(normed.value), np.array(want, np.float32), rtol=6e-7)
     assert tfg.nn.gcn_norm_adj(g.adj(), cache=g.cache) is normed       # warm hit returns the cached object
     # a reference-style (index, value, shape) numpy triple in the cache is honoured too
     triple_cache = {key: (host(normed.index), host(normed.value), [5, 5])}
