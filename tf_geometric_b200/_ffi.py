@@ -15,6 +15,7 @@ _lib = None
 ABI_VERSION = 1
 
 OK = 0
+ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED, ERR_INDEX_OUT_OF_RANGE = 1, 2, 3, 4, 5
 REDUCE_SUM, REDUCE_MEAN, REDUCE_MAX = 0, 1, 2
 ACT_NONE, ACT_RELU = 0, 1
 POW_INV_SQRT, POW_INV = 0, 1

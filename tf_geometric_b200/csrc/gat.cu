@@ -10,6 +10,7 @@
 // roofline of the reference's 5-pass segment_softmax + two [E,A] gathers + SpMM pipeline.
 // No tensor cores: the per-edge dot products are 16-wide and the kernel is bound by the gathers.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace tfgk {
 
@@ -188,6 +189,126 @@ __global__ void __launch_bounds__(kGatThreads) gat_fast_kernel(const GatParams p
     }
 }
 
+// ---- single-pass path (dqk == dv): one walk over the edges with an online softmax ----------------------------------
+// Per edge the K row gives the per-head score, and the V row is consumed in the same iteration:
+//     m' = max(m, s);  acc = acc * exp(m - m') + exp(s - m') * V[col];  l = l * exp(m - m') + exp(s - m')
+// (U edges share one rescale).  K and V are each read once, together - when the caller projects them into one
+// [N, A+U] buffer (V == K + A, same leading dimension) the two 16-byte loads of a lane hit the same 1 KB DRAM
+// burst.  No score scratch is touched unless the attention coefficients are requested.  The result differs from the
+// reference's max -> exp -> sum -> divide order only by the rounding of the rescales (<= 1e-6 relative).
+template <int NC, int U>
+__global__ void __launch_bounds__(kGatThreads) gat_online_kernel(const GatParams p) {
+    __shared__ float s_max[kGatWarps][kMaxHeadsFast];
+    __shared__ float s_den[kGatWarps][kMaxHeadsFast];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r = (int64_t)blockIdx.x * kGatWarps + warp;
+    if (r >= p.N) return;
+    const int H = p.H;
+    const int A = H * p.dqk;
+    const int lanes_per_head = p.dqk >> 2;
+    const bool head_leader = (lane & (lanes_per_head - 1)) == 0;
+    const int64_t start = p.rowptr[r];
+    const int deg = (int)(p.rowptr[r + 1] - start);
+    float *att = p.att ? p.att + start * H : nullptr;
+    const bool want_att = p.write_att != 0;
+
+    int ccol[NC];
+    bool cok[NC];
+    float4 q[NC];
+    float mx[NC], den[NC];
+    float acc[NC][4];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        ccol[k] = (lane + 32 * k) * 4;
+        cok[k] = ccol[k] < A;
+        q[k] = cok[k] ? ldg4(p.Q + r * p.ldq + ccol[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        mx[k] = -FLT_MAX;
+        den[k] = 0.0f;
+        acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.0f;
+    }
+    for (int t = 0; t < deg; t += 32) {
+        const int e = t + lane;
+        const int my_c = e < deg ? ld_stream_i32(p.col + start + e) : 0;
+        const int nb = min(32, deg - t);
+        for (int j = 0; j < nb; j += U) {
+            float4 kk[U][NC], vv[U][NC];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int c = __shfl_sync(0xffffffffu, my_c, j + u);
+                const float *krow = p.K + (int64_t)c * p.ldk;
+                const float *vrow = p.V + (int64_t)c * p.ldv;
+#pragma unroll
+                for (int k = 0; k < NC; ++k)
+                    if (j + u < nb && cok[k]) {
+                        kk[u][k] = ldg4(krow + ccol[k]);
+                        vv[u][k] = ldg4(vrow + ccol[k]);
+                    }
+            }
+            float sc[U][NC];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool ok = j + u < nb;       // warp-uniform
+#pragma unroll
+                for (int k = 0; k < NC; ++k) {
+                    float d = 0.0f;
+                    if (ok && cok[k])
+                        d = q[k].x * kk[u][k].x + q[k].y * kk[u][k].y + q[k].z * kk[u][k].z + q[k].w * kk[u][k].w;
+                    for (int off = 1; off < lanes_per_head; off <<= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+                    sc[u][k] = ok ? __fdiv_rn(d, p.scale) : -FLT_MAX;
+                    if (want_att && ok && cok[k] && head_leader) att[(int64_t)(t + j + u) * H + ccol[k] / p.dqk] = sc[u][k];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                float m_new = mx[k];
+#pragma unroll
+                for (int u = 0; u < U; ++u) m_new = fmaxf(m_new, sc[u][k]);
+                const float corr = expf(mx[k] - m_new);        // exp(-huge) = 0 on the first group
+                mx[k] = m_new;
+                den[k] *= corr;
+                acc[k][0] *= corr; acc[k][1] *= corr; acc[k][2] *= corr; acc[k][3] *= corr;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (j + u < nb && cok[k]) {
+                        const float pe = expf(sc[u][k] - m_new);
+                        den[k] += pe;
+                        acc[k][0] = fmaf(pe, vv[u][k].x, acc[k][0]);
+                        acc[k][1] = fmaf(pe, vv[u][k].y, acc[k][1]);
+                        acc[k][2] = fmaf(pe, vv[u][k].z, acc[k][2]);
+                        acc[k][3] = fmaf(pe, vv[u][k].w, acc[k][3]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        if (!cok[k]) continue;
+        const float inv = 1.0f / (den[k] + 1e-8f);
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) b = ldg4(p.bias + ccol[k]);
+        float4 o;
+        o.x = apply_act(acc[k][0] * inv + b.x, p.act);
+        o.y = apply_act(acc[k][1] * inv + b.y, p.act);
+        o.z = apply_act(acc[k][2] * inv + b.z, p.act);
+        o.w = apply_act(acc[k][3] * inv + b.w, p.act);
+        *reinterpret_cast<float4 *>(p.out + r * p.ldo + ccol[k]) = o;
+        if (want_att && head_leader) {
+            s_max[warp][ccol[k] / p.dqk] = mx[k];
+            s_den[warp][ccol[k] / p.dqk] = den[k] + 1e-8f;
+        }
+    }
+    if (want_att) {      // raw scores -> coefficients, flat and coalesced (head of a lane = lane % H)
+        __syncwarp();
+        const float m = s_max[warp][lane & (H - 1)], dn = s_den[warp][lane & (H - 1)];
+        const int total = deg * H;
+        for (int f = 0; f < total; f += 32) {
+            const int idx = f + lane;
+            if (idx < total) att[idx] = __fdiv_rn(expf(att[idx] - m), dn);
+        }
+    }
+}
+
 // ---- generic path: any H / dqk / dv, split or averaged heads (correctness first) --------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -305,6 +426,15 @@ __global__ void __launch_bounds__(kGatThreads) segment_softmax_kernel(const int6
 
 static inline bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
+template <int NC>
+static int launch_gat_online(const GatParams &p, cudaStream_t st) {
+    constexpr int U = NC == 1 ? 4 : 2;
+    const unsigned blocks = (unsigned)ceil_div64(p.N, kGatWarps);
+    gat_online_kernel<NC, U><<<blocks, kGatThreads, 0, st>>>(p);
+    TFGK_LAUNCH_CHECK();
+    return TFGK_OK;
+}
+
 template <int NCK, int NCV>
 static int launch_gat_fast(const GatParams &p, cudaStream_t st) {
     constexpr int U = (NCK + NCV <= 2) ? 4 : 2;
@@ -348,7 +478,8 @@ extern "C" int tfgk_gat_fused_f32(const int64_t *rowptr, const int32_t *col,
     TFGK_CHECK_ARG(act == TFGK_ACT_NONE || act == TFGK_ACT_RELU, "gat: unknown activation %d", act);
     TFGK_CHECK_ARG(scale > 0.0f, "gat: scale must be positive");
     if (N == 0) return TFGK_OK;
-    TFGK_CHECK_ARG(rowptr && col && Q && K && V && att && out, "gat: null pointer");
+    TFGK_CHECK_ARG(rowptr && col && Q && K && V && out, "gat: null pointer");
+    TFGK_CHECK_ARG(att != nullptr || (!write_att), "gat: write_att needs an attention buffer");
     const int A = H * dqk, VW = H * dv;
     const int out_w = split_value_heads ? VW : dv;
     TFGK_CHECK_ARG(ldq >= A && ldk >= A && ldv >= VW && ldo >= out_w, "gat: leading dimension too small");
@@ -364,6 +495,16 @@ extern "C" int tfgk_gat_fused_f32(const int64_t *rowptr, const int32_t *col,
                       dqk <= 128 && dv % 4 == 0 && A <= 512 && VW <= 512 && ldq % 4 == 0 && ldk % 4 == 0 &&
                       ldv % 4 == 0 && ldo % 4 == 0 && aligned16(Q) && aligned16(K) && aligned16(V) && aligned16(out) &&
                       (!bias || aligned16(bias));
+    const char *impl = getenv("TFGK_GAT_IMPL");          // "twopass" forces the reference-order kernel
+    if (fast && dqk == dv && !(impl && impl[0] == 't')) {
+        switch ((A + 127) / 128) {
+            case 1: return launch_gat_online<1>(p, st);
+            case 2: return launch_gat_online<2>(p, st);
+            case 3: return launch_gat_online<3>(p, st);
+            default: return launch_gat_online<4>(p, st);
+        }
+    }
+    if (att == nullptr) return set_error(TFGK_ERR_WORKSPACE, "gat: this shape needs the [E,H] attention scratch buffer");
     if (fast) {
         const int nck = (A + 127) / 128, ncv = (VW + 127) / 128;
         switch (nck) {

@@ -11,6 +11,7 @@
 //
 // Algorithmic bytes per launch: E*(4*D + 4 [+4 weighted]) + N*(4*D + 8).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace tfgk {
 
@@ -166,6 +167,188 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_kernel(const SpmmParams p) 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// TMA variant (D % 4 == 0): the neighbour rows are pulled by the bulk-copy engine (cp.async.bulk, SASS UBLKCP)
+// straight into a per-warp shared-memory ring, 32 rows per stage, completion tracked by an mbarrier transaction
+// count.  A warp owns a block of consecutive destination rows, i.e. a CONTIGUOUS range of CSR edges, and streams
+// that range in 32-edge chunks regardless of row boundaries: chunk j+1 is in flight while chunk j is reduced, so
+// the memory pipe never drains at a row change and no registers are spent on in-flight data.
+// Accumulation order and rounding are identical to spmm_kernel (CSR order, separate mul/add) => same bits.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kBulkChunk = 32;        // edges (= bulk copies) per stage, one per lane
+constexpr int kBulkRowsPerWarp = 32;  // destination rows per warp
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spin > (1u << 28)) __trap();     // a lost transaction becomes a launch failure, never a hang
+    }
+}
+
+template <int NC, bool IS_MAX>
+__global__ void __launch_bounds__(256) spmm_bulk_kernel(const SpmmParams p, int warps_per_cta, uint32_t row_bytes) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // layout: [warps][2 stages][32 rows][row_bytes] then [warps][2] mbarriers
+    const uint32_t stage_bytes = kBulkChunk * row_bytes;
+    uint8_t *my_buf = smem_raw + (size_t)warp * 2 * stage_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)warps_per_cta * 2 * stage_bytes) + warp * 2;
+    const uint32_t bar0 = smem_addr(bars);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    const int64_t r0 = ((int64_t)blockIdx.x * warps_per_cta + warp) * kBulkRowsPerWarp;
+    if (r0 >= p.n_dst) return;
+    const int64_t r1 = min((int64_t)p.n_dst, r0 + kBulkRowsPerWarp);
+    // lane l keeps rowptr[r0+l] and rowptr[r0+l+1] (clamped): ends of the warp's rows, broadcast by shuffle
+    const int64_t rp_lo = p.rowptr[min(r0 + lane, r1)];
+    const int64_t rp_hi = p.rowptr[min(r0 + lane + 1, r1)];
+    const int64_t e_begin = __shfl_sync(0xffffffffu, rp_lo, 0);
+    const int64_t e_end = p.rowptr[r1];
+    const int n_edges = (int)(e_end - e_begin);
+    const int n_chunks = (n_edges + kBulkChunk - 1) / kBulkChunk;
+    const bool weighted = p.w != nullptr;
+    const uint32_t buf_addr = smem_addr(my_buf);
+
+    float wreg[2] = {1.0f, 1.0f};
+    auto issue = [&](int j) {
+        const int stage = j & 1;
+        const int e = j * kBulkChunk + lane;
+        const int nb = min(kBulkChunk, n_edges - j * kBulkChunk);
+        const uint32_t bar = bar0 + 8 * stage;
+        if (lane == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)nb * row_bytes) : "memory");
+        float wv = 1.0f;
+        if (e < n_edges) {
+            const int c = ld_stream_i32(p.col + e_begin + e);
+            if (weighted) wv = ld_stream_f32(p.w + e_begin + e);
+            const float *src = p.h + (int64_t)c * p.ldh;
+            const uint32_t dst = buf_addr + stage * stage_bytes + lane * row_bytes;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(src), "r"(row_bytes), "r"(bar) : "memory");
+        }
+        wreg[stage] = wv;
+    };
+
+    int coff[NC];
+    bool cok[NC];
+    float acc[NC][4];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        coff[k] = (lane + 32 * k) * 4;
+        cok[k] = coff[k] < p.D;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) acc[k][x] = IS_MAX ? -FLT_MAX : 0.0f;
+    }
+
+    int64_t r = r0;
+    int64_t row_end = __shfl_sync(0xffffffffu, rp_hi, 0) - e_begin;   // end of row r, relative to e_begin
+    const bool is_mean = p.reduce == TFGK_REDUCE_MEAN;
+
+    auto finalize_row = [&]() {
+        const int64_t row_start = __shfl_sync(0xffffffffu, rp_lo, (int)(r - r0));
+        const int deg = (int)(row_end + e_begin - row_start);
+        const float cnt = (float)max(deg, 1);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            if (cok[k]) {
+                float ad[4], bs[4], o[4];
+                if (p.addend) load_vec<4>(p.addend + r * p.ld_addend + coff[k], ad);
+                if (p.bias) load_vec<4>(p.bias + coff[k], bs);
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    float a = acc[k][x];
+                    if (is_mean) a = __fdiv_rn(a, cnt);
+                    if (p.addend) a = __fadd_rn(__fmul_rn(a, p.alpha), __fmul_rn(ad[x], p.beta));
+                    else if (p.alpha != 1.0f) a = __fmul_rn(a, p.alpha);
+                    if (p.bias) a = __fadd_rn(a, bs[x]);
+                    o[x] = apply_act(a, p.act);
+                    acc[k][x] = IS_MAX ? -FLT_MAX : 0.0f;
+                }
+                store_vec<4>(p.out + r * p.ldo + coff[k], o);
+            }
+        }
+        ++r;
+        if (r < r1) row_end = __shfl_sync(0xffffffffu, rp_hi, (int)(r - r0)) - e_begin;
+    };
+
+    if (n_chunks > 0) issue(0);
+    for (int j = 0; j < n_chunks; ++j) {
+        __syncwarp();                                   // every lane is done reading the stage issue(j+1) overwrites
+        if (j + 1 < n_chunks) issue(j + 1);
+        const int stage = j & 1;
+        mbar_wait_parity(bar0 + 8 * stage, (uint32_t)(j >> 1) & 1u);
+        const int nb = min(kBulkChunk, n_edges - j * kBulkChunk);
+        const uint8_t *sbuf = my_buf + stage * stage_bytes;
+        const float wmine = wreg[stage];
+        for (int i = 0; i < nb; ++i) {
+            const int64_t e = (int64_t)j * kBulkChunk + i;
+            while (e == row_end) finalize_row();        // also steps over empty rows
+            const float we = __shfl_sync(0xffffffffu, wmine, i);
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                if (cok[k]) {
+                    const float4 v = *reinterpret_cast<const float4 *>(sbuf + (size_t)i * row_bytes + coff[k] * 4);
+                    const float m0 = __fmul_rn(v.x, we), m1 = __fmul_rn(v.y, we), m2 = __fmul_rn(v.z, we), m3 = __fmul_rn(v.w, we);
+                    acc[k][0] = IS_MAX ? fmaxf(acc[k][0], m0) : __fadd_rn(acc[k][0], m0);
+                    acc[k][1] = IS_MAX ? fmaxf(acc[k][1], m1) : __fadd_rn(acc[k][1], m1);
+                    acc[k][2] = IS_MAX ? fmaxf(acc[k][2], m2) : __fadd_rn(acc[k][2], m2);
+                    acc[k][3] = IS_MAX ? fmaxf(acc[k][3], m3) : __fadd_rn(acc[k][3], m3);
+                }
+            }
+        }
+    }
+    while (r < r1) finalize_row();                      // last row and trailing empty rows
+}
+
+static int spmm_impl_choice() {
+    // 0 = register-staged LDG gather, 1 = TMA bulk gather.  TFGK_SPMM_IMPL overrides (read per call: cheap).
+    const char *e = getenv("TFGK_SPMM_IMPL");
+    if (e && e[0] == 'b') return 1;
+    return 0;      // measured on B200 (profiles/r1_kernel_variants.json): 512 B bulk copies are TMA-issue bound
+}
+
+template <int NC>
+static int launch_spmm_bulk(const SpmmParams &p, cudaStream_t st) {
+    const uint32_t row_bytes = (uint32_t)p.D * 4u;
+    const size_t per_warp = 2u * kBulkChunk * row_bytes + 16;
+    int warps = (int)((220 * 1024) / per_warp);
+    if (warps > 8) warps = 8;
+    if (warps < 1) return TFGK_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)warps * per_warp;
+    const int64_t rows_per_cta = (int64_t)warps * kBulkRowsPerWarp;
+    const unsigned blocks = (unsigned)ceil_div64(p.n_dst, rows_per_cta);
+    if (p.reduce == TFGK_REDUCE_MAX) {
+        TFGK_CUDA(cudaFuncSetAttribute(spmm_bulk_kernel<NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        spmm_bulk_kernel<NC, true><<<blocks, warps * 32, smem, st>>>(p, warps, row_bytes);
+    } else {
+        TFGK_CUDA(cudaFuncSetAttribute(spmm_bulk_kernel<NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        spmm_bulk_kernel<NC, false><<<blocks, warps * 32, smem, st>>>(p, warps, row_bytes);
+    }
+    TFGK_LAUNCH_CHECK();
+    return TFGK_OK;
+}
+
+static int dispatch_spmm_bulk(const SpmmParams &p, cudaStream_t st) {
+    const int lanes = (p.D + 3) / 4;
+    if (lanes <= 32) return launch_spmm_bulk<1>(p, st);
+    if (lanes <= 64) return launch_spmm_bulk<2>(p, st);
+    if (lanes <= 96) return launch_spmm_bulk<3>(p, st);
+    return launch_spmm_bulk<4>(p, st);
+}
+
 template <int VEC, int G, int NC, int U>
 static int launch_spmm(const SpmmParams &p, cudaStream_t st) {
     constexpr int rows_per_block = (kSpmmThreads / 32) * (32 / G);
@@ -222,6 +405,10 @@ extern "C" int tfgk_spmm_f32(const int64_t *rowptr, const int32_t *col, const fl
         p.bias = bias ? bias + c0 : nullptr; p.act = act;
         p.out = out + c0; p.ldo = ldo;
         const int lanes = (p.D + vec - 1) / vec;
+        if (vec4 && p.D >= 32 && spmm_impl_choice() == 1) {
+            const int rcb = dispatch_spmm_bulk(p, as_stream(stream));
+            if (rcb != TFGK_ERR_UNSUPPORTED) { if (rcb != TFGK_OK) return rcb; continue; }
+        }
         const int rc = vec4 ? dispatch_spmm<4>(p, lanes, as_stream(stream)) : dispatch_spmm<1>(p, lanes, as_stream(stream));
         if (rc != TFGK_OK) return rc;
     }

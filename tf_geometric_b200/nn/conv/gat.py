@@ -40,11 +40,17 @@ def gat(x, edge_index,
                  bias=ops.as_device(query_bias, torch.float32, device=dev), act=q_act)
     if q_left is not None:
         Q = q_left(Q)
-    K = ops.gemm(x, ops.as_device(key_kernel, torch.float32, device=dev),
-                 bias=ops.as_device(key_bias, torch.float32, device=dev), act=k_act)
+    # K and V are projected into ONE [N, A + U] buffer: the fused kernel then fetches a neighbour's key and value
+    # from the same DRAM burst (and the multi-GPU path ships them in a single all-gather)
+    wk = ops.as_device(key_kernel, torch.float32, device=dev)
+    wv = ops.as_device(kernel, torch.float32, device=dev)
+    a_units = wk.shape[1]
+    kv = torch.empty((num_nodes, a_units + wv.shape[1]), dtype=torch.float32, device=dev)
+    K, V = kv[:, :a_units], kv[:, a_units:]
+    ops.gemm(x, wk, bias=ops.as_device(key_bias, torch.float32, device=dev), act=k_act, out=K)
     if k_left is not None:
-        K = k_left(K)
-    V = ops.gemm(x, ops.as_device(kernel, torch.float32, device=dev))
+        K.copy_(k_left(K))
+    ops.gemm(x, wv, out=V)
 
     act_code, leftover = ops.activation_code(activation)
     bias = None if bias is None else ops.as_device(bias, torch.float32, device=dev)

@@ -209,15 +209,29 @@ def gat_fused(csr, Q, K, V, num_heads, split_value_heads=True, bias=None, act=AC
     if out is None:
         out = torch.empty((N, out_w), dtype=torch.float32, device=Q.device)
     att = att_buffer
-    if att is None or att.numel() < csr.nnz * H:
+    if att is not None and att.numel() < csr.nnz * H:
+        att = None
+    if att is None and return_attention:
         att = torch.empty((csr.nnz, H), dtype=torch.float32, device=Q.device)
     if bias is not None:
         _check(bias, torch.float32, "bias")
     # gat.py:78  scale = sqrt(cast(shape(Q_)[-1], float32))
     scale = float(np.sqrt(np.float32(dqk)))
-    _ffi.call("tfgk_gat_fused_f32", _p(csr.rowptr), _p(csr.col), _p(Q), _row_major_2d(Q, "Q"), _p(K),
-              _row_major_2d(K, "K"), _p(V), _row_major_2d(V, "V"), N, H, dqk, dv, scale, 1 if split_value_heads else 0,
-              _p(bias), act, _p(att), 1 if return_attention else 0, _p(out), _row_major_2d(out, "out"), _stream(Q))
+
+    def launch(att_buf):
+        _ffi.call("tfgk_gat_fused_f32", _p(csr.rowptr), _p(csr.col), _p(Q), _row_major_2d(Q, "Q"), _p(K),
+                  _row_major_2d(K, "K"), _p(V), _row_major_2d(V, "V"), N, H, dqk, dv, scale,
+                  1 if split_value_heads else 0, _p(bias), act, _p(att_buf), 1 if return_attention else 0, _p(out),
+                  _row_major_2d(out, "out"), _stream(Q))
+
+    try:
+        launch(att)
+    except _ffi.TfgkError as err:
+        # the single-pass kernel needs no scratch; the two-pass / generic kernels ask for an [E, H] score buffer
+        if err.code != _ffi.ERR_WORKSPACE or att is not None:
+            raise
+        att = torch.empty((csr.nnz, H), dtype=torch.float32, device=Q.device)
+        launch(att)
     if return_attention:
         return out, att[:csr.nnz]
     return out
