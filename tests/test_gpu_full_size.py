@@ -118,5 +118,6 @@ def test_gat_full_size_attention_is_a_distribution_and_rows_match(big):
         want = c_oracle.gat_core(np.zeros(m, np.int32), np.arange(1, m + 1, dtype=np.int32), loc_q, loc_k, loc_v, H)[0]
         got = out[r].cpu().numpy()
         assert np.all(np.abs(got - want) <= 2e-5 * np.abs(want) + 2e-6 * np.abs(want).max()), (r, np.abs(got - want).max())
-    out2 = ops.gat_fused(csr, q, k, h, H)
-    assert torch.equal(out, out2)
+    out2 = ops.gat_fused(csr, q, k, h, H)           # no attention output: the cp.async kernel
+    assert float((out - out2).abs().max()) <= 2e-6 * float(out.abs().max())
+    assert torch.equal(out2, ops.gat_fused(csr, q, k, h, H))       # deterministic

@@ -309,6 +309,152 @@ __global__ void __launch_bounds__(kGatThreads) gat_online_kernel(const GatParams
     }
 }
 
+// ---- single-pass path on a cp.async ring (A == H*dv <= 128) ----------------------------------------------------------
+// Same arithmetic as gat_online_kernel, same memory pipeline as spmm_async_kernel (see spmm.cu): a warp owns
+// kGatAsyncRows consecutive destination rows = one contiguous CSR range and streams it in rounds of U edges; every
+// round is 2*U LDGSTS per lane (the K and the V slice of each neighbour) into a per-warp ring of S stages tracked by
+// commit groups, so (S-1)*U neighbour pairs are always in flight per warp at 64 registers.  The online softmax is
+// updated per edge (one expf), which lets a round straddle row boundaries.
+constexpr int kGatAsyncRows = 32;
+constexpr int kGatAsyncWarps = 4;
+
+__device__ __forceinline__ void gat_cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+template <int U, int S>
+__global__ void __launch_bounds__(kGatAsyncWarps * 32) gat_async_kernel(const GatParams p) {
+    static_assert(32 % U == 0, "a round must not straddle an index chunk");
+    constexpr int RPC = 32 / U;
+    static_assert(S <= RPC, "index chunk refill assumes the prologue stays inside chunk 0");
+    extern __shared__ __align__(16) uint8_t gat_ring[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r0 = ((int64_t)blockIdx.x * kGatAsyncWarps + warp) * kGatAsyncRows;
+    if (r0 >= p.N) return;
+    const int64_t r1 = min((int64_t)p.N, r0 + kGatAsyncRows);
+    const int64_t rp_hi = p.rowptr[min(r0 + lane + 1, r1)];
+    const int64_t e_begin = p.rowptr[r0];
+    const int n_edges = (int)(p.rowptr[r1] - e_begin);
+    const int n_rounds = (n_edges + U - 1) / U;
+    const int A = p.H * p.dqk;
+    const int lanes_per_head = p.dqk >> 2;
+    const int ccol = lane * 4;
+    const bool cok = ccol < A;
+    const uint32_t row_bytes = (uint32_t)A * 4u;
+    const uint32_t stage_bytes = 2u * U * row_bytes;          // [U][K slice row | V slice row]
+    uint8_t *my_ring = gat_ring + (size_t)warp * S * stage_bytes;
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(my_ring);
+
+    int64_t r = r0;
+    int row_end = (int)(__shfl_sync(0xffffffffu, rp_hi, 0) - e_begin);
+    float4 q = cok ? ldg4(p.Q + r * p.ldq + ccol) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 q_next = (cok && r + 1 < r1) ? ldg4(p.Q + (r + 1) * p.ldq + ccol) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float mx = -FLT_MAX, den = 0.0f, a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias && cok) bias = ldg4(p.bias + ccol);
+
+    auto finalize_row = [&]() {
+        if (cok) {
+            const float inv = 1.0f / (den + 1e-8f);
+            float4 o;
+            o.x = apply_act(a0 * inv + bias.x, p.act);
+            o.y = apply_act(a1 * inv + bias.y, p.act);
+            o.z = apply_act(a2 * inv + bias.z, p.act);
+            o.w = apply_act(a3 * inv + bias.w, p.act);
+            *reinterpret_cast<float4 *>(p.out + r * p.ldo + ccol) = o;
+        }
+        mx = -FLT_MAX; den = 0.0f; a0 = a1 = a2 = a3 = 0.0f;
+        ++r;
+        q = q_next;
+        if (r < r1) {
+            row_end = (int)(__shfl_sync(0xffffffffu, rp_hi, (int)(r - r0)) - e_begin);
+            if (cok && r + 1 < r1) q_next = ldg4(p.Q + (r + 1) * p.ldq + ccol);
+        }
+    };
+    auto load_chunk = [&](int c) {
+        const int e = c * 32 + lane;
+        return e < n_edges ? ld_stream_i32(p.col + e_begin + e) : 0;
+    };
+    auto issue = [&](int g, int ci) {
+        if (g < n_rounds) {
+            const int base = (g % RPC) * U;
+            const uint32_t dst0 = ring_addr + (uint32_t)(g % S) * stage_bytes;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int c = __shfl_sync(0xffffffffu, ci, base + u);
+                if (g * U + u < n_edges && cok) {
+                    gat_cp_async16(dst0 + (2 * u) * row_bytes + ccol * 4, p.K + (int64_t)c * p.ldk + ccol);
+                    gat_cp_async16(dst0 + (2 * u + 1) * row_bytes + ccol * 4, p.V + (int64_t)c * p.ldv + ccol);
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    int ca = load_chunk(0), cb = load_chunk(1);
+#pragma unroll
+    for (int g = 0; g < S - 1; ++g) issue(g, ca);
+
+    for (int g = 0; g < n_rounds; ++g) {
+        {
+            const int gn = g + S - 1;
+            issue(gn, ((gn / RPC) & 1) ? cb : ca);
+        }
+        asm volatile("cp.async.wait_group %0;" ::"n"(S - 1) : "memory");
+        const uint8_t *sbuf = my_ring + (size_t)(g % S) * stage_bytes;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = g * U + u;
+            if (e < n_edges) {
+                while (e == row_end) finalize_row();
+                float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+                if (cok) {
+                    kk = *reinterpret_cast<const float4 *>(sbuf + (size_t)(2 * u) * row_bytes + ccol * 4);
+                    vv = *reinterpret_cast<const float4 *>(sbuf + (size_t)(2 * u + 1) * row_bytes + ccol * 4);
+                }
+                float d = q.x * kk.x + q.y * kk.y + q.z * kk.z + q.w * kk.w;
+                for (int off = 1; off < lanes_per_head; off <<= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+                const float s = __fdiv_rn(d, p.scale);
+                // one exponential per edge: the new maximum is either s (rescale the running sums) or mx (scale the term)
+                const bool up = s > mx;
+                const float t = expf(up ? mx - s : s - mx);
+                const float corr = up ? t : 1.0f, pe = up ? 1.0f : t;
+                mx = up ? s : mx;
+                den = fmaf(den, corr, pe);
+                a0 = fmaf(a0, corr, pe * vv.x);
+                a1 = fmaf(a1, corr, pe * vv.y);
+                a2 = fmaf(a2, corr, pe * vv.z);
+                a3 = fmaf(a3, corr, pe * vv.w);
+            }
+        }
+        if ((g + S) % RPC == 0) {                 // the last round of chunk `dead` has been issued: refill its register
+            const int dead = (g + S) / RPC - 1;
+            if (dead & 1) cb = load_chunk(dead + 2); else ca = load_chunk(dead + 2);
+        }
+    }
+    while (r < r1) finalize_row();
+}
+
+template <int U, int S>
+static int launch_gat_async(const GatParams &p, cudaStream_t st) {
+    const size_t smem = (size_t)kGatAsyncWarps * S * 2 * U * (size_t)(p.H * p.dqk) * 4;
+    TFGK_CUDA(cudaFuncSetAttribute(gat_async_kernel<U, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned blocks = (unsigned)ceil_div64(p.N, (int64_t)kGatAsyncWarps * kGatAsyncRows);
+    gat_async_kernel<U, S><<<blocks, kGatAsyncWarps * 32, smem, st>>>(p);
+    TFGK_LAUNCH_CHECK();
+    return TFGK_OK;
+}
+
+static int dispatch_gat_async(const GatParams &p, cudaStream_t st) {
+    const char *cfg = getenv("TFGK_GAT_ASYNC_CFG");        // "UxS"; default 2x3
+    if (cfg && cfg[0] == '4' && cfg[2] == '2') return launch_gat_async<4, 2>(p, st);
+    if (cfg && cfg[0] == '4' && cfg[2] == '3') return launch_gat_async<4, 3>(p, st);
+    if (cfg && cfg[0] == '2' && cfg[2] == '4') return launch_gat_async<2, 4>(p, st);
+    if (cfg && cfg[0] == '2' && cfg[2] == '2') return launch_gat_async<2, 2>(p, st);
+    if (cfg && cfg[0] == '1' && cfg[2] == '4') return launch_gat_async<1, 4>(p, st);
+    return launch_gat_async<2, 3>(p, st);
+}
+
 // ---- generic path: any H / dqk / dv, split or averaged heads (correctness first) --------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -496,6 +642,8 @@ extern "C" int tfgk_gat_fused_f32(const int64_t *rowptr, const int32_t *col,
                       ldv % 4 == 0 && ldo % 4 == 0 && aligned16(Q) && aligned16(K) && aligned16(V) && aligned16(out) &&
                       (!bias || aligned16(bias));
     const char *impl = getenv("TFGK_GAT_IMPL");          // "twopass" forces the reference-order kernel
+    if (fast && dqk == dv && A <= 128 && !write_att && !(impl && (impl[0] == 't' || impl[0] == 'o')))
+        return dispatch_gat_async(p, st);                    // "online" forces the register-staged single-pass kernel
     if (fast && dqk == dv && !(impl && impl[0] == 't')) {
         switch ((A + 127) / 128) {
             case 1: return launch_gat_online<1>(p, st);

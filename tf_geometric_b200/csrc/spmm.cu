@@ -313,11 +313,360 @@ __global__ void __launch_bounds__(256) spmm_bulk_kernel(const SpmmParams p, int 
     while (r < r1) finalize_row();                      // last row and trailing empty rows
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Streaming variant (float4 rows): a warp owns kStreamRows consecutive destination rows = one CONTIGUOUS range of CSR
+// edges, and walks that range in rounds of U edges with two register buffers: the gathers of round g+1 are issued
+// before round g is reduced, and the (col, w) of the next 32-edge chunk are fetched one chunk ahead.  The memory
+// pipe therefore never drains at a row boundary or while indices are being fetched - by Little's law the achieved
+// bandwidth is (bytes in flight) / (loaded latency), and this keeps 8-16 rows in flight per warp all the time instead
+// of 8 for a fraction of it.  Rounding and order are unchanged (CSR order, separate mul/add) => same bits.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kStreamRows = 16;        // destination rows per warp (their finished sums wait in shared memory)
+constexpr int kStreamThreads = 128;
+constexpr int kStreamWarps = kStreamThreads / 32;
+
+template <bool IS_MAX, int U, int MINB>
+__global__ void __launch_bounds__(kStreamThreads, MINB) spmm_stream_kernel(const SpmmParams p) {
+    static_assert(32 % U == 0, "a round must not straddle an index chunk");
+    constexpr int RPC = 32 / U;                 // rounds per 32-edge index chunk
+    __shared__ float4 stash[kStreamWarps][kStreamRows][32];      // finished row sums, one float4 per lane
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r0 = ((int64_t)blockIdx.x * kStreamWarps + warp) * kStreamRows;
+    if (r0 >= p.n_dst) return;
+    const int n_rows = (int)min((int64_t)kStreamRows, (int64_t)p.n_dst - r0);
+    // lane l < n_rows describes row r0 + l
+    const int64_t rp_lo = p.rowptr[r0 + min(lane, n_rows)];
+    const int64_t rp_hi = p.rowptr[r0 + min(lane + 1, n_rows)];
+    const int64_t e_begin = __shfl_sync(0xffffffffu, rp_lo, 0);
+    const int n_edges = (int)(__shfl_sync(0xffffffffu, rp_hi, n_rows - 1) - e_begin);
+    const int my_end = (int)(rp_hi - e_begin);                   // end of row `lane`, relative
+    const int my_deg = (int)(rp_hi - rp_lo);
+    const uint32_t nonempty = __ballot_sync(0xffffffffu, lane < n_rows && my_deg > 0);
+    const bool weighted = p.w != nullptr;
+    const float *__restrict__ h = p.h;
+    const int coff = lane * 4;
+    const bool cok = coff < p.D;
+    const float init = IS_MAX ? -FLT_MAX : 0.0f;
+
+#pragma unroll
+    for (int i = 0; i < kStreamRows; ++i) stash[warp][i][lane] = make_float4(init, init, init, init);
+
+    float a0 = init, a1 = init, a2 = init, a3 = init;
+    int rel = nonempty ? __ffs(nonempty) - 1 : n_rows;           // current (non-empty) row
+    int row_end = rel < n_rows ? __shfl_sync(0xffffffffu, my_end, rel & 31) : -1;
+
+    auto load_chunk = [&](int c, int &ci, float &wi) {
+        const int e = c * 32 + lane;
+        ci = 0;
+        wi = 1.0f;
+        if (e < n_edges) {
+            ci = ld_stream_i32(p.col + e_begin + e);
+            if (weighted) wi = ld_stream_f32(p.w + e_begin + e);
+        }
+    };
+    auto issue = [&](int g, int ci, float4 (&buf)[U]) {
+        const int base = (g % RPC) * U;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int c = __shfl_sync(0xffffffffu, ci, base + u);
+            if (g * U + u < n_edges && cok) buf[u] = __ldg(reinterpret_cast<const float4 *>(h + (int64_t)c * p.ldh + coff));
+        }
+    };
+    auto consume = [&](int g, float wi, const float4 (&buf)[U]) {
+        const int base = (g % RPC) * U;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = g * U + u;
+            const float we = __shfl_sync(0xffffffffu, wi, base + u);
+            if (e < n_edges) {
+                const float m0 = __fmul_rn(buf[u].x, we), m1 = __fmul_rn(buf[u].y, we);
+                const float m2 = __fmul_rn(buf[u].z, we), m3 = __fmul_rn(buf[u].w, we);
+                a0 = IS_MAX ? fmaxf(a0, m0) : __fadd_rn(a0, m0);
+                a1 = IS_MAX ? fmaxf(a1, m1) : __fadd_rn(a1, m1);
+                a2 = IS_MAX ? fmaxf(a2, m2) : __fadd_rn(a2, m2);
+                a3 = IS_MAX ? fmaxf(a3, m3) : __fadd_rn(a3, m3);
+                if (e + 1 == row_end) {          // last edge of the row: park the sum, move to the next non-empty row
+                    stash[warp][rel][lane] = make_float4(a0, a1, a2, a3);
+                    a0 = a1 = a2 = a3 = init;
+                    const uint32_t rest = rel < 31 ? (nonempty >> (rel + 1)) : 0u;
+                    rel = rest ? rel + __ffs(rest) : n_rows;
+                    row_end = rel < n_rows ? __shfl_sync(0xffffffffu, my_end, rel & 31) : -1;
+                }
+            }
+        }
+    };
+
+    float4 buf0[U], buf1[U];
+    int ca, cb;
+    float wa, wb;
+    load_chunk(0, ca, wa);
+    load_chunk(1, cb, wb);
+    issue(0, ca, buf0);
+    const int n_rounds = (n_edges + U - 1) / U;
+    // two rounds per iteration (buf0 <-> buf1); the chunk registers are picked with selects, not by unrolling
+    for (int g = 0; g < n_rounds; g += 2) {
+        {
+            const int cn = (g + 1) / RPC, cc = g / RPC;
+            issue(g + 1, (cn & 1) ? cb : ca, buf1);
+            consume(g, (cc & 1) ? wb : wa, buf0);
+            if ((g + 1) % RPC == 0) { if (cc & 1) load_chunk(cc + 2, cb, wb); else load_chunk(cc + 2, ca, wa); }
+        }
+        {
+            const int cn = (g + 2) / RPC, cc = (g + 1) / RPC;
+            issue(g + 2, (cn & 1) ? cb : ca, buf0);
+            consume(g + 1, (cc & 1) ? wb : wa, buf1);
+            if ((g + 2) % RPC == 0) { if (cc & 1) load_chunk(cc + 2, cb, wb); else load_chunk(cc + 2, ca, wa); }
+        }
+    }
+
+    // epilogue for the warp's rows: uniform loop, coalesced 512-byte stores
+    const bool is_mean = p.reduce == TFGK_REDUCE_MEAN;
+    float bs[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.bias && cok) load_vec<4>(p.bias + coff, bs);
+    for (int i = 0; i < n_rows; ++i) {
+        const float cnt = (float)max(__shfl_sync(0xffffffffu, my_deg, i), 1);     // every lane takes part in the shuffle
+        if (!cok) continue;
+        const float4 v = stash[warp][i][lane];
+        float a[4] = {v.x, v.y, v.z, v.w}, ad[4], o[4];
+        const int64_t r = r0 + i;
+        if (p.addend) load_vec<4>(p.addend + r * p.ld_addend + coff, ad);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            float t = a[x];
+            if (is_mean) t = __fdiv_rn(t, cnt);
+            if (p.addend) t = __fadd_rn(__fmul_rn(t, p.alpha), __fmul_rn(ad[x], p.beta));
+            else if (p.alpha != 1.0f) t = __fmul_rn(t, p.alpha);
+            if (p.bias) t = __fadd_rn(t, bs[x]);
+            o[x] = apply_act(t, p.act);
+        }
+        store_vec<4>(p.out + r * p.ldo + coff, o);
+    }
+}
+
+template <int U, int MINB>
+static int launch_spmm_stream(const SpmmParams &p, cudaStream_t st) {
+    const int64_t rows_per_cta = (int64_t)kStreamWarps * kStreamRows;
+    const unsigned blocks = (unsigned)ceil_div64(p.n_dst, rows_per_cta);
+    if (p.reduce == TFGK_REDUCE_MAX) spmm_stream_kernel<true, U, MINB><<<blocks, kStreamThreads, 0, st>>>(p);
+    else spmm_stream_kernel<false, U, MINB><<<blocks, kStreamThreads, 0, st>>>(p);
+    TFGK_LAUNCH_CHECK();
+    return TFGK_OK;
+}
+
+static int dispatch_spmm_stream(const SpmmParams &p, cudaStream_t st) {
+    if (p.D > 128) return TFGK_ERR_UNSUPPORTED;            // wider rows: the per-row kernel (register budget)
+    const char *cfg = getenv("TFGK_SPMM_STREAM_CFG");     // tuning knob: "8x4" (default), "8x5", "4x8", "16x2"
+    if (cfg && cfg[0] == '4') return launch_spmm_stream<4, 8>(p, st);
+    if (cfg && cfg[0] == '1') return launch_spmm_stream<16, 2>(p, st);
+    if (cfg && cfg[0] == '8' && cfg[2] == '5') return launch_spmm_stream<8, 5>(p, st);
+    return launch_spmm_stream<8, 4>(p, st);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// cp.async variant.  Register double-buffering cannot overlap two gather rounds: a warp has six counting scoreboard
+// slots, ptxas puts the loads of both rounds on the same slots, and the first use of round g then also waits for
+// round g+1 (decoded from SASS, profiles/r1_notes.md).  LDGSTS copies are tracked by commit groups instead, so a
+// per-warp shared-memory ring of S stages x U rows keeps (S-1)*U rows in flight per warp with no register cost.
+// Each lane copies - and later reads back - only its own 16-byte slices: shared memory is used as an asynchronous
+// extension of the register file, no cross-lane traffic, no barriers.  Edge streaming as above: a warp owns
+// kAsyncRows consecutive rows = a contiguous CSR range.  Same rounding and order => same bits.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kAsyncRows = 32;
+constexpr int kAsyncWarps = 4;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NC, bool IS_MAX, int U, int S>
+__global__ void __launch_bounds__(kAsyncWarps * 32) spmm_async_kernel(const SpmmParams p, uint32_t row_bytes) {
+    static_assert(32 % U == 0, "a round must not straddle an index chunk");
+    constexpr int RPC = 32 / U;
+    extern __shared__ __align__(16) uint8_t ring_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r0 = ((int64_t)blockIdx.x * kAsyncWarps + warp) * kAsyncRows;
+    if (r0 >= p.n_dst) return;
+    const int64_t r1 = min((int64_t)p.n_dst, r0 + kAsyncRows);
+    const int64_t rp_lo = p.rowptr[min(r0 + lane, r1)];
+    const int64_t rp_hi = p.rowptr[min(r0 + lane + 1, r1)];
+    const int64_t e_begin = __shfl_sync(0xffffffffu, rp_lo, 0);
+    const int n_edges = (int)(p.rowptr[r1] - e_begin);
+    const int n_rounds = (n_edges + U - 1) / U;
+    const bool weighted = p.w != nullptr;
+    const uint32_t stage_bytes = U * row_bytes;
+    uint8_t *my_ring = ring_raw + (size_t)warp * S * stage_bytes;
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(my_ring);
+
+    int coff[NC];
+    bool cok[NC];
+    float acc[NC][4];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        coff[k] = (lane + 32 * k) * 4;
+        cok[k] = coff[k] < p.D;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) acc[k][x] = IS_MAX ? -FLT_MAX : 0.0f;
+    }
+    int64_t r = r0;
+    int row_end = (int)(__shfl_sync(0xffffffffu, rp_hi, 0) - e_begin);
+    const bool is_mean = p.reduce == TFGK_REDUCE_MEAN;
+
+    auto finalize_row = [&]() {
+        const int64_t row_start = __shfl_sync(0xffffffffu, rp_lo, (int)(r - r0));
+        const int deg = (int)(row_end + e_begin - row_start);
+        const float cnt = (float)max(deg, 1);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            if (cok[k]) {
+                float ad[4], bs[4], o[4];
+                if (p.addend) load_vec<4>(p.addend + r * p.ld_addend + coff[k], ad);
+                if (p.bias) load_vec<4>(p.bias + coff[k], bs);
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    float a = acc[k][x];
+                    if (is_mean) a = __fdiv_rn(a, cnt);
+                    if (p.addend) a = __fadd_rn(__fmul_rn(a, p.alpha), __fmul_rn(ad[x], p.beta));
+                    else if (p.alpha != 1.0f) a = __fmul_rn(a, p.alpha);
+                    if (p.bias) a = __fadd_rn(a, bs[x]);
+                    o[x] = apply_act(a, p.act);
+                    acc[k][x] = IS_MAX ? -FLT_MAX : 0.0f;
+                }
+                store_vec<4>(p.out + r * p.ldo + coff[k], o);
+            }
+        }
+        ++r;
+        if (r < r1) row_end = (int)(__shfl_sync(0xffffffffu, rp_hi, (int)(r - r0)) - e_begin);
+    };
+    auto load_chunk = [&](int c, int &ci, float &wi) {
+        const int e = c * 32 + lane;
+        ci = 0;
+        wi = 1.0f;
+        if (e < n_edges) {
+            ci = ld_stream_i32(p.col + e_begin + e);
+            if (weighted) wi = ld_stream_f32(p.w + e_begin + e);
+        }
+    };
+    // copy round g (edges [g*U, g*U+U)) into ring stage g % S; always commits one group (possibly empty)
+    auto issue = [&](int g, int ci) {
+        if (g < n_rounds) {
+            const int base = (g % RPC) * U;
+            const uint32_t dst0 = ring_addr + (uint32_t)(g % S) * stage_bytes;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int c = __shfl_sync(0xffffffffu, ci, base + u);
+                if (g * U + u < n_edges) {
+                    const float *rowp = p.h + (int64_t)c * p.ldh;
+#pragma unroll
+                    for (int k = 0; k < NC; ++k)
+                        if (cok[k]) cp_async16(dst0 + u * row_bytes + coff[k] * 4, rowp + coff[k]);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    // Index registers (ca: even chunks, cb: odd chunks) are dead once the chunk's last round has been ISSUED; its
+    // weights are needed until that round is CONSUMED, S-1 iterations later: wa/wb serve the consumer, wna/wnb hold the
+    // weights fetched ahead together with the indices (requires S <= 2*RPC, asserted below).
+    static_assert(S <= 2 * RPC, "weight look-ahead registers would be overwritten before they are consumed");
+    int ca, cb;
+    float wa, wb, wna = 1.0f, wnb = 1.0f;
+    load_chunk(0, ca, wa);
+    load_chunk(1, cb, wb);
+    // prologue: S-1 rounds in flight (they all live in chunk 0 / 1 as long as (S-1)*U <= 64)
+#pragma unroll
+    for (int g = 0; g < S - 1; ++g) issue(g, ((g / RPC) & 1) ? cb : ca);
+    if (S - 1 >= RPC) load_chunk(2, ca, wna);       // chunk 0 was issued completely by the prologue
+
+    for (int g = 0; g < n_rounds; ++g) {
+        // keep the pipe full: round g+S-1 goes into the stage consumed in the previous iteration
+        {
+            const int gn = g + S - 1;
+            issue(gn, ((gn / RPC) & 1) ? cb : ca);
+        }
+        cp_async_wait<S - 1>();                     // round g has landed (groups retire in order)
+        const int cc = g / RPC;
+        const float wi = (cc & 1) ? wb : wa;
+        const int base = (g % RPC) * U;
+        const uint8_t *sbuf = my_ring + (size_t)(g % S) * stage_bytes;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = g * U + u;
+            const float we = __shfl_sync(0xffffffffu, wi, base + u);
+            if (e < n_edges) {
+                while (e == row_end) finalize_row();
+#pragma unroll
+                for (int k = 0; k < NC; ++k) {
+                    if (cok[k]) {
+                        const float4 v = *reinterpret_cast<const float4 *>(sbuf + (size_t)u * row_bytes + coff[k] * 4);
+                        const float m0 = __fmul_rn(v.x, we), m1 = __fmul_rn(v.y, we), m2 = __fmul_rn(v.z, we), m3 = __fmul_rn(v.w, we);
+                        acc[k][0] = IS_MAX ? fmaxf(acc[k][0], m0) : __fadd_rn(acc[k][0], m0);
+                        acc[k][1] = IS_MAX ? fmaxf(acc[k][1], m1) : __fadd_rn(acc[k][1], m1);
+                        acc[k][2] = IS_MAX ? fmaxf(acc[k][2], m2) : __fadd_rn(acc[k][2], m2);
+                        acc[k][3] = IS_MAX ? fmaxf(acc[k][3], m3) : __fadd_rn(acc[k][3], m3);
+                    }
+                }
+            }
+        }
+        // the index chunk that the LAST issued round (g+S-1) no longer needs can be refilled: chunk j is dead once
+        // round (j+1)*RPC - 1 has been issued, i.e. when g + S - 1 == (j+1)*RPC - 1
+        if ((g + 1) % RPC == 0) {                   // chunk cc fully consumed: promote the look-ahead weights
+            if (cc & 1) wb = wnb; else wa = wna;
+        }
+        if ((g + S) % RPC == 0) {
+            const int dead = (g + S) / RPC - 1;
+            if (dead & 1) load_chunk(dead + 2, cb, wnb); else load_chunk(dead + 2, ca, wna);
+        }
+    }
+    while (r < r1) finalize_row();
+}
+
+template <int NC, int U, int S>
+static int launch_spmm_async(const SpmmParams &p, cudaStream_t st) {
+    const uint32_t row_bytes = (uint32_t)p.D * 4u;
+    const size_t smem = (size_t)kAsyncWarps * S * U * row_bytes;
+    if (smem > 200 * 1024) return TFGK_ERR_UNSUPPORTED;
+    const unsigned blocks = (unsigned)ceil_div64(p.n_dst, (int64_t)kAsyncWarps * kAsyncRows);
+    if (p.reduce == TFGK_REDUCE_MAX) {
+        TFGK_CUDA(cudaFuncSetAttribute(spmm_async_kernel<NC, true, U, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        spmm_async_kernel<NC, true, U, S><<<blocks, kAsyncWarps * 32, smem, st>>>(p, row_bytes);
+    } else {
+        TFGK_CUDA(cudaFuncSetAttribute(spmm_async_kernel<NC, false, U, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        spmm_async_kernel<NC, false, U, S><<<blocks, kAsyncWarps * 32, smem, st>>>(p, row_bytes);
+    }
+    TFGK_LAUNCH_CHECK();
+    return TFGK_OK;
+}
+
+static int dispatch_spmm_async(const SpmmParams &p, cudaStream_t st) {
+    const int lanes = (p.D + 3) / 4;
+    const char *cfg = getenv("TFGK_SPMM_ASYNC_CFG");      // tuning knob for NC == 1, "UxS"; default 4x3
+    if (lanes <= 32) {
+        if (cfg && cfg[0] == '8' && cfg[2] == '4') return launch_spmm_async<1, 8, 4>(p, st);
+        if (cfg && cfg[0] == '8' && cfg[2] == '2') return launch_spmm_async<1, 8, 2>(p, st);
+        if (cfg && cfg[0] == '8' && cfg[2] == '6') return launch_spmm_async<1, 8, 6>(p, st);
+        if (cfg && cfg[0] == '8' && cfg[2] == '3') return launch_spmm_async<1, 8, 3>(p, st);
+        if (cfg && cfg[0] == '4' && cfg[2] == '4') return launch_spmm_async<1, 4, 4>(p, st);
+        if (cfg && cfg[0] == '4' && cfg[2] == '6') return launch_spmm_async<1, 4, 6>(p, st);
+        if (cfg && cfg[0] == '2' && cfg[2] == '6') return launch_spmm_async<1, 2, 6>(p, st);
+        if (cfg && cfg[0] == '2' && cfg[2] == '4') return launch_spmm_async<1, 2, 4>(p, st);
+        return launch_spmm_async<1, 4, 3>(p, st);      // 99% of the measured HBM peak at D=128 (profiles/r1_kernel_variants_spmm_async.json)
+    }
+    if (lanes <= 64) return launch_spmm_async<2, 4, 4>(p, st);
+    if (lanes <= 96) return launch_spmm_async<3, 4, 3>(p, st);
+    return launch_spmm_async<4, 2, 4>(p, st);
+}
+
 static int spmm_impl_choice() {
     // 0 = register-staged LDG gather, 1 = TMA bulk gather.  TFGK_SPMM_IMPL overrides (read per call: cheap).
     const char *e = getenv("TFGK_SPMM_IMPL");
     if (e && e[0] == 'b') return 1;
-    return 0;      // measured on B200 (profiles/r1_kernel_variants.json): 512 B bulk copies are TMA-issue bound
+    if (e && e[0] == 's') return 2;
+    if (e && e[0] == 'l') return 0;
+    return 3;      // cp.async ring (default); "ldg" / "stream" / "bulk" select the measured alternatives      // measured on B200 (profiles/r1_kernel_variants.json): 512 B bulk copies are TMA-issue bound
 }
 
 template <int NC>
@@ -405,6 +754,14 @@ extern "C" int tfgk_spmm_f32(const int64_t *rowptr, const int32_t *col, const fl
         p.bias = bias ? bias + c0 : nullptr; p.act = act;
         p.out = out + c0; p.ldo = ldo;
         const int lanes = (p.D + vec - 1) / vec;
+        if (vec4 && p.D >= 32 && spmm_impl_choice() == 3) {
+            const int rca = dispatch_spmm_async(p, as_stream(stream));
+            if (rca != TFGK_ERR_UNSUPPORTED) { if (rca != TFGK_OK) return rca; continue; }
+        }
+        if (vec4 && p.D >= 32 && spmm_impl_choice() == 2) {
+            const int rcs = dispatch_spmm_stream(p, as_stream(stream));
+            if (rcs != TFGK_ERR_UNSUPPORTED) { if (rcs != TFGK_OK) return rcs; continue; }
+        }
         if (vec4 && p.D >= 32 && spmm_impl_choice() == 1) {
             const int rcb = dispatch_spmm_bulk(p, as_stream(stream));
             if (rcb != TFGK_ERR_UNSUPPORTED) { if (rcb != TFGK_OK) return rcb; continue; }

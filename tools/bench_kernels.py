@@ -55,25 +55,40 @@ def timed(fn, label, nbytes=None):
 D = B.UNITS
 spmm_bytes = csr.nnz * (4 * D + 8) + n * (4 * D + 8)
 out = torch.empty((n, D), device=dev)
-for impl in ("ldg", "bulk"):
+ref_out = None
+for impl, cfg in (("ldg", ""), ("async", "4x3"), ("async", "8x2")):
     os.environ["TFGK_SPMM_IMPL"] = impl
-    timed(lambda: ops.spmm(csr, w, h, out=out), "spmm_D128_" + impl, spmm_bytes)
-    timed(lambda: ops.spmm(csr, None, x, reduce="mean"), "spmm_mean_D100_" + impl,
+    os.environ["TFGK_SPMM_ASYNC_CFG"] = cfg
+    tag = impl + ("_" + cfg if cfg else "")
+    timed(lambda: ops.spmm(csr, w, h, out=out), "spmm_D128_" + tag, spmm_bytes)
+    if ref_out is None:
+        ref_out = out.clone()
+    else:
+        assert torch.equal(out, ref_out), "variant {} changed the bits".format(tag)
+    timed(lambda: ops.spmm(csr, None, x, reduce="mean"), "spmm_mean_D100_" + tag,
           csr.nnz * (4 * 100 + 4) + n * (4 * 100 + 8))
 os.environ.pop("TFGK_SPMM_IMPL")
+os.environ.pop("TFGK_SPMM_ASYNC_CFG")
 
 q = torch.randn((n, D), generator=gen, device=dev)
 kv = torch.randn((n, 2 * D), generator=gen, device=dev)
 k_sep, v_sep = kv[:, :D].contiguous(), kv[:, D:].contiguous()
 gat_bytes = csr.nnz * (8 * D + 4) + n * (8 * D + 8)
 att = torch.empty((csr.nnz, B.HEADS), device=dev)
-os.environ["TFGK_GAT_IMPL"] = "twopass"
-timed(lambda: ops.gat_fused(csr, q, k_sep, v_sep, B.HEADS, att_buffer=att), "gat_twopass_separate", gat_bytes)
+os.environ["TFGK_GAT_IMPL"] = "online"
+timed(lambda: ops.gat_fused(csr, q, kv[:, :D], kv[:, D:], B.HEADS), "gat_online_ldg_interleaved", gat_bytes)
+ref_gat = ops.gat_fused(csr, q, kv[:, :D], kv[:, D:], B.HEADS).clone()
 os.environ.pop("TFGK_GAT_IMPL")
-timed(lambda: ops.gat_fused(csr, q, k_sep, v_sep, B.HEADS), "gat_online_separate", gat_bytes)
-timed(lambda: ops.gat_fused(csr, q, kv[:, :D], kv[:, D:], B.HEADS), "gat_online_interleaved", gat_bytes)
-timed(lambda: ops.gat_fused(csr, q, kv[:, :D], kv[:, D:], B.HEADS, return_attention=True, att_buffer=att),
-      "gat_online_interleaved_with_att", gat_bytes)
+for cfg in ("2x3", "4x2", "4x3", "2x4", "2x2", "1x4"):
+    os.environ["TFGK_GAT_ASYNC_CFG"] = cfg
+    timed(lambda: ops.gat_fused(csr, q, kv[:, :D], kv[:, D:], B.HEADS), "gat_async_interleaved_" + cfg, gat_bytes)
+    got = ops.gat_fused(csr, q, kv[:, :D], kv[:, D:], B.HEADS)
+    err = float((got - ref_gat).abs().max() / ref_gat.abs().max())
+    print("   max rel diff vs online ldg:", err, flush=True)
+    assert err < 1e-5
+os.environ["TFGK_GAT_ASYNC_CFG"] = "2x3"
+timed(lambda: ops.gat_fused(csr, q, k_sep, v_sep, B.HEADS), "gat_async_separate_2x3", gat_bytes)
+os.environ.pop("TFGK_GAT_ASYNC_CFG")
 
 wmat = B.glorot((B.FEATURES, B.UNITS), 2).to(dev)
 gemm_bytes = 4 * (n * B.FEATURES + B.FEATURES * B.UNITS + n * B.UNITS)
