@@ -11,7 +11,7 @@ from tf_geometric_b200 import ops
 from conftest import assert_close
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("TFGK_GEMM_TC") != "1", reason="tensor-core GEMM is opt-in: TFGK_GEMM_TC=1")]
+              pytest.mark.skipif(os.environ.get("TFGK_GEMM_TC") == "0", reason="tensor-core GEMM disabled by TFGK_GEMM_TC=0")]
 
 
 def dev(a):

@@ -5,9 +5,9 @@
 //   * fp32-accurate via the 3xTF32 split: a = hi + lo with hi = rna_tf32(a), lo = a - hi (exact);
 //     D += Ahi*Bhi + Ahi*Blo + Alo*Bhi  (the dropped lo*lo term is ~2^-22 relative)  => ~1e-6 relative error, well
 //     inside the 1e-4 parity gate that single-pass TF32 (~1e-3) would fail (SURVEY.md section 7 "hard parts")
-//   * operands are staged by all threads: coalesced 16 B global loads -> hi/lo split in registers -> st.shared in the
-//     canonical K-major, no-swizzle UMMA layout (8-row x 16 B core matrices; LBO = 128 B along K, SBO = 1024 B along M/N)
-//     W is transposed on the fly (it is [K,N] row-major, the MMA wants K-major) - it is tiny and L2 resident
+//   * A streams through a cp.async ring straight into the canonical K-major, no-swizzle UMMA layout (8-row x 16 B core
+//     matrices; LBO = 128 B along K, SBO = 1024 B along M); the raw fp32 tile IS the hi operand (hardware truncation) and
+//     only lo = a - trunc(a) is computed by the CUDA cores.  W ([K,N] row-major) is transposed, split and kept resident
 //   * one elected thread issues the MMAs; tcgen05.commit -> mbarrier releases the smem stage / publishes the accumulator
 //   * persistent CTAs: the epilogue of tile i (tcgen05.ld -> +bias -> act -> global) overlaps the MMAs of tile i+1
 // The kernel is memory bound (4(MK+MN) bytes for ~6MNK tf32 flops at K~100): the tensor pipe is lightly loaded by design.
@@ -20,7 +20,6 @@ namespace tc {
 constexpr int BM = 128;            // UMMA_M
 constexpr int BK = 32;             // K elements per smem stage (8 core matrices of 16 B along K)
 constexpr int UMMA_K = 8;          // tf32
-constexpr int kStages = 2;
 constexpr int kThreads = 256;
 constexpr int kMaxUN = 256;
 constexpr int kTmemCols = 512;
@@ -102,51 +101,122 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, float x, float y, fl
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
 
-// smem carve-up (dynamic): per stage  Ahi | Alo (16 KB each) | Bhi | Blo (un*128 B each); then barriers
-struct SmemLayout {
-    uint32_t a_bytes, b_bytes, stage_bytes, total;
-    __host__ __device__ explicit SmemLayout(int un) {
-        a_bytes = BM * BK * 4;
-        b_bytes = (uint32_t)un * BK * 4;
-        stage_bytes = 2 * a_bytes + 2 * b_bytes;
-        total = kStages * stage_bytes + 64;
+// ---- shared memory plan ------------------------------------------------------------------------------------------------
+//   W resident for the whole kernel, already split:  Bhi | Blo, each UN x Kpad fp32 in K-major core-matrix order
+//        element (n, k) at  (n/8)*SBO_B + (k/4)*128 + (n%8)*16 + (k%4)*4 ,  SBO_B = (Kpad/4)*128
+//   A ring of S stages, one 128 x 32 k-block per stage:  Araw | Alo (16 KB each), chunk c = rg*64 + kc*8 + r8 at 16*c
+//        Araw is written by cp.async straight from global memory and used AS the hi operand (the tensor core ignores the
+//        low 13 mantissa bits of a tf32 operand, i.e. hi = trunc(a)); Alo = a - trunc(a) is produced in place by the thread
+//        that issued the copy, so no cross-thread hand-off precedes the conversion.
+struct SmemPlan {
+    uint32_t kpad, b_bytes, a_stage_bytes, stages, total;
+    __host__ __device__ SmemPlan(int un, int K) {
+        kpad = (uint32_t)((K + BK - 1) / BK) * BK;
+        b_bytes = (uint32_t)un * kpad * 4u;
+        a_stage_bytes = 2u * BM * BK * 4u;
+        const uint32_t budget = 227u * 1024u - 256u;
+        stages = 0;
+        for (uint32_t st = 3; st >= 2; --st)
+            if (2u * b_bytes + st * a_stage_bytes + 128u <= budget) { stages = st; break; }
+        total = 2u * b_bytes + stages * a_stage_bytes + 128u;
     }
 };
 
-template <bool VEC_A>
+__device__ __forceinline__ uint64_t make_desc_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(128u >> 4) << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+template <int STAGES>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const SmemLayout L(p.un);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * L.stage_bytes);   // [0..kStages): stage free, then 2: acc full
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + kStages + 2);
+    const SmemPlan L(p.un, p.K);
+    uint8_t *b_hi_ptr = smem, *b_lo_ptr = smem + L.b_bytes;
+    uint8_t *a_ring = smem + 2 * L.b_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(a_ring + STAGES * L.a_stage_bytes);   // [STAGES] stage free, [2] acc full
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + STAGES + 2);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
 
     if (t == 0) {
-        for (int i = 0; i < kStages + 2; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < STAGES + 2; ++i) mbar_init(&bars[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // ---- W: transpose + RNA split, once per CTA ----
+    {
+        const int kchunks = (int)L.kpad / 4;
+        const int total = p.un * kchunks;
+        const uint32_t bh = smem_u32(b_hi_ptr), bl = smem_u32(b_lo_ptr);
+        for (int cb = t; cb < total; cb += kThreads) {
+            const int n8 = cb & 7, kc = (cb >> 3) % kchunks, ng = (cb >> 3) / kchunks;
+            const int n = ng * 8 + n8, k = kc * 4;
+            float w[4] = {0.f, 0.f, 0.f, 0.f}, h[4], l[4];
+            if (n < p.N) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (k + i < p.K) w[i] = __ldg(p.B + (int64_t)(k + i) * p.ldb + n);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_tf32(w[i], h[i], l[i]);
+            st_shared_v4(bh + cb * 16, h[0], h[1], h[2], h[3]);
+            st_shared_v4(bl + cb * 16, l[0], l[1], l[2], l[3]);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t idesc = make_idesc(p.un);
-    const int nkb = (p.K + BK - 1) / BK;
-    const int b_chunks = p.un * (BK / 4);          // 16-byte chunks of one B operand stage
+    const int nkb = (int)L.kpad / BK;
+    const uint32_t sbo_b = (L.kpad / 4) * 128u;
+    const int my_tiles = blockIdx.x < p.tiles_m ? (p.tiles_m - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int total_kb = my_tiles * nkb;
+    const uint32_t a_ring_addr = smem_u32(a_ring);
 
-    uint32_t g = 0;                                // global k-block counter (stage ring position)
-    int it = 0;                                    // tiles processed by this CTA
-    int prev_tile = -1;
+    auto issue_load = [&](int G) {
+        if (G < total_kb) {
+            const int stage = G % STAGES;
+            if (G >= STAGES) mbar_wait(&bars[stage], (uint32_t)((G / STAGES - 1) & 1));   // MMAs that read this stage retired
+            const int tile = blockIdx.x + (G / nkb) * gridDim.x, kb = G % nkb;
+            const int64_t m0 = (int64_t)tile * BM;
+            const uint32_t dst0 = a_ring_addr + stage * L.a_stage_bytes;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = t + kThreads * i;
+                const int r8 = c & 7, kc = (c >> 3) & 7, rg = c >> 6;
+                const int64_t row = m0 + rg * 8 + r8;
+                const int k = kb * BK + kc * 4;
+                uint32_t bytes = 0;
+                const float *src = p.A;
+                if (row < p.M && k < p.K) {
+                    bytes = (uint32_t)min(4, p.K - k) * 4u;
+                    src = p.A + row * p.lda + k;
+                }
+                cp_async16_zfill(dst0 + c * 16, src, bytes);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
 
     auto epilogue = [&](int tile, int buf, uint32_t use) {
-        mbar_wait(&bars[kStages + buf], use & 1u);
+        mbar_wait(&bars[STAGES + buf], use & 1u);
         tc_fence_after();
         const int q = warp & 3, half = warp >> 2;
         const int64_t row = (int64_t)tile * BM + q * 32 + lane;
         const int col_begin = half * (p.un / 2), col_end = (half + 1) * (p.un / 2);
+        const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
         for (int c0 = col_begin; c0 < col_end; c0 += 8) {
             uint32_t r[8];
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kMaxUN + c0);
@@ -155,105 +225,77 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const Params p
                          : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (row < p.M) {
-                float *dst = p.C + row * p.ldc + c0;
+                float v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    if (c0 + j < p.N) {
-                        float v = __uint_as_float(r[j]);
-                        if (p.bias) v += __ldg(p.bias + c0 + j);
-                        dst[j] = apply_act(v, p.act);
-                    }
+                    v[j] = __uint_as_float(r[j]);
+                    if (p.bias && c0 + j < p.N) v[j] += __ldg(p.bias + c0 + j);
+                    v[j] = apply_act(v[j], p.act);
+                }
+                float *dst = p.C + row * p.ldc + c0;
+                if (vec_ok && c0 + 8 <= p.N) {
+                    *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4 *>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (c0 + j < p.N) dst[j] = v[j];
                 }
             }
         }
         tc_fence_before();
     };
 
-    for (int tile = blockIdx.x; tile < p.tiles_m; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const int64_t m0 = (int64_t)tile * BM;
-        for (int kb = 0; kb < nkb; ++kb, ++g) {
-            const uint32_t stage = g % kStages;
-            const uint32_t use = g / kStages;
-            if (use > 0) mbar_wait(&bars[stage], (use - 1) & 1u);      // MMAs that read this stage have retired
-            uint8_t *sbase = smem + stage * L.stage_bytes;
-            const uint32_t a_hi = smem_u32(sbase), a_lo = a_hi + L.a_bytes;
-            const uint32_t b_hi = a_lo + L.a_bytes, b_lo = b_hi + L.b_bytes;
-            const int k0 = kb * BK;
+#pragma unroll
+    for (int G = 0; G < STAGES - 1; ++G) issue_load(G);
 
-            // ---- A: 128 rows x 32 floats = 1024 chunks of 16 B; chunk c -> smem offset 16*c (rg*1024 + kc*128 + r8*16)
-            float4 av[4];
+    int prev_tile = -1;
+    for (int G = 0; G < total_kb; ++G) {
+        issue_load(G + STAGES - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+        const int stage = G % STAGES;
+        const int it = G / nkb, kb = G % nkb;             // CTA-local tile counter, k-block within the tile
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int buf = it & 1;
+        uint8_t *sraw = a_ring + stage * L.a_stage_bytes;
+        uint8_t *slo = sraw + BM * BK * 4;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int c = t + kThreads * i;
-                const int r8 = c & 7, kc = (c >> 3) & 7, rg = c >> 6;
-                const int64_t row = m0 + rg * 8 + r8;
-                const int k = k0 + kc * 4;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row < p.M && k < p.K) {
-                    const float *src = p.A + row * p.lda + k;
-                    if (VEC_A && k + 3 < p.K) {
-                        v = __ldg(reinterpret_cast<const float4 *>(src));
-                    } else {
-                        v.x = __ldg(src);
-                        if (k + 1 < p.K) v.y = __ldg(src + 1);
-                        if (k + 2 < p.K) v.z = __ldg(src + 2);
-                        if (k + 3 < p.K) v.w = __ldg(src + 3);
-                    }
-                }
-                av[i] = v;
-            }
-            // ---- B: un rows (n) x 32 floats (k), transposed on the fly from W[k][n]
-            for (int cb = t; cb < b_chunks; cb += kThreads) {
-                const int n8 = cb & 7, kc = (cb >> 3) & 7, ng = cb >> 6;
-                const int n = ng * 8 + n8;
-                const int k = k0 + kc * 4;
-                float w[4] = {0.f, 0.f, 0.f, 0.f};
-                if (n < p.N) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (k + i < p.K) w[i] = __ldg(p.B + (int64_t)(k + i) * p.ldb + n);
-                }
-                float h[4], l[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) split_tf32(w[i], h[i], l[i]);
-                st_shared_v4(b_hi + cb * 16, h[0], h[1], h[2], h[3]);
-                st_shared_v4(b_lo + cb * 16, l[0], l[1], l[2], l[3]);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int c = t + kThreads * i;
-                float h[4], l[4];
-                split_tf32(av[i].x, h[0], l[0]);
-                split_tf32(av[i].y, h[1], l[1]);
-                split_tf32(av[i].z, h[2], l[2]);
-                split_tf32(av[i].w, h[3], l[3]);
-                st_shared_v4(a_hi + c * 16, h[0], h[1], h[2], h[3]);
-                st_shared_v4(a_lo + c * 16, l[0], l[1], l[2], l[3]);
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-            tc_fence_before();
-            __syncthreads();
-            if (t == 0) {
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kMaxUN);
-#pragma unroll
-                for (int j = 0; j < BK / UMMA_K; ++j) {
-                    const uint32_t off = (uint32_t)j * 2u * 128u;          // two 16-byte core matrices along K per MMA
-                    const uint64_t dah = make_desc(a_hi + off), dal = make_desc(a_lo + off);
-                    const uint64_t dbh = make_desc(b_hi + off), dbl = make_desc(b_lo + off);
-                    umma_tf32(d_tmem, dal, dbh, idesc, (kb | j) != 0);     // small terms first, the hi*hi term last
-                    umma_tf32(d_tmem, dah, dbl, idesc, 1u);
-                    umma_tf32(d_tmem, dah, dbh, idesc, 1u);
-                }
-                umma_commit(&bars[stage]);                                 // frees the smem stage when these MMAs retire
-                if (kb == nkb - 1) umma_commit(&bars[kStages + buf]);      // accumulator of this tile complete
-            }
+        for (int i = 0; i < 4; ++i) {                       // lo = a - trunc_tf32(a), on the chunks this thread copied itself
+            const int c = t + kThreads * i;
+            const float4 v = *reinterpret_cast<const float4 *>(sraw + c * 16);
+            float4 l;
+            l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+            l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+            l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+            l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+            *reinterpret_cast<float4 *>(slo + c * 16) = l;
         }
-        if (prev_tile >= 0) epilogue(prev_tile, buf ^ 1, (uint32_t)((it - 1) >> 1));
-        prev_tile = tile;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        __syncthreads();
+        if (t == 0) {
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kMaxUN);
+            const uint32_t a_raw = smem_u32(sraw), a_lo = a_raw + BM * BK * 4;
+            const uint32_t b_hi = smem_u32(b_hi_ptr) + (uint32_t)kb * (BK / 4) * 128u, b_lo = b_hi + L.b_bytes;
+#pragma unroll
+            for (int j = 0; j < BK / UMMA_K; ++j) {
+                const uint32_t off = (uint32_t)j * 2u * 128u;
+                const uint64_t dah = make_desc_sbo(a_raw + off, 1024u), dal = make_desc_sbo(a_lo + off, 1024u);
+                const uint64_t dbh = make_desc_sbo(b_hi + off, sbo_b), dbl = make_desc_sbo(b_lo + off, sbo_b);
+                umma_tf32(d_tmem, dal, dbh, idesc, (kb | j) != 0);
+                umma_tf32(d_tmem, dah, dbl, idesc, 1u);
+                umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+            }
+            umma_commit(&bars[stage]);
+            if (kb == nkb - 1) umma_commit(&bars[STAGES + buf]);
+        }
+        if (kb == nkb - 1) {
+            if (prev_tile >= 0) epilogue(prev_tile, buf ^ 1, (uint32_t)((it - 1) >> 1));
+            prev_tile = tile;
+        }
     }
-    if (prev_tile >= 0) epilogue(prev_tile, (it - 1) & 1, (uint32_t)((it - 1) >> 1));
+    if (prev_tile >= 0) epilogue(prev_tile, (my_tiles - 1) & 1, (uint32_t)((my_tiles - 1) >> 1));
 
     __syncthreads();
     if (warp == 0) {
@@ -268,29 +310,30 @@ using namespace tfgk;
 
 extern "C" int tfgk_gemm_tc_f32(const float *A, int64_t lda, const float *B, int64_t ldb, const float *bias, int act,
                                 int32_t M, int32_t N, int32_t K, float *C, int64_t ldc, void *stream) {
-    // Opt-in (TFGK_GEMM_TC=1) until the TMA-fed version lands: this register-staged variant is correct but latency
-    // bound (profiles/r1_kernel_variants.json).  K <= 512: tensor-core accumulation truncates (round-toward-zero), so
-    // the error grows ~K^1.5; at K <= 512 it stays below 5e-6 relative, beyond that the exact-fp32 SIMT path is used.
+    // Default path for the forward projections; TFGK_GEMM_TC=0 forces the exact-fp32 SIMT kernel.
+    // K <= 512: tensor-core accumulation truncates (round-toward-zero), so the error grows ~K^1.5; up to K = 512 it stays
+    // below 5e-6 relative (tests/test_gpu_gemm_tc.py), beyond that the SIMT path is used.
     const char *env = getenv("TFGK_GEMM_TC");
-    const bool enabled = env != nullptr && env[0] == '1';
+    const bool enabled = !(env != nullptr && env[0] == '0');
     if (!enabled || N > tc::kMaxUN || M < 1 || K < 1 || K > 512 || (int64_t)M * K < (1 << 14)) return TFGK_ERR_UNSUPPORTED;
     tc::Params p;
     p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.bias = bias; p.act = act;
     p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc;
     p.un = ((N + 15) / 16) * 16;
     p.tiles_m = (int)ceil_div64(M, tc::BM);
-    const tc::SmemLayout L(p.un);
+    if ((lda % 4 != 0) || !aligned16(A)) return TFGK_ERR_UNSUPPORTED;       // cp.async moves 16-byte chunks
+    const tc::SmemPlan L(p.un, K);
+    if (L.stages == 0) return TFGK_ERR_UNSUPPORTED;                         // W does not fit next to two A stages
     int dev = 0, sms = 0;
     TFGK_CUDA(cudaGetDevice(&dev));
     TFGK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = p.tiles_m < sms ? p.tiles_m : sms;       // persistent: one CTA per SM
-    const bool vec_a = (lda % 4 == 0) && aligned16(A);
-    if (vec_a) {
-        TFGK_CUDA(cudaFuncSetAttribute(tc::gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-        tc::gemm_tf32x3_kernel<true><<<grid, tc::kThreads, L.total, as_stream(stream)>>>(p);
+    if (L.stages == 3) {
+        TFGK_CUDA(cudaFuncSetAttribute(tc::gemm_tf32x3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+        tc::gemm_tf32x3_kernel<3><<<grid, tc::kThreads, L.total, as_stream(stream)>>>(p);
     } else {
-        TFGK_CUDA(cudaFuncSetAttribute(tc::gemm_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-        tc::gemm_tf32x3_kernel<false><<<grid, tc::kThreads, L.total, as_stream(stream)>>>(p);
+        TFGK_CUDA(cudaFuncSetAttribute(tc::gemm_tf32x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+        tc::gemm_tf32x3_kernel<2><<<grid, tc::kThreads, L.total, as_stream(stream)>>>(p);
     }
     TFGK_LAUNCH_CHECK();
     return TFGK_OK;
