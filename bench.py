@@ -46,7 +46,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (testing only; 1.0 = BASELINE size)")
-    ap.add_argument("--cpu-sample-div", type=int, default=25, help="reference arm: graph scaled down by this factor")
+    ap.add_argument("--cpu-sample-div", type=int, default=0,
+                    help="reference arm: graph scaled down by this factor (0 = auto: about two minutes of CPU work in total)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -77,54 +78,66 @@ def glorot(shape, seed):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML in a background thread every
+    ~2 ms (nvidia-smi -lms cannot resolve a 50 ms region); falls back to one nvidia-smi query if NVML is unavailable."""
 
     def __init__(self, index):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.stop_flag = False
+        self.thread = None
+        self.nvml = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.thread = threading.Thread(target=self._loop, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
+            self.nvml = None
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _loop(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                try:
+                    reasons = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    reasons = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                power = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                self.samples.append((sm, reasons, power))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.nvml is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self.stop_flag = True
+        self.thread.join(timeout=1.0)
+        n = self.nvml
+        smax = None
         try:
-            self.proc.wait(timeout=2)
+            smax = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
         except Exception:
-            self.proc.kill()
-        sm, smax, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0])); smax.append(float(parts[1])); power.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+            pass
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80}
+        seen = set()
+        for _, r, _ in self.samples:
+            for k, bit in names.items():
+                if r & bit:
+                    seen.add(k)
+        sm = [x[0] for x in self.samples]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "power_w_max": max([x[2] for x in self.samples]) if self.samples else None,
+                "samples": len(sm), "reasons": sorted(seen)}
 
 
 def measured_peak_gbs():
@@ -179,9 +192,20 @@ def cpu_model_name():
     return "unknown"
 
 
+def cpu_sample_div(args, passes):
+    """Bounded sample for the CPU arm: the op-for-op port sustains ~0.6 M edges/s on the box's host cores (measured), so
+    `passes` step executions of the full graph would take hours; scale the graph so the whole arm takes ~2 minutes."""
+    if args.cpu_sample_div > 0:
+        return args.cpu_sample_div
+    budget_edges = 0.6e6 * 120.0                       # edge-layer passes affordable in ~120 s
+    per_step_full = 4.0 * PRODUCTS_UNDIRECTED * args.scale
+    return max(25, int(np.ceil(per_step_full * passes / budget_edges)))
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    args.cpu_sample_div = cpu_sample_div(args, args.steps + args.warmup)
     n = max(int(PRODUCTS_NODES * args.scale) // args.cpu_sample_div, 1000)
     pairs = max(int(PRODUCTS_UNDIRECTED * args.scale) // args.cpu_sample_div, 1000)
     res = cpu_reference(n, pairs, args.steps, args.warmup)
@@ -209,6 +233,61 @@ def workload_config(args, world):
 
 
 # ---- our arm -----------------------------------------------------------------------------------------------------------
+
+def run_e2e(args, device, x_host, step_fn, n_out_rows, edges_per_layer, barrier=None):
+    """Host-to-host throughput of the same step: every step copies its input features from pinned host memory and lands
+    both layer outputs in pinned host memory.  The three engines are pipelined the way a serving loop would do it:
+    H2D of step i+1 and D2H of step i's outputs run on their own streams while step i / i+1 compute; device and host
+    buffers are double buffered and every dependency is an event.  All copies are inside the timed region."""
+    s_in, s_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    main = torch.cuda.current_stream(device)
+    outs = [[torch.empty((n_out_rows, UNITS), dtype=torch.float32).pin_memory() for _ in range(2)] for _ in range(2)]
+    x_dev = [torch.empty(x_host.shape, dtype=torch.float32, device=device) for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]       # x_dev[slot] no longer read by compute
+    ev_out_done = [torch.cuda.Event() for _ in range(2)]   # host output slot drained (previous use)
+
+    def submit(i):
+        slot = i & 1
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_free[slot])
+            x_dev[slot].copy_(x_host, non_blocking=True)
+            ev_in[slot].record(s_in)
+        main.wait_event(ev_in[slot])
+        a, b = step_fn(x_dev[slot])                          # public layer API, GCN then GAT
+        ev_free[slot].record(main)
+        ev_done = torch.cuda.Event()
+        ev_done.record(main)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_done)
+            s_out.wait_event(ev_out_done[slot])
+            outs[slot][0].copy_(a, non_blocking=True)
+            outs[slot][1].copy_(b, non_blocking=True)
+            ev_out_done[slot].record(s_out)
+        a.record_stream(s_out)
+        b.record_stream(s_out)
+
+    for slot in range(2):
+        ev_free[slot].record(main)
+        ev_out_done[slot].record(s_out)
+    for i in range(2):
+        submit(i)
+    torch.cuda.synchronize(device)
+    if barrier is not None:
+        barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(main)
+    for i in range(args.steps):
+        submit(i)
+    main.wait_stream(s_out)                                  # the last outputs have landed on the host
+    main.wait_stream(s_in)
+    t1.record(main)
+    torch.cuda.synchronize(device)
+    ms = t0.elapsed_time(t1) / args.steps
+    return {"value": 2.0 * edges_per_layer / (ms * 1e-3), "unit": "edges/s", "ms_per_step": ms,
+            "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 2 * n_out_rows * UNITS * 4,
+            "pipelining": "H2D / compute / D2H on three streams, double buffered, all inside the timed region"}
+
 
 def run_ours(args, rank, world, local_rank):
     import tf_geometric_b200 as tfg
@@ -279,10 +358,13 @@ def run_ours(args, rank, world, local_rank):
     spmm_bytes = e_loop * (4 * UNITS + 4 + 4) + n * (4 * UNITS + 8)
     peak, peak_src = measured_peak_gbs()
     achieved = gat_bytes / (gat_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "gat_fast_kernel (tfgk_gat_fused_f32)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+    roofline = {"bound": "hbm", "kernel": "gat_async_kernel<2,3> (tfgk_gat_fused_f32)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
+                # (profiles/r1_ncu_full_final_kernels.json); only valid for the default full-size workload
+                "traffic": 128184537000 if args.scale == 1.0 else None, "peak_source": peak_src,
                 "algorithmic_bytes": gat_bytes, "kernel_ms": gat_ms,
-                "secondary": {"kernel": "spmm_kernel (tfgk_spmm_f32)", "algorithmic_bytes": spmm_bytes,
+                "secondary": {"kernel": "spmm_async_kernel<1,0,4,3> (tfgk_spmm_f32)", "traffic": 63515602000 if args.scale == 1.0 else None, "algorithmic_bytes": spmm_bytes,
                               "kernel_ms": spmm_ms, "achieved": spmm_bytes / (spmm_ms * 1e-3) / 1e9,
                               "frac": spmm_bytes / (spmm_ms * 1e-3) / 1e9 / peak},
                 "gemm_ms_per_step": gemm_ms}
@@ -290,30 +372,11 @@ def run_ours(args, rank, world, local_rank):
     # ---- end to end: host buffers in, host buffers out, through the same public API ----
     e2e = None
     if not args.no_e2e:
-        out_a = torch.empty((n, UNITS), dtype=torch.float32).pin_memory()
-        out_b = torch.empty((n, UNITS), dtype=torch.float32).pin_memory()
-
-        def e2e_step():
-            xd = x_host.to(device, non_blocking=True)
-            a, b = step(xd)
-            out_a.copy_(a, non_blocking=True)
-            out_b.copy_(b, non_blocking=True)
-
-        for _ in range(2):
-            e2e_step()
-        torch.cuda.synchronize()
-        ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        ev2[0].record()
-        for _ in range(args.steps):
-            e2e_step()
-        ev2[1].record()
-        torch.cuda.synchronize()
-        ms_e2e = ev2[0].elapsed_time(ev2[1]) / args.steps
-        e2e = {"value": 2.0 * E / (ms_e2e * 1e-3), "unit": "edges/s", "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": (out_a.numel() + out_b.numel()) * 4}
+        e2e = run_e2e(args, device, x_host, lambda xd: step(xd), n, E)
 
     cpu_base = None
     if not args.no_cpu_baseline:
+        args.cpu_sample_div = cpu_sample_div(args, 2)
         ns = max(n // args.cpu_sample_div, 1000)
         ps = max(pairs // args.cpu_sample_div, 1000)
         res = cpu_reference(ns, ps, steps=1, warmup=1)

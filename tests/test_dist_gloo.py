@@ -54,6 +54,10 @@ def _worker(rank, world, port, n, seed, renorm, queue):
         x_local = x[p.lo:p.hi]
         gcn_local = tdist.gcn_partitioned(pg, x_local, k, b, ops.relu, renorm=renorm)
         gat_local = tdist.gat_partitioned(pg, x_local, wq, bq, ops.relu, wk, bk, ops.relu, wv, b, ops.relu, num_heads=heads)
+        both = tdist.gcn_gat_overlapped(pg, x_local, k, b, ops.relu, wq, bq, wk, bk, wv, b, ops.relu, heads)
+        if renorm:      # the overlapped step uses the default normalisation
+            assert np.array_equal(both[0].numpy(), gcn_local.numpy())
+        assert np.array_equal(both[1].numpy(), gat_local.numpy())
         queue.put((rank, p.lo, p.hi, gcn_local.numpy(), gat_local.numpy()))
         dist.barrier()
     finally:
