@@ -156,3 +156,43 @@ def test_appnp(k, alpha):
     want = o.appnp(x, ei, w, [p["kernel_0"], p["kernel_1"]], [p["bias_0"], p["bias_1"]], o.relu, None, k=k, alpha=alpha)
     assert_close(host(out), want, what="APPNP layer")
     assert "gcn_normed_adj_both_True_True_True_False" in g.cache
+
+
+@pytest.mark.parametrize("kind,weighted,concat", [("mean", False, True), ("mean", True, False), ("sum", True, True)])
+def test_graph_sage_forward_backward(kind, weighted, concat):
+    """BASELINE config 4 semantics at test size: loss = sum(out * G); gradients w.r.t. x, both kernels and the bias
+    against torch-CPU autograd over the reference's op sequence (gather -> gcn_mapper -> unsorted_segment_mean -> matmuls),
+    which is what TensorFlow's GradientTape differentiates in demo/demo_graph_sage.py:100-106."""
+    rs = np.random.RandomState(17)
+    n, f, u = 3000, 100, 64
+    ei = random_graph(n, 40000, seed=23, isolated=6, hub=(11, 3000))
+    w = (rs.rand(ei.shape[1]) + 0.1).astype(np.float32) if weighted else None
+    x = rs.randn(n, f).astype(np.float32)
+    ws, wn = glorot(rs, f, u), glorot(rs, f, u)
+    b = rs.randn(2 * u if concat else u).astype(np.float32)
+    G = rs.randn(n, 2 * u if concat else u).astype(np.float32)
+
+    # reference: op-for-op on torch CPU with autograd
+    tx, tws, twn, tb = (torch.tensor(a, requires_grad=True) for a in (x, ws, wn, b))
+    row, col = torch.from_numpy(ei[0]).long(), torch.from_numpy(ei[1]).long()
+    msg = tx.index_select(0, col)
+    if weighted:
+        msg = msg * torch.from_numpy(w).unsqueeze(1)
+    agg = torch.zeros((n, f)).index_add_(0, row, msg)
+    if kind == "mean":
+        agg = agg / torch.bincount(row, minlength=n).clamp(min=1).to(torch.float32).unsqueeze(1)
+    left, right = tx @ tws, agg @ twn
+    h = torch.relu((torch.cat([left, right], 1) if concat else left + right) + tb)
+    (h * torch.from_numpy(G)).sum().backward()
+
+    dx, dws, dwn, db = (dev(a).requires_grad_(True) for a in (x, ws, wn, b))
+    fn = tfg.nn.mean_graph_sage if kind == "mean" else tfg.nn.sum_graph_sage
+    out = fn(dx, dev(ei), dev(w), dws, dwn, db, tfg.nn.relu, concat=concat)
+    assert out.requires_grad
+    assert_close(host(out), h.detach().numpy(), what="sage fwd (autograd path)")
+    (out * dev(G)).sum().backward()
+    for name, got, want in (("dx", dx.grad, tx.grad), ("dWs", dws.grad, tws.grad), ("dWn", dwn.grad, twn.grad),
+                            ("db", db.grad, tb.grad)):
+        assert_close(host(got), want.numpy(), what="sage " + name)
+    # isolated nodes only receive gradient through the self path
+    assert np.isfinite(host(dx.grad)).all()

@@ -1,0 +1,82 @@
+# coding=utf-8
+"""Backward passes for the GraphSAGE path (mean/sum_graph_sage forward + backward; the reference gets
+them from TensorFlow autodiff, demo/demo_graph_sage.py:100-106).
+
+    d(unsorted_segment_mean(x[col] * w, row)) / dx  =  scatter-add by col of  (w_e / max(cnt[row_e], 1)) * g[row_e]
+
+i.e. the SAME gather - edge-apply - segment-reduce kernel (tfgk_spmm_f32) run on the TRANSPOSED structure (a CSC = the
+destination-sorted CSR of the reversed edges) with rescaled weights; it is built once per edge list and memoised next
+to the forward CSR.  Dense layers: dX = dY W^T and dW = X^T dY are tfgk_gemm_f32 with transposes (deterministic split-K
+over the node dimension), db = 1^T dY through the same kernel.
+"""
+import torch
+
+from . import ops, _structure
+
+
+def _transposed_structure(edge_index, num_nodes, edge_weight, mean, csr):
+    """(csr_t, w_t): CSR of the reversed edges and w_e / max(cnt[row_e], 1) (or w_e for sum) in its order."""
+    tag = ("csc", int(num_nodes), bool(mean), None if edge_weight is None else id(edge_weight))
+    hit = _structure._lookup(edge_index, tag)
+    if hit is not None and (edge_weight is None or hit[2] == edge_weight._version):
+        return hit[0], hit[1]
+    row, col = edge_index[0].contiguous(), edge_index[1].contiguous()
+    csr_t = ops.csr_build(col, row, num_nodes, num_nodes)
+    w = edge_weight if edge_weight is not None else torch.ones((edge_index.shape[1],), dtype=torch.float32,
+                                                               device=edge_index.device)
+    if mean:
+        cnt = (csr.rowptr[1:] - csr.rowptr[:-1]).clamp(min=1).to(torch.float32)
+        w = ops.scale_edges(row, None, w, dl=torch.reciprocal(cnt))
+    w_t = ops.permute(w.contiguous(), csr_t.perm)
+    _structure._store(edge_index, tag, (csr_t, w_t, None if edge_weight is None else edge_weight._version))
+    return csr_t, w_t
+
+
+class NeighborAggregate(torch.autograd.Function):
+    """agg = REDUCE_{e: row_e = r} w_e x[col_e]  (sum | mean), differentiable w.r.t. x."""
+
+    @staticmethod
+    def forward(ctx, x, edge_index, edge_weight, reduce, num_nodes):
+        csr, _ = _structure.csr_for_edge_index(edge_index, num_nodes)
+        w_csr = None if edge_weight is None else _structure.weights_in_csr_order(edge_weight, csr)
+        ctx.saved = (edge_index, edge_weight, reduce, num_nodes, csr)
+        return ops.spmm(csr, w_csr, x.detach(), reduce=reduce)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        edge_index, edge_weight, reduce, num_nodes, csr = ctx.saved
+        csr_t, w_t = _transposed_structure(edge_index, num_nodes, edge_weight, reduce == "mean", csr)
+        grad_x = ops.spmm(csr_t, w_t, grad_out.contiguous(), reduce="sum")
+        return grad_x, None, None, None, None
+
+
+class Dense(torch.autograd.Function):
+    """y = act(x @ W + b) with act in {None, relu}; dX, dW, db through tfgk_gemm_f32."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act_code):
+        y = ops.gemm(x.detach(), weight.detach(), bias=None if bias is None else bias.detach(), act=act_code)
+        ctx.save_for_backward(x, weight, y if act_code == ops.ACT_RELU else None)
+        ctx.has_bias = bias is not None
+        ctx.act_code = act_code
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        x, weight, y = ctx.saved_tensors
+        g = grad_y.contiguous()
+        if ctx.act_code == ops.ACT_RELU:
+            g = g * (y > 0).to(g.dtype)                      # elementwise mask (torch: plumbing, not a hot op)
+        grad_x = grad_w = grad_b = None
+        if ctx.needs_input_grad[0]:
+            grad_x = ops.gemm(g, weight.detach(), trans_b=True)
+        if ctx.needs_input_grad[1]:
+            grad_w = ops.gemm(x.detach(), g, trans_a=True)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            ones = torch.ones((g.shape[0], 1), dtype=torch.float32, device=g.device)
+            grad_b = ops.gemm(ones, g, trans_a=True).reshape(-1)
+        return grad_x, grad_w, grad_b, None
+
+
+def needs_grad(*tensors):
+    return torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in tensors)

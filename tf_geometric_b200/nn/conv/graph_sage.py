@@ -9,7 +9,7 @@ is replaced by ones in the gcn / pool variants (graph_sage.py:139-140,190-191,25
 """
 import torch
 
-from ... import ops, _structure
+from ... import ops, _structure, autograd
 from .gcn import gcn_norm_edge
 from ...sparse import SparseMatrix
 
@@ -51,11 +51,38 @@ def _project_pair(x, agg, self_kernel, neighbor_kernel, bias, activation, concat
     return out
 
 
+def _plain_sage_autograd(reduce, x, edge_index, edge_weight, ws, wn, bias, activation, concat, normalize):
+    """Training path (any input requires grad): the same kernels wrapped in autograd Functions (autograd.py)."""
+    num_nodes = x.shape[0]
+    act_code, leftover = ops.activation_code(activation)
+    agg = autograd.NeighborAggregate.apply(x, edge_index, edge_weight, reduce, num_nodes)
+    if concat:
+        u = ws.shape[1]
+        left = autograd.Dense.apply(x, ws, None if bias is None else bias[:u], act_code)
+        right = autograd.Dense.apply(agg, wn, None if bias is None else bias[u:], act_code)
+        h = torch.cat([left, right], dim=1)
+    else:
+        h = autograd.Dense.apply(x, ws, None, ops.ACT_NONE) + autograd.Dense.apply(agg, wn, bias, ops.ACT_NONE)
+        if act_code == ops.ACT_RELU:
+            h = torch.relu(h)
+    if leftover is not None:
+        h = leftover(h)
+    if normalize:
+        h = h * torch.rsqrt(torch.clamp((h * h).sum(dim=-1, keepdim=True), min=1e-12))
+    return h
+
+
 def _plain_sage(reduce, x, edge_index, edge_weight, self_kernel, neighbor_kernel, bias, activation, concat, normalize):
     edge_index = ops.as_device(edge_index, torch.int32)
     dev = edge_index.device
     x = ops.as_device(x, torch.float32, device=dev)
     num_nodes = x.shape[0]
+    if autograd.needs_grad(x, self_kernel, neighbor_kernel, bias):
+        ew = None if edge_weight is None else ops.as_device(edge_weight, torch.float32, device=dev)
+        return _plain_sage_autograd(reduce, x, edge_index, ew, ops.as_device(self_kernel, torch.float32, device=dev),
+                                    ops.as_device(neighbor_kernel, torch.float32, device=dev),
+                                    None if bias is None else ops.as_device(bias, torch.float32, device=dev),
+                                    activation, concat, normalize)
     csr, _ = _structure.csr_for_edge_index(edge_index, num_nodes)
     w_csr = None
     if edge_weight is not None:
