@@ -603,6 +603,98 @@ def appnp(x, edge_index, edge_weight, kernels, biases, dense_activation=relu, ac
 
 
 # --------------------------------------------------------------------------------------------------------------
+# nn/conv/{sgc,ssgc,tagcn,gin,le_conv}.py  
+# --------------------------------------------------------------------------------------------------------------
+
+def sgc(x, edge_index, edge_weight, k, kernel, bias=None, activation=None, renorm=True, improved=False):
+    """nn/conv/sgc.py:10-61."""
+    x = _as_f32(x)
+    n = x.shape[0]
+    normed = gcn_norm_adj(SparseMatrix(edge_index, edge_weight, [n, n]), renorm=renorm, improved=improved)
+    h = (x @ _as_f32(kernel)).astype(F32)
+    for _ in range(k):
+        h = normed.matmul(h)
+    if bias is not None:
+        h = h + _as_f32(bias)
+    if activation is not None:
+        h = activation(h)
+    return h.astype(F32)
+
+
+def ssgc(x, edge_index, edge_weight, kernels=None, biases=None, k=10, alpha=0.1, dense_activation=relu, activation=None):
+    """nn/conv/ssgc.py:11-99 at inference."""
+    h = _as_f32(x)
+    n = h.shape[0]
+    normed = gcn_norm_adj(SparseMatrix(edge_index, edge_weight, [n, n]))
+    if kernels is not None:
+        nd = len(kernels)
+        for i, (kern, b) in enumerate(zip(kernels, biases)):
+            h = (h @ _as_f32(kern)).astype(F32)
+            if b is not None:
+                h = h + _as_f32(b)
+            if i < nd - 1 and dense_activation is not None:
+                h = dense_activation(h)
+    h = h.astype(F32)
+    output = (h * F32(alpha)).astype(F32)
+    for _ in range(k):
+        h = normed.matmul(h)
+        output = (output + (F32(1 - alpha) * h / F32(k)).astype(F32)).astype(F32)
+    if activation is not None:
+        output = activation(output)
+    return output.astype(F32)
+
+
+def tagcn(x, edge_index, edge_weight, k, kernel, bias=None, activation=None, renorm=False, improved=False):
+    """nn/conv/tagcn.py:10-51."""
+    x = _as_f32(x)
+    n = x.shape[0]
+    normed = gcn_norm_adj(SparseMatrix(edge_index, edge_weight, [n, n]), renorm=renorm, improved=improved)
+    xs = [x]
+    for _ in range(k):
+        xs.append(normed.matmul(xs[-1]))
+    out = (np.concatenate(xs, axis=-1) @ _as_f32(kernel)).astype(F32)
+    if bias is not None:
+        out = out + _as_f32(bias)
+    if activation is not None:
+        out = activation(out)
+    return out.astype(F32)
+
+
+def gin(x, edge_index, mlp_model, eps=0.0):
+    """nn/conv/gin.py:11-38."""
+    x = _as_f32(x)
+    n = x.shape[0]
+    neighbor_h = SparseMatrix(edge_index, None, [n, n]).matmul(x)
+    h = (x * F32(1.0 + eps) + neighbor_h).astype(F32)
+    return mlp_model(h)
+
+
+def le_conv(x, edge_index, edge_weight, self_kernel, self_bias, aggr_self_kernel, aggr_self_bias,
+            aggr_neighbor_kernel, aggr_neighbor_bias, activation=None):
+    """nn/conv/le_conv.py:5-52 - both aggregation terms are gathered by `col` (:40-41), literally."""
+    x = _as_f32(x)
+    edge_index = np.asarray(edge_index, dtype=I32)
+    if edge_weight is None:
+        edge_weight = np.ones([edge_index.shape[1]], dtype=F32)
+    n = x.shape[0]
+    self_h = (x @ _as_f32(self_kernel)).astype(F32)
+    if self_bias is not None:
+        self_h = self_h + _as_f32(self_bias)
+    aggr_self_h = (x @ _as_f32(aggr_self_kernel)).astype(F32)
+    if aggr_self_bias is not None:
+        aggr_self_h = aggr_self_h + _as_f32(aggr_self_bias)
+    aggr_neighbor_h = (x @ _as_f32(aggr_neighbor_kernel)).astype(F32)
+    if aggr_neighbor_bias is not None:
+        aggr_neighbor_h = aggr_neighbor_h + _as_f32(aggr_neighbor_bias)
+    row, col = edge_index
+    rep = ((aggr_self_h[col] - aggr_neighbor_h[col]) * _as_f32(edge_weight)[:, None]).astype(F32)
+    h = self_h + unsorted_segment_sum(rep, row, n)
+    if activation is not None:
+        h = activation(h)
+    return h.astype(F32)
+
+
+# --------------------------------------------------------------------------------------------------------------
 # float64 dense model used by property tests (NOT a restatement: an independent cross-check of the oracle)
 # --------------------------------------------------------------------------------------------------------------
 

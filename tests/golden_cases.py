@@ -59,7 +59,7 @@ class ProductApi(object):
         for name in ("aggregate_neighbors", "identity_mapper", "gcn_mapper", "neighbor_count_mapper", "sum_reducer",
                      "mean_reducer", "max_reducer", "sum_updater", "identity_updater", "segment_softmax", "segment_count",
                      "gcn", "gat", "mean_graph_sage", "sum_graph_sage", "gcn_graph_sage", "mean_pool_graph_sage",
-                     "max_pool_graph_sage", "appnp"):
+                     "max_pool_graph_sage", "appnp", "sgc", "ssgc", "tagcn", "gin", "le_conv"):
             setattr(self, name, getattr(tfg.nn, name))
         for name in ("convert_edge_to_directed", "merge_duplicated_edge", "add_self_loop_edge", "remove_self_loop_edge",
                      "adj_norm_edge"):
@@ -186,3 +186,30 @@ def _replay_appnp(d, api):
     _close(O(api.appnp(A(d["x"]), A(d["ei"]), A(d["w"]), ks, bs, k=10, alpha=0.1)), d["k10"], "appnp k=10", **tol)
     _close(O(api.appnp(A(d["x"]), A(d["ei"]), A(d["w"]), ks, bs, activation=api.relu, k=2, alpha=0.3)), d["k2_relu"],
            "appnp k=2 relu", **tol)
+
+
+def _replay_propagation(d, api):
+    A, O = api.arr, api.out
+    tol = dict(rtol=0, atol_scale=0) if api.exact_float else dict(rtol=1e-4, atol_scale=1e-4)
+    x, ei, w = A(d["x"]), A(d["ei"]), A(d["w"])
+    _close(O(api.sgc(x, ei, w, 2, A(d["kernel"]), A(d["bias"]), api.relu)), d["sgc_k2"], "sgc k=2", **tol)
+    _close(O(api.sgc(x, ei, w, 1, A(d["kernel"]), None, None, renorm=True, improved=True)), d["sgc_k1_improved"],
+           "sgc improved", **tol)
+    ks, bs = [A(d["k0"]), A(d["k1"])], [A(d["b0"]), A(d["b1"])]
+    _close(O(api.ssgc(x, ei, w, ks, bs, k=5, alpha=0.2)), d["ssgc_k5"], "ssgc k=5",
+           **(dict(rtol=1e-6, atol_scale=1e-7) if api.exact_float else tol))
+    _close(O(api.ssgc(x, ei, w, None, None, k=3, alpha=0.1, activation=api.relu)), d["ssgc_nokernel"], "ssgc no kernel",
+           **(dict(rtol=1e-6, atol_scale=1e-7) if api.exact_float else tol))
+    _close(O(api.tagcn(x, ei, w, 3, A(d["tag_kernel"]), A(d["bias"]), api.relu)), d["tagcn_k3"], "tagcn", **tol)
+    mlp_w = A(d["mlp_w"])
+    if api.exact_float:
+        mlp = lambda h: api.relu((h @ mlp_w).astype(np.float32))        # noqa: E731
+        got = api.gin(x, ei, mlp, eps=0.25)
+    else:
+        mlp = lambda h, training=None: api.tfg.ops.gemm(h, mlp_w, act=api.tfg.ops.ACT_RELU)   # noqa: E731
+        got = api.gin(x, ei, mlp, eps=0.25)
+    _close(O(got), d["gin_eps"], "gin", **tol)
+    _close(O(api.le_conv(x, ei, w, A(d["ws"]), A(d["bs"]), A(d["wa"]), A(d["ba"]), A(d["wn"]), None, api.relu)),
+           d["le_conv"], "le_conv", **tol)
+    _close(O(api.le_conv(x, ei, None, A(d["ws"]), None, A(d["wa"]), None, A(d["wn"]), None, None)), d["le_conv_now"],
+           "le_conv unweighted", **tol)

@@ -196,3 +196,48 @@ def test_graph_sage_forward_backward(kind, weighted, concat):
         assert_close(host(got), want.numpy(), what="sage " + name)
     # isolated nodes only receive gradient through the self path
     assert np.isfinite(host(dx.grad)).all()
+
+
+def test_propagation_layers_sgc_ssgc_tagcn_gin_leconv():
+    """the remaining norm(A) @ H convolutions through the layer API, against the oracle."""
+    rs = np.random.RandomState(31)
+    n, f, u = 2500, 48, 32
+    ei = random_graph(n, 30000, seed=33, symmetric=True, isolated=4)
+    w = (rs.rand(ei.shape[1]) + 0.2).astype(np.float32)
+    w[len(w) // 2:] = w[:len(w) // 2]
+    x = rs.randn(n, f).astype(np.float32)
+    g = tfg.Graph(x, ei, edge_weight=w).to_device()
+    inputs = [g.x, g.edge_index, g.edge_weight]
+
+    layer = tfg.layers.SGC(u, k=3, activation=tfg.nn.relu, seed=1)
+    out = layer(inputs, cache=g.cache)
+    p = {k: host(v) for k, v in layer.named_parameters()}
+    assert_close(host(out), o.sgc(x, ei, w, 3, p["kernel"], p["bias"], o.relu), what="SGC")
+    assert "gcn_normed_adj_both_True_True_True_False" in g.cache
+
+    layer = tfg.layers.TAGCN(u, k=2, activation=tfg.nn.relu, seed=2)
+    out = layer(inputs)
+    p = {k: host(v) for k, v in layer.named_parameters()}
+    assert p["kernel"].shape == (f * 3, u)
+    assert_close(host(out), o.tagcn(x, ei, w, 2, p["kernel"], p["bias"], o.relu), what="TAGCN")
+
+    layer = tfg.layers.SSGC([64, 7], k=6, alpha=0.15, seed=3)
+    out = layer(inputs, cache=g.cache)
+    p = {k: host(v) for k, v in layer.named_parameters()}
+    want = o.ssgc(x, ei, w, [p["kernel_0"], p["kernel_1"]], [p["bias_0"], p["bias_1"]], k=6, alpha=0.15)
+    assert_close(host(out), want, what="SSGC")
+
+    layer = tfg.layers.LEConv(u, activation=tfg.nn.relu, seed=4)
+    out = layer(inputs)
+    p = {k: host(v) for k, v in layer.named_parameters()}
+    assert sorted(p) == ["aggr_neighbor_kernel", "aggr_self_bias", "aggr_self_kernel", "self_bias", "self_kernel"]
+    want = o.le_conv(x, ei, w, p["self_kernel"], p["self_bias"], p["aggr_self_kernel"], p["aggr_self_bias"],
+                     p["aggr_neighbor_kernel"], None, o.relu)
+    assert_close(host(out), want, what="LEConv")
+
+    mlp_w = glorot(rs, f, u)
+    mlp_d = dev(mlp_w)
+    layer = tfg.layers.GIN(lambda h, training=None: ops.gemm(h, mlp_d, act=ops.ACT_RELU), eps=0.5)
+    out = layer([g.x, g.edge_index])
+    want = o.gin(x, ei, lambda h: o.relu((h @ mlp_w).astype(np.float32)), eps=0.5)
+    assert_close(host(out), want, what="GIN")

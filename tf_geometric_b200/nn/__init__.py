@@ -9,4 +9,5 @@ from .conv.gat import gat
 from .conv.graph_sage import (mean_graph_sage, sum_graph_sage, gcn_graph_sage, mean_pool_graph_sage,
                               max_pool_graph_sage)
 from .conv.appnp import appnp
+from .conv.propagation import sgc, ssgc, tagcn, gin, gin_updater, le_conv
 from ..ops import relu

@@ -1,0 +1,118 @@
+# coding=utf-8
+"""The remaining `norm(A) @ H` convolutions of tf_geometric: sgc, ssgc, tagcn, gin, le_conv.
+Each one is the K1 kernel (tfgk_spmm_f32) in a loop with the per-layer arithmetic fused into its epilogue where the
+reference's rounding order allows it; signatures follow tf_geometric/nn/conv/{sgc,ssgc,tagcn,gin,le_conv}.py."""
+import torch
+
+from ... import ops, _structure
+from ...sparse import SparseMatrix
+from .gcn import gcn_norm_adj
+
+
+def _f32(t, dev):
+    return None if t is None else ops.as_device(t, torch.float32, device=dev)
+
+
+def sgc(x, edge_index, edge_weight, k, kernel, bias=None, activation=None, renorm=True, improved=False, cache=None):
+    """Simple Graph Convolution: act(norm(A)^k (x W) + b)   (reference sgc.py:10-61)."""
+    edge_index = ops.as_device(edge_index, torch.int32)
+    dev = edge_index.device
+    x = _f32(x, dev)
+    n = x.shape[0]
+    normed = gcn_norm_adj(SparseMatrix(edge_index, edge_weight, [n, n]), renorm=renorm, improved=improved, cache=cache)
+    h = ops.gemm(x, _f32(kernel, dev))
+    act_code, leftover = ops.activation_code(activation)
+    b = _f32(bias, dev)
+    for i in range(k):
+        last = i == k - 1
+        h = normed.matmul(h, bias=b if last else None, act=act_code if last else ops.ACT_NONE)
+    if k == 0:
+        if b is not None:
+            h = h + b
+        if act_code == ops.ACT_RELU:
+            h = torch.relu(h)
+    if leftover is not None:
+        h = leftover(h)
+    return h
+
+
+def ssgc(x, edge_index, edge_weight, kernels=None, biases=None, k=10, alpha=0.1, dense_activation=ops.relu,
+         activation=None, dense_drop_rate=0.0, last_dense_drop_rate=0.0, edge_drop_rate=0.0, cache=None, training=False):
+    """Simple Spectral Graph Convolution: alpha * h + (1 - alpha)/k * sum_{i=1..k} norm(A)^i h   (reference ssgc.py:11-99)."""
+    if training and (dense_drop_rate > 0.0 or last_dense_drop_rate > 0.0 or edge_drop_rate > 0.0):
+        raise NotImplementedError("dropout (TF RNG stream) is outside the forward hot path of this backend")
+    edge_index = ops.as_device(edge_index, torch.int32)
+    dev = edge_index.device
+    h = _f32(x, dev)
+    n = h.shape[0]
+    normed = gcn_norm_adj(SparseMatrix(edge_index, edge_weight, [n, n]), cache=cache)
+    if kernels is not None:
+        num_dense = len(kernels)
+        for i, (kern, b) in enumerate(zip(kernels, biases)):
+            act_code, leftover = ops.activation_code(dense_activation if i < num_dense - 1 else None)
+            h = ops.gemm(h, _f32(kern, dev), bias=_f32(b, dev), act=act_code)
+            if leftover is not None:
+                h = leftover(h)
+    output = h * alpha                                    # elementwise glue in the reference's rounding order (:91-94)
+    for _ in range(k):
+        h = normed.matmul(h)
+        output += (1 - alpha) * h / k
+    if activation is not None:
+        output = activation(output)
+    return output
+
+
+def tagcn(x, edge_index, edge_weight, k, kernel, bias=None, activation=None, renorm=False, improved=False, cache=None):
+    """Topology Adaptive GCN: act([x, Ax, ..., A^k x] W + b); the hops are written straight into the column blocks of
+    the concatenated operand (reference tagcn.py:10-51)."""
+    edge_index = ops.as_device(edge_index, torch.int32)
+    dev = edge_index.device
+    x = _f32(x, dev)
+    n, f = x.shape
+    normed = gcn_norm_adj(SparseMatrix(edge_index, edge_weight, [n, n]), renorm=renorm, improved=improved, cache=cache)
+    hops = torch.empty((n, f * (k + 1)), dtype=torch.float32, device=dev)
+    hops[:, :f].copy_(x)
+    for i in range(k):
+        normed.matmul(hops[:, i * f:(i + 1) * f], out=hops[:, (i + 1) * f:(i + 2) * f])
+    act_code, leftover = ops.activation_code(activation)
+    out = ops.gemm(hops, _f32(kernel, dev), bias=_f32(bias, dev), act=act_code)
+    return leftover(out) if leftover is not None else out
+
+
+def gin_updater(x, reduced_neighbor_msg, eps):
+    return x * (1.0 + eps) + reduced_neighbor_msg
+
+
+def gin(x, edge_index, mlp_model, eps=0.0, training=None):
+    """Graph Isomorphism Network: mlp((1 + eps) x + sum_{j in N(i)} x_j); the update is the aggregation kernel's axpby
+    epilogue (reference gin.py:11-38)."""
+    edge_index = ops.as_device(edge_index, torch.int32)
+    dev = edge_index.device
+    x = _f32(x, dev)
+    csr, _ = _structure.csr_for_edge_index(edge_index, x.shape[0])
+    eps_value = float(eps.detach().item()) if torch.is_tensor(eps) else float(eps)
+    h = ops.spmm(csr, None, x, reduce="sum", alpha=1.0, addend=x, beta=1.0 + eps_value)
+    try:
+        return mlp_model(h, training=training)
+    except TypeError:
+        return mlp_model(h)
+
+
+def le_conv(x, edge_index, edge_weight, self_kernel, self_bias, aggr_self_kernel, aggr_self_bias,
+            aggr_neighbor_kernel, aggr_neighbor_bias, activation=None):
+    """LEConv (ASAP): act(x Ws + sum_j w_ij (x_j Wa - x_j Wn)).  Note the reference gathers BOTH aggregation terms by the
+    neighbour index `col` (le_conv.py:40-43), so the per-edge difference is a per-node difference gathered once."""
+    edge_index = ops.as_device(edge_index, torch.int32)
+    dev = edge_index.device
+    x = _f32(x, dev)
+    n = x.shape[0]
+    csr, _ = _structure.csr_for_edge_index(edge_index, n)
+    w_csr = None
+    if edge_weight is not None:
+        w_csr = _structure.weights_in_csr_order(_f32(edge_weight, dev), csr)
+    self_h = ops.gemm(x, _f32(self_kernel, dev), bias=_f32(self_bias, dev))
+    diff = ops.gemm(x, _f32(aggr_self_kernel, dev), bias=_f32(aggr_self_bias, dev)) \
+        - ops.gemm(x, _f32(aggr_neighbor_kernel, dev), bias=_f32(aggr_neighbor_bias, dev))
+    act_code, leftover = ops.activation_code(activation)
+    h = ops.spmm(csr, w_csr, diff, reduce="sum", alpha=1.0, addend=self_h, beta=1.0, act=act_code)
+    return leftover(h) if leftover is not None else h

@@ -28,6 +28,11 @@ gcn_m = importlib.import_module("tf_geometric.nn.conv.gcn")
 gat_m = importlib.import_module("tf_geometric.nn.conv.gat")
 sage_m = importlib.import_module("tf_geometric.nn.conv.graph_sage")
 appnp_m = importlib.import_module("tf_geometric.nn.conv.appnp")
+sgc_m = importlib.import_module("tf_geometric.nn.conv.sgc")
+ssgc_m = importlib.import_module("tf_geometric.nn.conv.ssgc")
+tagcn_m = importlib.import_module("tf_geometric.nn.conv.tagcn")
+gin_m = importlib.import_module("tf_geometric.nn.conv.gin")
+le_m = importlib.import_module("tf_geometric.nn.conv.le_conv")
 
 
 def glorot(rs, a, b):
@@ -173,6 +178,31 @@ def main():
     out["k10"] = appnp_m.appnp(T(x), T(ei), T(w), [T(k0), T(k1)], [T(b0), T(b1)], k=10, alpha=0.1)
     out["k2_relu"] = appnp_m.appnp(T(x), T(ei), T(w), [T(k0), T(k1)], [T(b0), T(b1)], activation=tf.nn.relu, k=2, alpha=0.3)
     save("appnp", **out)
+
+    # ---- sgc / ssgc / tagcn / gin / le_conv ------------------------------------------------------------
+    n, f, u = 48, 9, 6
+    ei = graph(n, 420, 13, True)
+    w = rs.rand(ei.shape[1]).astype(np.float32) + 0.3
+    w[len(w) // 2:] = w[:len(w) // 2]
+    x = rs.randn(n, f).astype(np.float32)
+    kernel, bias = glorot(rs, f, u), rs.randn(u).astype(np.float32)
+    k0, b0, k1, b1 = glorot(rs, f, 12), rs.randn(12).astype(np.float32), glorot(rs, 12, u), rs.randn(u).astype(np.float32)
+    tag_kernel = glorot(rs, f * 4, u)
+    mlp_w = glorot(rs, f, u)
+    ws, bs = glorot(rs, f, u), rs.randn(u).astype(np.float32)
+    wa, ba, wn = glorot(rs, f, u), rs.randn(u).astype(np.float32), glorot(rs, f, u)
+    out = {"n": n, "ei": ei, "w": w, "x": x, "kernel": kernel, "bias": bias, "k0": k0, "b0": b0, "k1": k1, "b1": b1,
+           "tag_kernel": tag_kernel, "mlp_w": mlp_w, "ws": ws, "bs": bs, "wa": wa, "ba": ba, "wn": wn}
+    out["sgc_k2"] = sgc_m.sgc(T(x), T(ei), T(w), 2, T(kernel), T(bias), tf.nn.relu)
+    out["sgc_k1_improved"] = sgc_m.sgc(T(x), T(ei), T(w), 1, T(kernel), None, None, renorm=True, improved=True)
+    out["ssgc_k5"] = ssgc_m.ssgc(T(x), T(ei), T(w), [T(k0), T(k1)], [T(b0), T(b1)], k=5, alpha=0.2)
+    out["ssgc_nokernel"] = ssgc_m.ssgc(T(x), T(ei), T(w), None, None, k=3, alpha=0.1, activation=tf.nn.relu)
+    out["tagcn_k3"] = tagcn_m.tagcn(T(x), T(ei), T(w), 3, T(tag_kernel), T(bias), tf.nn.relu)
+    mlp = lambda h, training=None: tf.nn.relu(h @ T(mlp_w))      # noqa: E731
+    out["gin_eps"] = gin_m.gin(T(x), T(ei), mlp, eps=0.25)
+    out["le_conv"] = le_m.le_conv(T(x), T(ei), T(w), T(ws), T(bs), T(wa), T(ba), T(wn), None, tf.nn.relu)
+    out["le_conv_now"] = le_m.le_conv(T(x), T(ei), None, T(ws), None, T(wa), None, T(wn), None, None)
+    save("propagation", **out)
 
 
 if __name__ == "__main__":
