@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TFGK_ABI_VERSION 1
+#define TFGK_ABI_VERSION 2
 
 enum tfgk_status {
     TFGK_OK = 0,
@@ -66,6 +66,35 @@ int tfgk_csr_build(const int32_t *row, const int32_t *col, int64_t E, int32_t N_
                    int64_t *rowptr, int32_t *col_sorted, int32_t *perm,
                    void *workspace, size_t workspace_bytes, void *stream);
 
+/* Work plan of a CSR for the streaming kernels (K1, K3): destination rows are grouped into tasks of at most
+ * `rows_per_task` consecutive rows (one warp each), and every row with more than `hub_threshold` edges is cut into slices
+ * of `chunk` edges that are reduced by separate warps into `scratch` and merged by a fix-up kernel in slice order
+ * (deterministic; a hub row is therefore summed slice by slice instead of strictly left to right).  Without hub rows the
+ * kernels need no plan (pass NULL).  The reference has no counterpart: tf.math.unsorted_segment_sum is one sequential loop. */
+typedef struct tfgk_plan {
+    int32_t n_tasks, n_hubs, n_slots, chunk;
+    const int32_t *task_row;    /* [n_tasks] first destination row                                   */
+    const int32_t *task_nrows;  /* [n_tasks] number of rows (1 for a hub slice)                      */
+    const int64_t *task_e0;     /* [n_tasks] first CSR edge                                          */
+    const int64_t *task_e1;     /* [n_tasks] one past the last CSR edge                              */
+    const int32_t *task_slot;   /* [n_tasks] -1: whole rows; >= 0: hub slice -> partial in scratch   */
+    const int32_t *hub_row;     /* [n_hubs]                                                          */
+    const int32_t *hub_slot0;   /* [n_hubs] first scratch slot of the row                            */
+    const int32_t *hub_nslots;  /* [n_hubs]                                                          */
+    float *scratch;             /* K1: n_slots * D floats;  K3: n_slots * (H*dv + 64) floats         */
+    size_t scratch_bytes;
+} tfgk_plan;
+
+/* Upper bounds for the plan arrays of a CSR with E edges and N rows. */
+int tfgk_plan_capacity(int64_t E, int32_t N, int32_t hub_threshold, int32_t chunk, int32_t rows_per_task,
+                       int64_t *max_tasks, int64_t *max_hubs);
+int tfgk_plan_workspace_bytes(int32_t N, size_t *out_bytes);
+/* Fills the arrays; counts_host[3] = {n_tasks, n_hubs, n_slots} (synchronises `stream` once). */
+int tfgk_plan_build(const int64_t *rowptr, int32_t N, int32_t hub_threshold, int32_t chunk, int32_t rows_per_task,
+                    int32_t *task_row, int32_t *task_nrows, int64_t *task_e0, int64_t *task_e1, int32_t *task_slot,
+                    int32_t *hub_row, int32_t *hub_slot0, int32_t *hub_nslots, int64_t cap_tasks, int64_t cap_hubs,
+                    int32_t *counts_host, void *workspace, size_t workspace_bytes, void *stream);
+
 /* dst[i*width + j] = src[perm[i]*width + j]   (COO order -> CSR order) and the inverse scatter. */
 int tfgk_permute_f32(const float *src, const int32_t *perm, int64_t E, int32_t width, float *dst, void *stream);
 int tfgk_unpermute_f32(const float *src, const int32_t *perm, int64_t E, int32_t width, float *dst, void *stream);
@@ -90,12 +119,13 @@ int tfgk_scale_edges_f32(const int32_t *row, const int32_t *col, const float *w,
  *   w NULL = identity_mapper (map_reduce.py:7-8), else gcn_mapper (gcn.py:221-222); CSR order.
  *   epilogue: v = agg*alpha + addend*beta (addend NULL -> v = agg; APPNP appnp.py:86-87, sum_updater
  *   map_reduce.py:19-20), then + bias[D] (NULL ok), then activation  (gcn.py:284-288).
- * Deterministic (no atomics); per-row accumulation is sequential in CSR order for rows of <= 1024 edges. */
+ * Deterministic (no atomics); per-row accumulation is sequential in CSR order, except for the hub rows of `plan`
+ * (NULL = none), which are accumulated slice by slice. */
 int tfgk_spmm_f32(const int64_t *rowptr, const int32_t *col, const float *w,
                   const float *h, int64_t ldh, int32_t n_dst, int32_t D, int reduce,
                   float alpha, const float *addend, int64_t ld_addend, float beta,
                   const float *bias, int act,
-                  float *out, int64_t ldo, void *stream);
+                  float *out, int64_t ldo, const tfgk_plan *plan, void *stream);
 
 /* ---- K3: edge softmax and fused GAT ------------------------------------------------------------------------- */
 
@@ -115,7 +145,7 @@ int tfgk_gat_fused_f32(const int64_t *rowptr, const int32_t *col,
                        const float *Q, int64_t ldq, const float *K, int64_t ldk, const float *V, int64_t ldv,
                        int32_t N, int32_t H, int32_t dqk, int32_t dv, float scale, int split_value_heads,
                        const float *bias, int act, float *att, int write_att, float *out, int64_t ldo,
-                       void *stream);
+                       const tfgk_plan *plan, void *stream);
 
 /* ---- K4: dense projections (gcn.py:272, gat.py:52,61,70, graph_sage.py:43-44, appnp.py:69) ------------------- */
 

@@ -30,7 +30,7 @@ def test_library_is_built_and_loads():
 def test_every_declared_symbol_is_exported_and_bound():
     decl = _header_functions()
     names = [n for n, _ in decl]
-    assert len(names) >= 18
+    assert len(names) >= 21
     handle = ctypes.CDLL(_ffi.library_path())
     for name in names:
         assert hasattr(handle, name), "{} declared in include/tfgk.h but not exported".format(name)
@@ -55,8 +55,8 @@ def test_argument_validation_without_gpu():
     assert lib.tfgk_csr_workspace_bytes(-1, 10, ctypes.byref(out)) == 1
     assert b"E" in lib.tfgk_last_error()
     assert lib.tfgk_gemm_workspace_bytes(100, 128, 1 << 20, ctypes.byref(out)) == 0 and out.value > 0
-    assert lib.tfgk_spmm_f32(None, None, None, None, 0, -1, 4, 0, 1.0, None, 0, 0.0, None, 0, None, 0, None) == 1
-    assert lib.tfgk_spmm_f32(None, None, None, None, 0, 5, 4, 7, 1.0, None, 0, 0.0, None, 0, None, 0, None) == 1
+    assert lib.tfgk_spmm_f32(None, None, None, None, 0, -1, 4, 0, 1.0, None, 0, 0.0, None, 0, None, 0, None, None) == 1
+    assert lib.tfgk_spmm_f32(None, None, None, None, 0, 5, 4, 7, 1.0, None, 0, 0.0, None, 0, None, 0, None, None) == 1
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a CPU-only machine")

@@ -107,3 +107,23 @@ def test_gat_layer_defaults_and_weight_names():
     want = o.gat(x, ei, p["query_kernel"], p["query_bias"], o.relu, p["key_kernel"], p["key_bias"], o.relu,
                  p["kernel"], p["bias"], o.relu, num_heads=8)
     assert_close(host(out), want, what="GAT layer")
+
+
+def test_gat_hub_rows_sliced_softmax_merge():
+    """Hub rows in the fused GAT: per-slice (sum, max, denominator) partials merged with the log-sum-exp rule."""
+    rs = np.random.RandomState(5)
+    n, heads, a = 30000, 8, 128
+    base = random_graph(n, 200000, seed=9)
+    extra = [np.stack([np.full(k, node), rs.randint(0, n, k)]) for node, k in ((11, 9000), (29999, 120000), (500, 2100))]
+    ei = np.concatenate([base] + extra, axis=1).astype(np.int32)
+    ei = ei[:, rs.permutation(ei.shape[1])]
+    full, _ = o.add_self_loop_edge(ei, n)
+    q, k, v = (rs.randn(n, a).astype(np.float32) for _ in range(3))
+    want = c_oracle.gat_core(full[0], full[1], q, k, v, heads, True)
+    csr = ops.csr_build(dev(full[0]), dev(full[1]), n)
+    assert csr.plan is not None and csr.plan.n_hubs == 3
+    got = ops.gat_fused(csr, dev(q), dev(k), dev(v), heads)
+    assert_close(host(got), want, rtol=2e-5, atol_scale=2e-6, what="gat with hub rows")
+    assert torch.equal(got, ops.gat_fused(csr, dev(q), dev(k), dev(v), heads))
+    got_att, att = ops.gat_fused(csr, dev(q), dev(k), dev(v), heads, return_attention=True)   # per-row kernel, same answer
+    assert_close(host(got_att), want, rtol=2e-5, atol_scale=2e-6, what="gat with hub rows (attention path)")

@@ -23,7 +23,7 @@ def host(t):
     return t.detach().cpu().numpy()
 
 
-GRAPH = dict(n=3000, e=45000, seed=5, isolated=11, hub=(42, 2500))
+GRAPH = dict(n=3000, e=45000, seed=5, isolated=11, hub=(42, 1900))     # <= ops.HUB_THRESHOLD: strictly sequential rows
 
 
 def _graph():
@@ -132,3 +132,41 @@ def test_determinism_run_to_run():
     first = host(adj @ x)
     for _ in range(3):
         np.testing.assert_array_equal(host(adj @ x), first)
+
+
+@pytest.mark.parametrize("d", [128, 100, 32, 200])
+def test_hub_rows_are_sliced_and_merged_deterministically(d):
+    """Rows above ops.HUB_THRESHOLD edges are reduced in 2048-edge slices by separate warps and merged in slice order:
+    every other row stays bit-identical to the sequential oracle, hub rows agree to fp32 rounding, runs are repeatable."""
+    n = 20000
+    rs = np.random.RandomState(d)
+    base = random_graph(n, 150000, seed=3, isolated=3)
+    hubs = {7: 5000, 123: 70000, 19999: 2049, 4000: 1500}          # 4000 stays below the threshold (with its base edges)
+    extra = [np.stack([np.full(k, node), rs.randint(0, n, k)]) for node, k in hubs.items()]
+    ei = np.concatenate([base] + extra, axis=1).astype(np.int32)
+    ei = ei[:, rs.permutation(ei.shape[1])]
+    w = rs.rand(ei.shape[1]).astype(np.float32)
+    x = rs.randn(n, d).astype(np.float32)
+    csr = ops.csr_build(dev(ei[0]), dev(ei[1]), n)
+    deg = np.bincount(ei[0], minlength=n)
+    is_hub = deg > ops.HUB_THRESHOLD
+    assert csr.plan is not None and csr.plan.n_hubs == int(is_hub.sum()) and is_hub[[7, 123, 19999]].all() and not is_hub[4000]
+    assert deg[4000] <= ops.HUB_THRESHOLD
+    assert csr.plan.n_slots == int(np.ceil(deg[is_hub] / ops.HUB_CHUNK).sum())
+    w_csr = ops.permute(dev(w), csr.perm)
+    for reduce in ("sum", "mean", "max"):
+        want = c_oracle.aggregate(ei[0], ei[1], w, x, n, reduce)
+        got = host(ops.spmm(csr, w_csr, dev(x), reduce=reduce))
+        np.testing.assert_array_equal(got[~is_hub], want[~is_hub])
+        if reduce == "max":
+            np.testing.assert_array_equal(got[is_hub], want[is_hub])
+        else:
+            scale = np.abs(want[is_hub]).max()
+            assert np.abs(got[is_hub] - want[is_hub]).max() <= 2e-5 * scale
+        np.testing.assert_array_equal(host(ops.spmm(csr, w_csr, dev(x), reduce=reduce)), got)
+    bias = rs.randn(d).astype(np.float32)
+    add = rs.randn(n, d).astype(np.float32)
+    want = np.maximum(c_oracle.aggregate(ei[0], ei[1], w, x, n, "sum") * np.float32(0.5) + add * np.float32(2.0) + bias, 0)
+    got = host(ops.spmm(csr, w_csr, dev(x), alpha=0.5, addend=dev(add), beta=2.0, bias=dev(bias), act=ops.ACT_RELU))
+    np.testing.assert_array_equal(got[~is_hub], want[~is_hub])
+    assert np.abs(got[is_hub] - want[is_hub]).max() <= 2e-5 * np.abs(want).max()

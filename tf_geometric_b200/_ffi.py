@@ -12,7 +12,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "lib
 _lock = threading.Lock()
 _lib = None
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 OK = 0
 ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED, ERR_INDEX_OUT_OF_RANGE = 1, 2, 3, 4, 5
@@ -32,21 +32,32 @@ SIGNATURES = {
     "tfgk_segment_count_i32": [_ptr, _i64, _i32, _ptr, _ptr],
     "tfgk_csr_workspace_bytes": [_i64, _i32, ctypes.POINTER(_size)],
     "tfgk_csr_build": [_ptr, _ptr, _i64, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _size, _ptr],
+    "tfgk_plan_capacity": [_i64, _i32, _i32, _i32, _i32, ctypes.POINTER(_i64), ctypes.POINTER(_i64)],
+    "tfgk_plan_workspace_bytes": [_i32, ctypes.POINTER(_size)],
+    "tfgk_plan_build": [_ptr, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64,
+                        ctypes.POINTER(_i32), _ptr, _size, _ptr],
     "tfgk_permute_f32": [_ptr, _ptr, _i64, _i32, _ptr, _ptr],
     "tfgk_unpermute_f32": [_ptr, _ptr, _i64, _i32, _ptr, _ptr],
     "tfgk_csr_rowsum_f32": [_ptr, _ptr, _i32, _ptr, _ptr],
     "tfgk_deg_inv_f32": [_ptr, _i32, _int, _ptr, _ptr],
     "tfgk_scale_edges_f32": [_ptr, _ptr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr],
     "tfgk_spmm_f32": [_ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _int, _f32, _ptr, _i64, _f32, _ptr, _int, _ptr, _i64,
-                      _ptr],
+                      _ptr, _ptr],
     "tfgk_segment_softmax_f32": [_ptr, _ptr, _i32, _i32, _ptr, _ptr],
     "tfgk_gat_fused_f32": [_ptr, _ptr, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _f32, _int, _ptr,
-                           _int, _ptr, _int, _ptr, _i64, _ptr],
+                           _int, _ptr, _int, _ptr, _i64, _ptr, _ptr],
     "tfgk_gemm_workspace_bytes": [_i32, _i32, _i32, ctypes.POINTER(_size)],
     "tfgk_gemm_f32": [_ptr, _i64, _int, _ptr, _i64, _int, _ptr, _int, _f32, _i32, _i32, _i32, _ptr, _i64, _ptr, _size,
                       _ptr],
     "tfgk_l2_normalize_f32": [_ptr, _i64, _i32, _i32, _ptr, _i64, _ptr],
 }
+
+
+class PlanStruct(ctypes.Structure):
+    """struct tfgk_plan of include/tfgk.h."""
+    _fields_ = [("n_tasks", _i32), ("n_hubs", _i32), ("n_slots", _i32), ("chunk", _i32),
+                ("task_row", _ptr), ("task_nrows", _ptr), ("task_e0", _ptr), ("task_e1", _ptr), ("task_slot", _ptr),
+                ("hub_row", _ptr), ("hub_slot0", _ptr), ("hub_nslots", _ptr), ("scratch", _ptr), ("scratch_bytes", _size)]
 
 
 class TfgkError(RuntimeError):

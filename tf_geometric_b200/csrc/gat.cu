@@ -34,6 +34,14 @@ struct GatParams {
     float *att;          // NOT restrict/const: written and re-read by the same warp
     int write_att;
     float *out; int64_t ldo;
+    // optional work plan (tfgk_plan)
+    int32_t n_tasks;
+    const int32_t *task_row, *task_nrows;
+    const int64_t *task_e0, *task_e1;
+    const int32_t *task_slot;
+    int32_t n_hubs;
+    const int32_t *hub_row, *hub_slot0, *hub_nslots;
+    float *scratch;      // per slot: [A] partial sums | [32] running max per lane | [32] denominators per lane
 };
 
 // ---- fast path: float4 lanes, H | 32, dqk/4 a power of two, heads concatenated ---------------------------------
@@ -329,12 +337,25 @@ __global__ void __launch_bounds__(kGatAsyncWarps * 32) gat_async_kernel(const Ga
     static_assert(S <= RPC, "index chunk refill assumes the prologue stays inside chunk 0");
     extern __shared__ __align__(16) uint8_t gat_ring[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t r0 = ((int64_t)blockIdx.x * kGatAsyncWarps + warp) * kGatAsyncRows;
-    if (r0 >= p.N) return;
-    const int64_t r1 = min((int64_t)p.N, r0 + kGatAsyncRows);
+    const int64_t task = (int64_t)blockIdx.x * kGatAsyncWarps + warp;
+    int64_t r0, r1, e_begin, e_stop;
+    int slot = -1;
+    if (p.task_row != nullptr) {
+        if (task >= p.n_tasks) return;
+        r0 = p.task_row[task];
+        r1 = r0 + p.task_nrows[task];
+        e_begin = p.task_e0[task];
+        e_stop = p.task_e1[task];
+        slot = p.task_slot[task];
+    } else {
+        r0 = task * kGatAsyncRows;
+        if (r0 >= p.N) return;
+        r1 = min((int64_t)p.N, r0 + kGatAsyncRows);
+        e_begin = p.rowptr[r0];
+        e_stop = p.rowptr[r1];
+    }
     const int64_t rp_hi = p.rowptr[min(r0 + lane + 1, r1)];
-    const int64_t e_begin = p.rowptr[r0];
-    const int n_edges = (int)(p.rowptr[r1] - e_begin);
+    const int n_edges = (int)(e_stop - e_begin);
     const int n_rounds = (n_edges + U - 1) / U;
     const int A = p.H * p.dqk;
     const int lanes_per_head = p.dqk >> 2;
@@ -346,7 +367,7 @@ __global__ void __launch_bounds__(kGatAsyncWarps * 32) gat_async_kernel(const Ga
     const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(my_ring);
 
     int64_t r = r0;
-    int row_end = (int)(__shfl_sync(0xffffffffu, rp_hi, 0) - e_begin);
+    int row_end = slot >= 0 ? 0x7fffffff : (int)(__shfl_sync(0xffffffffu, rp_hi, 0) - e_begin);   // hub slices never close
     float4 q = cok ? ldg4(p.Q + r * p.ldq + ccol) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 q_next = (cok && r + 1 < r1) ? ldg4(p.Q + (r + 1) * p.ldq + ccol) : make_float4(0.f, 0.f, 0.f, 0.f);
     float mx = -FLT_MAX, den = 0.0f, a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -432,16 +453,64 @@ __global__ void __launch_bounds__(kGatAsyncWarps * 32) gat_async_kernel(const Ga
             if (dead & 1) cb = load_chunk(dead + 2); else ca = load_chunk(dead + 2);
         }
     }
+    if (slot >= 0) {                      // hub slice: partial (sums, max, denominator), merged by gat_hub_fixup_kernel
+        float *dst = p.scratch + (int64_t)slot * (A + 64);
+        if (cok) *reinterpret_cast<float4 *>(dst + ccol) = make_float4(a0, a1, a2, a3);
+        dst[A + lane] = mx;
+        dst[A + 32 + lane] = den;
+        return;
+    }
     while (r < r1) finalize_row();
+}
+
+// merges the (sums, max, denominator) partials of every hub row with the log-sum-exp rule, in slice order
+__global__ void __launch_bounds__(256) gat_hub_fixup_kernel(const GatParams p) {
+    const int lane = threadIdx.x & 31;
+    const int h = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (h >= p.n_hubs) return;
+    const int64_t r = p.hub_row[h];
+    const int s0 = p.hub_slot0[h], ns = p.hub_nslots[h];
+    const int A = p.H * p.dqk;
+    const int ccol = lane * 4;
+    const bool cok = ccol < A;
+    const int64_t stride = A + 64;
+    float m = -FLT_MAX;
+    for (int s = 0; s < ns; ++s) m = fmaxf(m, p.scratch[(int64_t)(s0 + s) * stride + A + lane]);
+    float den = 0.0f, a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int s = 0; s < ns; ++s) {
+        const float *src = p.scratch + (int64_t)(s0 + s) * stride;
+        const float sc = expf(src[A + lane] - m);
+        den = fmaf(src[A + 32 + lane], sc, den);
+        if (cok) {
+            const float4 v = *reinterpret_cast<const float4 *>(src + ccol);
+            a0 = fmaf(v.x, sc, a0); a1 = fmaf(v.y, sc, a1); a2 = fmaf(v.z, sc, a2); a3 = fmaf(v.w, sc, a3);
+        }
+    }
+    if (cok) {
+        const float inv = 1.0f / (den + 1e-8f);
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) b = ldg4(p.bias + ccol);
+        float4 o;
+        o.x = apply_act(a0 * inv + b.x, p.act);
+        o.y = apply_act(a1 * inv + b.y, p.act);
+        o.z = apply_act(a2 * inv + b.z, p.act);
+        o.w = apply_act(a3 * inv + b.w, p.act);
+        *reinterpret_cast<float4 *>(p.out + r * p.ldo + ccol) = o;
+    }
 }
 
 template <int U, int S>
 static int launch_gat_async(const GatParams &p, cudaStream_t st) {
     const size_t smem = (size_t)kGatAsyncWarps * S * 2 * U * (size_t)(p.H * p.dqk) * 4;
     TFGK_CUDA(cudaFuncSetAttribute(gat_async_kernel<U, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned blocks = (unsigned)ceil_div64(p.N, (int64_t)kGatAsyncWarps * kGatAsyncRows);
+    const int64_t n_tasks = p.task_row ? p.n_tasks : ceil_div64(p.N, kGatAsyncRows);
+    const unsigned blocks = (unsigned)ceil_div64(n_tasks, kGatAsyncWarps);
     gat_async_kernel<U, S><<<blocks, kGatAsyncWarps * 32, smem, st>>>(p);
     TFGK_LAUNCH_CHECK();
+    if (p.task_row && p.n_hubs > 0) {
+        gat_hub_fixup_kernel<<<(unsigned)ceil_div64(p.n_hubs, 8), 256, 0, st>>>(p);
+        TFGK_LAUNCH_CHECK();
+    }
     return TFGK_OK;
 }
 
@@ -619,7 +688,7 @@ extern "C" int tfgk_gat_fused_f32(const int64_t *rowptr, const int32_t *col,
                                   const float *Q, int64_t ldq, const float *K, int64_t ldk, const float *V, int64_t ldv,
                                   int32_t N, int32_t H, int32_t dqk, int32_t dv, float scale, int split_value_heads,
                                   const float *bias, int act, float *att, int write_att, float *out, int64_t ldo,
-                                  void *stream) {
+                                  const tfgk_plan *plan, void *stream) {
     TFGK_CHECK_ARG(N >= 0 && H >= 1 && dqk >= 1 && dv >= 1, "gat: bad size (N=%d H=%d dqk=%d dv=%d)", N, H, dqk, dv);
     TFGK_CHECK_ARG(act == TFGK_ACT_NONE || act == TFGK_ACT_RELU, "gat: unknown activation %d", act);
     TFGK_CHECK_ARG(scale > 0.0f, "gat: scale must be positive");
@@ -635,6 +704,17 @@ extern "C" int tfgk_gat_fused_f32(const int64_t *rowptr, const int32_t *col,
     p.Q = Q; p.ldq = ldq; p.K = K; p.ldk = ldk; p.V = V; p.ldv = ldv;
     p.N = N; p.H = H; p.dqk = dqk; p.dv = dv; p.scale = scale; p.split = split_value_heads;
     p.bias = bias; p.act = act; p.att = att; p.write_att = write_att; p.out = out; p.ldo = ldo;
+    p.n_tasks = 0; p.task_row = nullptr; p.task_nrows = nullptr; p.task_e0 = nullptr; p.task_e1 = nullptr;
+    p.task_slot = nullptr; p.n_hubs = 0; p.hub_row = nullptr; p.hub_slot0 = nullptr; p.hub_nslots = nullptr; p.scratch = nullptr;
+    if (plan != nullptr && plan->n_tasks > 0) {
+        if (plan->n_hubs > 0)
+            TFGK_CHECK_ARG(plan->scratch != nullptr && plan->scratch_bytes >= (size_t)plan->n_slots * (H * dv + 64) * sizeof(float),
+                           "gat: plan scratch too small (need %zu bytes)", (size_t)plan->n_slots * (H * dv + 64) * sizeof(float));
+        p.n_tasks = plan->n_tasks; p.task_row = plan->task_row; p.task_nrows = plan->task_nrows;
+        p.task_e0 = plan->task_e0; p.task_e1 = plan->task_e1; p.task_slot = plan->task_slot;
+        p.n_hubs = plan->n_hubs; p.hub_row = plan->hub_row; p.hub_slot0 = plan->hub_slot0;
+        p.hub_nslots = plan->hub_nslots; p.scratch = plan->scratch;
+    }
     cudaStream_t st = as_stream(stream);
 
     const bool fast = split_value_heads && is_pow2(H) && H <= kMaxHeadsFast && dqk % 4 == 0 && is_pow2(dqk / 4) &&

@@ -287,6 +287,61 @@ __global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const int32_t *_
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// work plan: runs of <= rows_per_task light rows, hub rows cut into `chunk`-edge slices
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool plan_is_hub(const int64_t *rowptr, int32_t r, int32_t hub_threshold) {
+    return rowptr[r + 1] - rowptr[r] > hub_threshold;
+}
+
+__global__ void plan_count_kernel(const int64_t *__restrict__ rowptr, int32_t N, int32_t hub_threshold, int32_t chunk,
+                                  int32_t rpt, int32_t *__restrict__ cnt_tasks, int32_t *__restrict__ cnt_hubs,
+                                  int32_t *__restrict__ cnt_slots) {
+    const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    const int64_t deg = rowptr[r + 1] - rowptr[r];
+    const bool hub = deg > hub_threshold;
+    int32_t tasks = 0, slots = 0;
+    if (hub) {
+        slots = (int32_t)((deg + chunk - 1) / chunk);
+        tasks = slots;
+    } else if (r % rpt == 0 || plan_is_hub(rowptr, r - 1, hub_threshold)) {
+        tasks = 1;          // this row starts a run of light rows
+    }
+    cnt_tasks[r] = tasks;
+    cnt_hubs[r] = hub ? 1 : 0;
+    cnt_slots[r] = slots;
+}
+
+__global__ void plan_fill_kernel(const int64_t *__restrict__ rowptr, int32_t N, int32_t hub_threshold, int32_t chunk,
+                                 int32_t rpt, const int32_t *__restrict__ off_tasks, const int32_t *__restrict__ off_hubs,
+                                 const int32_t *__restrict__ off_slots, int32_t *__restrict__ task_row,
+                                 int32_t *__restrict__ task_nrows, int64_t *__restrict__ task_e0,
+                                 int64_t *__restrict__ task_e1, int32_t *__restrict__ task_slot,
+                                 int32_t *__restrict__ hub_row, int32_t *__restrict__ hub_slot0,
+                                 int32_t *__restrict__ hub_nslots) {
+    const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    const int64_t start = rowptr[r], end = rowptr[r + 1];
+    const int64_t deg = end - start;
+    if (deg > hub_threshold) {
+        const int32_t slots = (int32_t)((deg + chunk - 1) / chunk);
+        const int32_t h = off_hubs[r], s0 = off_slots[r], t0 = off_tasks[r];
+        hub_row[h] = r; hub_slot0[h] = s0; hub_nslots[h] = slots;
+        for (int32_t j = 0; j < slots; ++j) {
+            task_row[t0 + j] = r; task_nrows[t0 + j] = 1;
+            task_e0[t0 + j] = start + (int64_t)j * chunk;
+            task_e1[t0 + j] = min(end, start + (int64_t)(j + 1) * chunk);
+            task_slot[t0 + j] = s0 + j;
+        }
+    } else if (r % rpt == 0 || plan_is_hub(rowptr, r - 1, hub_threshold)) {
+        int32_t r2 = r + 1;
+        while (r2 < N && r2 % rpt != 0 && !plan_is_hub(rowptr, r2, hub_threshold)) ++r2;
+        const int32_t t = off_tasks[r];
+        task_row[t] = r; task_nrows[t] = r2 - r; task_e0[t] = start; task_e1[t] = rowptr[r2]; task_slot[t] = -1;
+    }
+}
+
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct CsrWorkspace {
@@ -441,6 +496,68 @@ int tfgk_csr_build(const int32_t *row, const int32_t *col, int64_t E, int32_t N_
     }
     // 4. col_sorted = col[perm]
     gather_i32_kernel<<<grid_for(E), 256, 0, st>>>(col, perm, E, col_sorted);
+    TFGK_LAUNCH_CHECK();
+    return TFGK_OK;
+}
+
+int tfgk_plan_capacity(int64_t E, int32_t N, int32_t hub_threshold, int32_t chunk, int32_t rows_per_task,
+                       int64_t *max_tasks, int64_t *max_hubs) {
+    TFGK_CHECK_ARG(E >= 0 && N >= 0 && hub_threshold >= 1 && chunk >= 1 && rows_per_task >= 1 && rows_per_task <= 32,
+                   "plan_capacity: bad argument");
+    TFGK_CHECK_ARG(max_tasks && max_hubs, "plan_capacity: null output");
+    const int64_t hubs = E / ((int64_t)hub_threshold + 1) + 1;
+    *max_hubs = hubs;
+    // runs: one per rows_per_task block plus one after every hub row; slices: ceil(deg/chunk) <= deg/chunk + 1 per hub
+    *max_tasks = ceil_div64(N, rows_per_task) + hubs + (E / chunk + hubs) + 2;
+    return TFGK_OK;
+}
+
+int tfgk_plan_workspace_bytes(int32_t N, size_t *out_bytes) {
+    TFGK_CHECK_ARG(out_bytes && N >= 0, "plan_workspace_bytes: bad argument");
+    const size_t arr = align_up(((size_t)N + 1) * 4);
+    *out_bytes = 6 * arr + align_up((size_t)(ceil_div64((int64_t)N + 1, kScanTile) + 1) * 8) + 256;
+    return TFGK_OK;
+}
+
+int tfgk_plan_build(const int64_t *rowptr, int32_t N, int32_t hub_threshold, int32_t chunk, int32_t rows_per_task,
+                    int32_t *task_row, int32_t *task_nrows, int64_t *task_e0, int64_t *task_e1, int32_t *task_slot,
+                    int32_t *hub_row, int32_t *hub_slot0, int32_t *hub_nslots, int64_t cap_tasks, int64_t cap_hubs,
+                    int32_t *counts_host, void *workspace, size_t workspace_bytes, void *stream) {
+    TFGK_CHECK_ARG(N >= 0 && hub_threshold >= 1 && chunk >= 1 && rows_per_task >= 1 && rows_per_task <= 32,
+                   "plan_build: bad argument");
+    TFGK_CHECK_ARG(counts_host != nullptr, "plan_build: null counts");
+    counts_host[0] = counts_host[1] = counts_host[2] = 0;
+    if (N == 0) return TFGK_OK;
+    TFGK_CHECK_ARG(rowptr && task_row && task_nrows && task_e0 && task_e1 && task_slot && hub_row && hub_slot0 && hub_nslots,
+                   "plan_build: null pointer");
+    size_t need = 0;
+    tfgk_plan_workspace_bytes(N, &need);
+    if (workspace == nullptr || workspace_bytes < need)
+        return set_error(TFGK_ERR_WORKSPACE, "plan_build: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+    cudaStream_t st = as_stream(stream);
+    char *ws = static_cast<char *>(workspace);
+    const size_t arr = align_up(((size_t)N + 1) * 4);
+    int32_t *cnt_t = reinterpret_cast<int32_t *>(ws), *cnt_h = reinterpret_cast<int32_t *>(ws + arr),
+            *cnt_s = reinterpret_cast<int32_t *>(ws + 2 * arr);
+    int32_t *off_t = reinterpret_cast<int32_t *>(ws + 3 * arr), *off_h = reinterpret_cast<int32_t *>(ws + 4 * arr),
+            *off_s = reinterpret_cast<int32_t *>(ws + 5 * arr);
+    int32_t *sums = reinterpret_cast<int32_t *>(ws + 6 * arr);
+    const unsigned blocks = (unsigned)ceil_div64(N, 256);
+    plan_count_kernel<<<blocks, 256, 0, st>>>(rowptr, N, hub_threshold, chunk, rows_per_task, cnt_t, cnt_h, cnt_s);
+    TFGK_LAUNCH_CHECK();
+    int rc;
+    if ((rc = exclusive_scan<int32_t, int32_t>(cnt_t, N, (int64_t)N + 1, off_t, sums, st)) != TFGK_OK) return rc;
+    if ((rc = exclusive_scan<int32_t, int32_t>(cnt_h, N, (int64_t)N + 1, off_h, sums, st)) != TFGK_OK) return rc;
+    if ((rc = exclusive_scan<int32_t, int32_t>(cnt_s, N, (int64_t)N + 1, off_s, sums, st)) != TFGK_OK) return rc;
+    TFGK_CUDA(cudaMemcpyAsync(&counts_host[0], off_t + N, 4, cudaMemcpyDeviceToHost, st));
+    TFGK_CUDA(cudaMemcpyAsync(&counts_host[1], off_h + N, 4, cudaMemcpyDeviceToHost, st));
+    TFGK_CUDA(cudaMemcpyAsync(&counts_host[2], off_s + N, 4, cudaMemcpyDeviceToHost, st));
+    TFGK_CUDA(cudaStreamSynchronize(st));
+    if (counts_host[0] > cap_tasks || counts_host[1] > cap_hubs)
+        return set_error(TFGK_ERR_WORKSPACE, "plan_build: capacity too small (tasks %d > %lld or hubs %d > %lld)",
+                         counts_host[0], (long long)cap_tasks, counts_host[1], (long long)cap_hubs);
+    plan_fill_kernel<<<blocks, 256, 0, st>>>(rowptr, N, hub_threshold, chunk, rows_per_task, off_t, off_h, off_s, task_row,
+                                             task_nrows, task_e0, task_e1, task_slot, hub_row, hub_slot0, hub_nslots);
     TFGK_LAUNCH_CHECK();
     return TFGK_OK;
 }

@@ -55,6 +55,14 @@ struct SpmmParams {
     int act;
     float *out;
     int64_t ldo;
+    // optional work plan (tfgk_plan): tasks + hub slices; task_row == nullptr -> implicit blocks of consecutive rows
+    int32_t n_tasks;
+    const int32_t *task_row, *task_nrows;
+    const int64_t *task_e0, *task_e1;
+    const int32_t *task_slot;
+    int32_t n_hubs;
+    const int32_t *hub_row, *hub_slot0, *hub_nslots;
+    float *scratch;
 };
 
 constexpr int kSpmmThreads = 256;
@@ -487,13 +495,26 @@ __global__ void __launch_bounds__(kAsyncWarps * 32) spmm_async_kernel(const Spmm
     constexpr int RPC = 32 / U;
     extern __shared__ __align__(16) uint8_t ring_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t r0 = ((int64_t)blockIdx.x * kAsyncWarps + warp) * kAsyncRows;
-    if (r0 >= p.n_dst) return;
-    const int64_t r1 = min((int64_t)p.n_dst, r0 + kAsyncRows);
+    const int64_t task = (int64_t)blockIdx.x * kAsyncWarps + warp;
+    int64_t r0, r1, e_begin, e_stop;
+    int slot = -1;
+    if (p.task_row != nullptr) {
+        if (task >= p.n_tasks) return;
+        r0 = p.task_row[task];
+        r1 = r0 + p.task_nrows[task];
+        e_begin = p.task_e0[task];
+        e_stop = p.task_e1[task];
+        slot = p.task_slot[task];
+    } else {
+        r0 = task * kAsyncRows;
+        if (r0 >= p.n_dst) return;
+        r1 = min((int64_t)p.n_dst, r0 + kAsyncRows);
+        e_begin = p.rowptr[r0];
+        e_stop = p.rowptr[r1];
+    }
     const int64_t rp_lo = p.rowptr[min(r0 + lane, r1)];
     const int64_t rp_hi = p.rowptr[min(r0 + lane + 1, r1)];
-    const int64_t e_begin = __shfl_sync(0xffffffffu, rp_lo, 0);
-    const int n_edges = (int)(p.rowptr[r1] - e_begin);
+    const int n_edges = (int)(e_stop - e_begin);
     const int n_rounds = (n_edges + U - 1) / U;
     const bool weighted = p.w != nullptr;
     const uint32_t stage_bytes = U * row_bytes;
@@ -511,7 +532,8 @@ __global__ void __launch_bounds__(kAsyncWarps * 32) spmm_async_kernel(const Spmm
         for (int x = 0; x < 4; ++x) acc[k][x] = IS_MAX ? -FLT_MAX : 0.0f;
     }
     int64_t r = r0;
-    int row_end = (int)(__shfl_sync(0xffffffffu, rp_hi, 0) - e_begin);
+    // a hub slice (slot >= 0) never closes its row: the partial sum goes to the scratch slot instead
+    int row_end = slot >= 0 ? 0x7fffffff : (int)(__shfl_sync(0xffffffffu, rp_hi, 0) - e_begin);
     const bool is_mean = p.reduce == TFGK_REDUCE_MEAN;
 
     auto finalize_row = [&]() {
@@ -621,7 +643,46 @@ __global__ void __launch_bounds__(kAsyncWarps * 32) spmm_async_kernel(const Spmm
             if (dead & 1) load_chunk(dead + 2, cb, wnb); else load_chunk(dead + 2, ca, wna);
         }
     }
+    if (slot >= 0) {                                  // hub slice: raw partial, merged by spmm_hub_fixup_kernel
+#pragma unroll
+        for (int k = 0; k < NC; ++k)
+            if (cok[k]) store_vec<4>(p.scratch + (int64_t)slot * p.D + coff[k], acc[k]);
+        return;
+    }
     while (r < r1) finalize_row();
+}
+
+// merges the slices of every hub row in slice order (deterministic) and applies the epilogue; one warp per hub row
+template <bool IS_MAX>
+__global__ void __launch_bounds__(256) spmm_hub_fixup_kernel(const SpmmParams p) {
+    const int lane = threadIdx.x & 31;
+    const int h = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (h >= p.n_hubs) return;
+    const int64_t r = p.hub_row[h];
+    const int s0 = p.hub_slot0[h], ns = p.hub_nslots[h];
+    const float cnt = (float)max((int)(p.rowptr[r + 1] - p.rowptr[r]), 1);
+    for (int c = lane * 4; c < p.D; c += 128) {
+        float acc[4] = {IS_MAX ? -FLT_MAX : 0.f, IS_MAX ? -FLT_MAX : 0.f, IS_MAX ? -FLT_MAX : 0.f, IS_MAX ? -FLT_MAX : 0.f};
+        for (int s = 0; s < ns; ++s) {
+            float v[4];
+            load_vec<4>(p.scratch + (int64_t)(s0 + s) * p.D + c, v);
+#pragma unroll
+            for (int x = 0; x < 4; ++x) acc[x] = IS_MAX ? fmaxf(acc[x], v[x]) : __fadd_rn(acc[x], v[x]);
+        }
+        float ad[4], bs[4], o[4];
+        if (p.addend) load_vec<4>(p.addend + r * p.ld_addend + c, ad);
+        if (p.bias) load_vec<4>(p.bias + c, bs);
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            float a = acc[x];
+            if (p.reduce == TFGK_REDUCE_MEAN) a = __fdiv_rn(a, cnt);
+            if (p.addend) a = __fadd_rn(__fmul_rn(a, p.alpha), __fmul_rn(ad[x], p.beta));
+            else if (p.alpha != 1.0f) a = __fmul_rn(a, p.alpha);
+            if (p.bias) a = __fadd_rn(a, bs[x]);
+            o[x] = apply_act(a, p.act);
+        }
+        store_vec<4>(p.out + r * p.ldo + c, o);
+    }
 }
 
 template <int NC, int U, int S>
@@ -629,7 +690,8 @@ static int launch_spmm_async(const SpmmParams &p, cudaStream_t st) {
     const uint32_t row_bytes = (uint32_t)p.D * 4u;
     const size_t smem = (size_t)kAsyncWarps * S * U * row_bytes;
     if (smem > 200 * 1024) return TFGK_ERR_UNSUPPORTED;
-    const unsigned blocks = (unsigned)ceil_div64(p.n_dst, (int64_t)kAsyncWarps * kAsyncRows);
+    const int64_t n_tasks = p.task_row ? p.n_tasks : ceil_div64(p.n_dst, kAsyncRows);
+    const unsigned blocks = (unsigned)ceil_div64(n_tasks, kAsyncWarps);
     if (p.reduce == TFGK_REDUCE_MAX) {
         TFGK_CUDA(cudaFuncSetAttribute(spmm_async_kernel<NC, true, U, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         spmm_async_kernel<NC, true, U, S><<<blocks, kAsyncWarps * 32, smem, st>>>(p, row_bytes);
@@ -638,6 +700,12 @@ static int launch_spmm_async(const SpmmParams &p, cudaStream_t st) {
         spmm_async_kernel<NC, false, U, S><<<blocks, kAsyncWarps * 32, smem, st>>>(p, row_bytes);
     }
     TFGK_LAUNCH_CHECK();
+    if (p.task_row && p.n_hubs > 0) {
+        const unsigned fb = (unsigned)ceil_div64(p.n_hubs, 8);
+        if (p.reduce == TFGK_REDUCE_MAX) spmm_hub_fixup_kernel<true><<<fb, 256, 0, st>>>(p);
+        else spmm_hub_fixup_kernel<false><<<fb, 256, 0, st>>>(p);
+        TFGK_LAUNCH_CHECK();
+    }
     return TFGK_OK;
 }
 
@@ -732,8 +800,11 @@ extern "C" int tfgk_spmm_f32(const int64_t *rowptr, const int32_t *col, const fl
                              const float *h, int64_t ldh, int32_t n_dst, int32_t D, int reduce,
                              float alpha, const float *addend, int64_t ld_addend, float beta,
                              const float *bias, int act,
-                             float *out, int64_t ldo, void *stream) {
+                             float *out, int64_t ldo, const tfgk_plan *plan, void *stream) {
     TFGK_CHECK_ARG(n_dst >= 0 && D >= 0, "spmm: negative size (n_dst=%d, D=%d)", n_dst, D);
+    if (plan != nullptr && plan->n_hubs > 0)
+        TFGK_CHECK_ARG(plan->scratch != nullptr && plan->scratch_bytes >= (size_t)plan->n_slots * D * sizeof(float),
+                       "spmm: plan scratch too small (need %zu bytes)", (size_t)plan->n_slots * D * sizeof(float));
     TFGK_CHECK_ARG(reduce >= TFGK_REDUCE_SUM && reduce <= TFGK_REDUCE_MAX, "spmm: unknown reduce %d", reduce);
     TFGK_CHECK_ARG(act == TFGK_ACT_NONE || act == TFGK_ACT_RELU, "spmm: unknown activation %d", act);
     if (n_dst == 0 || D == 0) return TFGK_OK;
@@ -753,6 +824,18 @@ extern "C" int tfgk_spmm_f32(const int64_t *rowptr, const int32_t *col, const fl
         p.addend = addend ? addend + c0 : nullptr; p.ld_addend = ld_addend; p.beta = beta;
         p.bias = bias ? bias + c0 : nullptr; p.act = act;
         p.out = out + c0; p.ldo = ldo;
+        p.n_tasks = 0; p.task_row = nullptr; p.task_nrows = nullptr; p.task_e0 = nullptr; p.task_e1 = nullptr;
+        p.task_slot = nullptr; p.n_hubs = 0; p.hub_row = nullptr; p.hub_slot0 = nullptr; p.hub_nslots = nullptr;
+        p.scratch = nullptr;
+        // the plan applies when the whole width runs in one launch of the streaming kernel (scratch rows are D wide)
+        const bool use_plan = plan != nullptr && plan->n_tasks > 0 && vec4 && D >= 32 && D <= cols_per_launch &&
+                              spmm_impl_choice() == 3;
+        if (use_plan) {
+            p.n_tasks = plan->n_tasks; p.task_row = plan->task_row; p.task_nrows = plan->task_nrows;
+            p.task_e0 = plan->task_e0; p.task_e1 = plan->task_e1; p.task_slot = plan->task_slot;
+            p.n_hubs = plan->n_hubs; p.hub_row = plan->hub_row; p.hub_slot0 = plan->hub_slot0;
+            p.hub_nslots = plan->hub_nslots; p.scratch = plan->scratch;
+        }
         const int lanes = (p.D + vec - 1) / vec;
         if (vec4 && p.D >= 32 && spmm_impl_choice() == 3) {
             const int rca = dispatch_spmm_async(p, as_stream(stream));

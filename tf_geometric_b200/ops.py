@@ -68,16 +68,43 @@ def _row_major_2d(t, name):
     return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
 
 
+HUB_THRESHOLD = 2048     # rows with more edges are cut into slices ...
+HUB_CHUNK = 2048         # ... of this many edges (about the work of one ordinary 32-row task)
+ROWS_PER_TASK = 32
+
+
+class Plan(object):
+    """Device-side work plan of a CSR with hub rows (struct tfgk_plan): task arrays + a scratch allocator."""
+
+    def __init__(self, arrays, n_tasks, n_hubs, n_slots):
+        self.arrays = arrays            # keeps the device tensors alive
+        self.n_tasks, self.n_hubs, self.n_slots = n_tasks, n_hubs, n_slots
+        self._scratch = None
+
+    def struct(self, floats_per_slot, device):
+        need = max(self.n_slots * floats_per_slot, 1)
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = torch.empty((need,), dtype=torch.float32, device=device)
+        a = self.arrays
+        st = _ffi.PlanStruct(self.n_tasks, self.n_hubs, self.n_slots, HUB_CHUNK,
+                             a["task_row"].data_ptr(), a["task_nrows"].data_ptr(), a["task_e0"].data_ptr(),
+                             a["task_e1"].data_ptr(), a["task_slot"].data_ptr(), a["hub_row"].data_ptr(),
+                             a["hub_slot0"].data_ptr(), a["hub_nslots"].data_ptr(), self._scratch.data_ptr(),
+                             self._scratch.numel() * 4)
+        return st
+
+
 class CSR(object):
     """Destination-sorted CSR of a COO edge list (stable by row): rowptr int64 [n_rows+1], col int32 [nnz],
-    perm int32 [nnz] (position of each CSR slot in the original edge list)."""
+    perm int32 [nnz] (position of each CSR slot in the original edge list); `plan` is set when the graph has hub rows."""
 
-    __slots__ = ("rowptr", "col", "perm", "n_rows", "n_cols", "nnz")
+    __slots__ = ("rowptr", "col", "perm", "n_rows", "n_cols", "nnz", "plan")
 
     def __init__(self, rowptr, col, perm, n_rows, n_cols):
         self.rowptr, self.col, self.perm = rowptr, col, perm
         self.n_rows, self.n_cols = int(n_rows), int(n_cols)
         self.nnz = int(col.shape[0])
+        self.plan = None
 
     def degree_i64(self):
         return self.rowptr[1:] - self.rowptr[:-1]
@@ -123,7 +150,36 @@ def csr_build(row, col, n_rows, n_cols=None):
     perm = torch.empty((E,), dtype=torch.int32, device=dev)
     _ffi.call("tfgk_csr_build", _p(row), _p(col), E, n_rows, n_cols, _p(rowptr), _p(col_sorted), _p(perm),
               _p(ws), need.value, _stream(row))
-    return CSR(rowptr, col_sorted, perm, n_rows, n_cols)
+    csr = CSR(rowptr, col_sorted, perm, n_rows, n_cols)
+    csr.plan = build_plan(csr)
+    return csr
+
+
+def build_plan(csr):
+    """Work plan for graphs with hub rows (> HUB_THRESHOLD edges); None when there are none (the kernels then use their
+    implicit 32-row tasks, which is also the fastest path)."""
+    if csr.nnz == 0 or csr.n_rows == 0:
+        return None
+    dev = csr.rowptr.device
+    cap_t, cap_h = ctypes.c_int64(), ctypes.c_int64()
+    _ffi.call("tfgk_plan_capacity", csr.nnz, csr.n_rows, HUB_THRESHOLD, HUB_CHUNK, ROWS_PER_TASK, ctypes.byref(cap_t),
+              ctypes.byref(cap_h))
+    need = ctypes.c_size_t()
+    _ffi.call("tfgk_plan_workspace_bytes", csr.n_rows, ctypes.byref(need))
+    ws = torch.empty((need.value,), dtype=torch.uint8, device=dev)
+    arrays = {k: torch.empty((cap_t.value,), dtype=torch.int32, device=dev) for k in ("task_row", "task_nrows", "task_slot")}
+    arrays.update({k: torch.empty((cap_t.value,), dtype=torch.int64, device=dev) for k in ("task_e0", "task_e1")})
+    arrays.update({k: torch.empty((cap_h.value,), dtype=torch.int32, device=dev) for k in ("hub_row", "hub_slot0", "hub_nslots")})
+    counts = (ctypes.c_int32 * 3)()
+    _ffi.call("tfgk_plan_build", _p(csr.rowptr), csr.n_rows, HUB_THRESHOLD, HUB_CHUNK, ROWS_PER_TASK,
+              _p(arrays["task_row"]), _p(arrays["task_nrows"]), _p(arrays["task_e0"]), _p(arrays["task_e1"]),
+              _p(arrays["task_slot"]), _p(arrays["hub_row"]), _p(arrays["hub_slot0"]), _p(arrays["hub_nslots"]),
+              cap_t.value, cap_h.value, counts, _p(ws), need.value, _stream(csr.rowptr))
+    n_tasks, n_hubs, n_slots = int(counts[0]), int(counts[1]), int(counts[2])
+    if n_hubs == 0:
+        return None
+    arrays = {k: v[:(n_tasks if k.startswith("task") else n_hubs)].clone() for k, v in arrays.items()}
+    return Plan(arrays, n_tasks, n_hubs, n_slots)
 
 
 def permute(src, perm, inverse=False):
@@ -178,8 +234,11 @@ def spmm(csr, w_csr, h, reduce="sum", alpha=1.0, addend=None, beta=0.0, bias=Non
     if bias is not None:
         _check(bias, torch.float32, "bias")
     code = _REDUCE_CODES[reduce] if isinstance(reduce, str) else reduce
+    plan = getattr(csr, "plan", None)
+    plan_struct = plan.struct(D, h.device) if plan is not None else None
     _ffi.call("tfgk_spmm_f32", _p(csr.rowptr), _p(csr.col if col is None else col), _p(w_csr), _p(h), ldh, n_dst, D,
-              code, float(alpha), _p(addend), lda, float(beta), _p(bias), act, _p(out), ldo, _stream(h))
+              code, float(alpha), _p(addend), lda, float(beta), _p(bias), act, _p(out), ldo,
+              ctypes.byref(plan_struct) if plan_struct is not None else None, _stream(h))
     return out
 
 
@@ -218,11 +277,14 @@ def gat_fused(csr, Q, K, V, num_heads, split_value_heads=True, bias=None, act=AC
     # gat.py:78  scale = sqrt(cast(shape(Q_)[-1], float32))
     scale = float(np.sqrt(np.float32(dqk)))
 
+    plan = getattr(csr, "plan", None)
+    plan_struct = plan.struct(VW + 64, Q.device) if plan is not None else None
+
     def launch(att_buf):
         _ffi.call("tfgk_gat_fused_f32", _p(csr.rowptr), _p(csr.col), _p(Q), _row_major_2d(Q, "Q"), _p(K),
                   _row_major_2d(K, "K"), _p(V), _row_major_2d(V, "V"), N, H, dqk, dv, scale,
                   1 if split_value_heads else 0, _p(bias), act, _p(att_buf), 1 if return_attention else 0, _p(out),
-                  _row_major_2d(out, "out"), _stream(Q))
+                  _row_major_2d(out, "out"), ctypes.byref(plan_struct) if plan_struct is not None else None, _stream(Q))
 
     try:
         launch(att)

@@ -59,6 +59,7 @@ def timed(fn, label, nbytes):
     print(label, json.dumps(res[label]), flush=True)
 
 
+print("plan:", None if csr.plan is None else (csr.plan.n_tasks, csr.plan.n_hubs, csr.plan.n_slots), flush=True)
 timed(lambda: ops.spmm(csr, w, h), "rmat_spmm_D128", csr.nnz * (4 * D + 8) + n * (4 * D + 8))
 timed(lambda: ops.gat_fused(csr, q, kv[:, :D], kv[:, D:], 8), "rmat_gat", csr.nnz * (8 * D + 4) + n * (8 * D + 8))
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", "bench_rmat.json"), "w"), indent=1)
