@@ -695,6 +695,34 @@ def le_conv(x, edge_index, edge_weight, self_kernel, self_bias, aggr_self_kernel
 
 
 # --------------------------------------------------------------------------------------------------------------
+# nn/pool/common_pool.py  
+# --------------------------------------------------------------------------------------------------------------
+
+def _num_graphs(node_graph_index, num_graphs):
+    return int(np.max(node_graph_index)) + 1 if num_graphs is None else int(num_graphs)
+
+
+def mean_pool(x, node_graph_index, num_graphs=None):
+    """common_pool.py:7-12: segment_sum / (float(segment_count) + 1e-8)."""
+    n = _num_graphs(node_graph_index, num_graphs)
+    cnt = segment_count(np.asarray(node_graph_index, dtype=I32), n)
+    s = unsorted_segment_sum(_as_f32(x), node_graph_index, n)
+    return (s / (cnt.astype(F32)[:, None] + F32(1e-8))).astype(F32)
+
+
+def sum_pool(x, node_graph_index, num_graphs=None):
+    return unsorted_segment_sum(_as_f32(x), node_graph_index, _num_graphs(node_graph_index, num_graphs))
+
+
+def max_pool(x, node_graph_index, num_graphs=None):
+    return unsorted_segment_max(_as_f32(x), node_graph_index, _num_graphs(node_graph_index, num_graphs))
+
+
+def min_pool(x, node_graph_index, num_graphs=None):
+    return unsorted_segment_min(_as_f32(x), node_graph_index, _num_graphs(node_graph_index, num_graphs))
+
+
+# --------------------------------------------------------------------------------------------------------------
 # float64 dense model used by property tests (NOT a restatement: an independent cross-check of the oracle)
 # --------------------------------------------------------------------------------------------------------------
 

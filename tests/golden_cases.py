@@ -59,7 +59,8 @@ class ProductApi(object):
         for name in ("aggregate_neighbors", "identity_mapper", "gcn_mapper", "neighbor_count_mapper", "sum_reducer",
                      "mean_reducer", "max_reducer", "sum_updater", "identity_updater", "segment_softmax", "segment_count",
                      "gcn", "gat", "mean_graph_sage", "sum_graph_sage", "gcn_graph_sage", "mean_pool_graph_sage",
-                     "max_pool_graph_sage", "appnp", "sgc", "ssgc", "tagcn", "gin", "le_conv"):
+                     "max_pool_graph_sage", "appnp", "sgc", "ssgc", "tagcn", "gin", "le_conv", "mean_pool", "sum_pool",
+                     "max_pool", "min_pool"):
             setattr(self, name, getattr(tfg.nn, name))
         for name in ("convert_edge_to_directed", "merge_duplicated_edge", "add_self_loop_edge", "remove_self_loop_edge",
                      "adj_norm_edge"):
@@ -213,3 +214,12 @@ def _replay_propagation(d, api):
            d["le_conv"], "le_conv", **tol)
     _close(O(api.le_conv(x, ei, None, A(d["ws"]), None, A(d["wa"]), None, A(d["wn"]), None, None)), d["le_conv_now"],
            "le_conv unweighted", **tol)
+
+
+def _replay_pool(d, api):
+    A, O = api.arr, api.out
+    g = int(d["g"])
+    for name in ("mean_pool", "sum_pool", "max_pool", "min_pool"):
+        got = O(getattr(api, name)(A(d["x"]), A(d["gi"]), g))
+        _eq(got, d[name], name)                       # bit-exact: sequential fp32 sums in node order
+    _eq(O(api.mean_pool(A(d["x"]), A(d["gi"]))), d["mean_pool_auto"], "mean_pool (num_graphs inferred)")

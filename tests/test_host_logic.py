@@ -38,10 +38,9 @@ def test_graph_casting_rules():
 def test_compute_num_or_size_splits():
     f = tfg.utils.compute_num_or_size_splits
     assert f(128, None) is None and f(128, 1) is None and f(128, 4) == 4
-    assert f(10, 3) == [4, 4, 2]
+    assert f(10, 3) == [4, 4, 2] and f(10, 4) == [3, 3, 3, 1]
     with pytest.raises(Exception):
-        f(10, 4)      # ceil(10/4)=3 -> [3,3,3,1] has 4 parts: valid; use a truly invalid one below
-        f(5, 4)
+        f(5, 4)           # ceil(5/4) = 2 -> [2, 2, 1] has 3 parts, not 4
 
 
 def test_cache_key_format():

@@ -14,21 +14,6 @@ from .gcn import gcn_norm_edge
 from ...sparse import SparseMatrix
 
 
-def _finish(from_x, from_neighbor, bias, activation, concat, normalize):
-    dev = from_x.device
-    if concat:
-        h = torch.cat([from_x, from_neighbor], dim=1)
-    else:
-        h = from_x + from_neighbor
-    if bias is not None:
-        h = h + ops.as_device(bias, torch.float32, device=dev)
-    if activation is not None:
-        h = activation(h)
-    if normalize:
-        h = ops.l2_normalize(h.contiguous())
-    return h
-
-
 def _project_pair(x, agg, self_kernel, neighbor_kernel, bias, activation, concat, normalize):
     """[x @ Ws || agg @ Wn] (+bias, act, l2) with both products written straight into the output columns."""
     dev = x.device

@@ -34,7 +34,11 @@ def _segment_reduce(neighbor_msg, node_index, num_nodes, reduce):
         num_nodes = int(node_index.max().item()) + 1
     csr = _structure.csr_for_segment_ids(node_index, int(num_nodes))
     # message e sits at row e of `msg`: gather through perm, no weights
-    out = ops.spmm(csr, None, msg, reduce=reduce, col=csr.perm)
+    if reduce == "min":       # min(x) = -max(-x): weight -1 per message and epilogue scale -1, both exact
+        minus = torch.full((csr.nnz,), -1.0, dtype=torch.float32, device=msg.device)
+        out = ops.spmm(csr, minus, msg, reduce="max", alpha=-1.0, col=csr.perm)
+    else:
+        out = ops.spmm(csr, None, msg, reduce=reduce, col=csr.perm)
     return out.squeeze(1) if squeeze else out
 
 

@@ -33,6 +33,9 @@ ssgc_m = importlib.import_module("tf_geometric.nn.conv.ssgc")
 tagcn_m = importlib.import_module("tf_geometric.nn.conv.tagcn")
 gin_m = importlib.import_module("tf_geometric.nn.conv.gin")
 le_m = importlib.import_module("tf_geometric.nn.conv.le_conv")
+sys.modules["tf_geometric.nn.pool"] = type(sys)("tf_geometric.nn.pool")
+sys.modules["tf_geometric.nn.pool"].__path__ = [os.path.join(REFERENCE, "tf_geometric", "nn", "pool")]
+pool_m = importlib.import_module("tf_geometric.nn.pool.common_pool")
 
 
 def glorot(rs, a, b):
@@ -203,6 +206,17 @@ def main():
     out["le_conv"] = le_m.le_conv(T(x), T(ei), T(w), T(ws), T(bs), T(wa), T(ba), T(wn), None, tf.nn.relu)
     out["le_conv_now"] = le_m.le_conv(T(x), T(ei), None, T(ws), None, T(wa), None, T(wn), None, None)
     save("propagation", **out)
+
+    # ---- graph pooling ----------------------------------------------------------------------------------
+    n, d, g = 300, 7, 12
+    gi = np.sort(rs.randint(0, g, n)).astype(np.int32)
+    gi[gi == 5] = 6                                   # graph 5 is empty
+    x = rs.randn(n, d).astype(np.float32)
+    out = {"x": x, "gi": gi, "g": g}
+    for name in ("mean_pool", "sum_pool", "max_pool", "min_pool"):
+        out[name] = getattr(pool_m, name)(T(x), T(gi), g)
+    out["mean_pool_auto"] = pool_m.mean_pool(T(x), T(gi))
+    save("pool", **out)
 
 
 if __name__ == "__main__":
