@@ -296,6 +296,7 @@ def run_ours(args, rank, world, local_rank):
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep NCCL's version banner off stdout: one JSON line only
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
     if world > 1:
