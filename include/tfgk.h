@@ -66,6 +66,21 @@ int tfgk_csr_build(const int32_t *row, const int32_t *col, int64_t E, int32_t N_
                    int64_t *rowptr, int32_t *col_sorted, int32_t *perm,
                    void *workspace, size_t workspace_bytes, void *stream);
 
+/* utils/graph_utils.py:67-125 merge_duplicated_edge, index half: duplicates of (row, col) collapse onto their FIRST occurrence
+ * (tf.unique order on the hash num_nodes*row + col, num_nodes = N).  unique_index is [2, E] row-major with the first
+ * *n_unique_host columns valid; unique_of_edge[e] = column of edge e's representative (the segment id the edge properties
+ * are merged with).  Bit-exact; synchronises `stream`. */
+int tfgk_edge_unique_workspace_bytes(int64_t E, int32_t N, size_t *out_bytes);
+int tfgk_edge_unique(const int32_t *row, const int32_t *col, int64_t E, int32_t N, int32_t *unique_index,
+                     int32_t *unique_of_edge, int32_t *n_unique_host, void *workspace, size_t workspace_bytes, void *stream);
+
+/* utils/graph_utils.py:181-190 convert_edge_to_directed, index half: out[2, out_ld] = upper edges followed by the mirrored
+ * non-self-loop upper edges (in order); lower_src[j] = column of the upper edge mirrored into column U + j (to copy its
+ * properties).  upper_index is [2, ld] row-major with U valid columns.  Bit-exact; synchronises `stream`. */
+int tfgk_directed_workspace_bytes(int64_t U, size_t *out_bytes);
+int tfgk_directed_edges(const int32_t *upper_index, int64_t U, int64_t ld, int32_t *out, int64_t out_ld,
+                        int32_t *lower_src, int32_t *n_lower_host, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Work plan of a CSR for the streaming kernels (K1, K3): destination rows are grouped into tasks of at most
  * `rows_per_task` consecutive rows (one warp each), and every row with more than `hub_threshold` edges is cut into slices
  * of `chunk` edges that are reduced by separate warps into `scratch` and merged by a fix-up kernel in slice order

@@ -123,6 +123,23 @@ def install(monkeypatch):
     def l2_normalize(x, out=None):
         return _t(o.l2_normalize(_np(x)))
 
+    def edge_unique(row, col, num_nodes):
+        idx, _ = o.merge_duplicated_edge(np.stack([_np(row), _np(col)]))
+        h = _np(row).astype(np.int64) * num_nodes + _np(col)
+        _, of_edge = o.tf_unique(h)
+        return _t(idx), _t(of_edge.astype(np.int32))
+
+    def directed_edges(upper):
+        up = _np(upper)
+        mask = up[0] != up[1]
+        lower = np.stack([up[1][mask], up[0][mask]])
+        return _t(np.concatenate([up, lower], axis=1).astype(np.int32)), _t(np.nonzero(mask)[0].astype(np.int32))
+
+    from tf_geometric_b200.utils import graph_utils as gu
+    monkeypatch.setattr(gu, "_is_device", lambda t: torch.is_tensor(t))     # CPU tensors take the device code path
+    monkeypatch.setattr(ops, "edge_unique", edge_unique)
+    monkeypatch.setattr(ops, "directed_edges", directed_edges)
+
     for name, fn in dict(self_loops=self_loops, self_loop_weights=self_loop_weights, segment_count=segment_count,
                          csr_build=csr_build, permute=permute, csr_rowsum=csr_rowsum, deg_inv=deg_inv,
                          scale_edges=scale_edges, spmm=spmm, segment_softmax_csr=segment_softmax_csr,

@@ -30,7 +30,7 @@ def test_library_is_built_and_loads():
 def test_every_declared_symbol_is_exported_and_bound():
     decl = _header_functions()
     names = [n for n, _ in decl]
-    assert len(names) >= 21
+    assert len(names) >= 25
     handle = ctypes.CDLL(_ffi.library_path())
     for name in names:
         assert hasattr(handle, name), "{} declared in include/tfgk.h but not exported".format(name)

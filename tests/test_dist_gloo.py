@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 class _Patch(object):
     def setattr(self, obj, name, value):
-        setattr(obj, name, value)
+        setattr(obj, name, value)      # worker processes are short-lived: no undo needed
 
 
 def _free_port():

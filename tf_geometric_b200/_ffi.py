@@ -32,6 +32,10 @@ SIGNATURES = {
     "tfgk_segment_count_i32": [_ptr, _i64, _i32, _ptr, _ptr],
     "tfgk_csr_workspace_bytes": [_i64, _i32, ctypes.POINTER(_size)],
     "tfgk_csr_build": [_ptr, _ptr, _i64, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _size, _ptr],
+    "tfgk_edge_unique_workspace_bytes": [_i64, _i32, ctypes.POINTER(_size)],
+    "tfgk_edge_unique": [_ptr, _ptr, _i64, _i32, _ptr, _ptr, ctypes.POINTER(_i32), _ptr, _size, _ptr],
+    "tfgk_directed_workspace_bytes": [_i64, ctypes.POINTER(_size)],
+    "tfgk_directed_edges": [_ptr, _i64, _i64, _ptr, _i64, _ptr, ctypes.POINTER(_i32), _ptr, _size, _ptr],
     "tfgk_plan_capacity": [_i64, _i32, _i32, _i32, _i32, ctypes.POINTER(_i64), ctypes.POINTER(_i64)],
     "tfgk_plan_workspace_bytes": [_i32, ctypes.POINTER(_size)],
     "tfgk_plan_build": [_ptr, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64,

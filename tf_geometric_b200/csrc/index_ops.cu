@@ -287,6 +287,101 @@ __global__ void __launch_bounds__(kRsThreads) rs_scatter_kernel(const int32_t *_
     }
 }
 
+
+// Stable LSD radix sort of int32 keys in [0, max_key] carrying the original positions; the sorted positions land in
+// `perm_out`.  keys_a/keys_b/vals_b/hist/sums are scratch (E ints each for the first three).
+static int stable_sort_positions(const int32_t *keys, int64_t E, int64_t max_key_exclusive, int32_t *perm_out,
+                                 int32_t *keys_a, int32_t *keys_b, int32_t *vals_b, uint32_t *hist, void *sums, int nblk,
+                                 cudaStream_t st) {
+    int bits = 1;
+    while (bits < 31 && (1ll << bits) < max_key_exclusive) ++bits;
+    const int passes = (bits + 7) / 8;
+    const int32_t *kin = keys;
+    const int32_t *vin = nullptr;   // implicit iota
+    for (int p = 1; p <= passes; ++p) {
+        const bool to_x = ((passes - p) % 2) == 0;        // X = (keys_a, perm_out), Y = (keys_b, vals_b)
+        int32_t *kout = to_x ? keys_a : keys_b;
+        int32_t *vout = to_x ? perm_out : vals_b;
+        const int shift = (p - 1) * 8;
+        rs_hist_kernel<<<nblk, kRsThreads, 0, st>>>(kin, E, shift, hist, nblk);
+        TFGK_LAUNCH_CHECK();
+        const int64_t n_hist = (int64_t)kRadix * nblk;
+        const int rc = exclusive_scan<uint32_t, uint32_t>(hist, n_hist, n_hist, hist, reinterpret_cast<uint32_t *>(sums), st);
+        if (rc != TFGK_OK) return rc;
+        rs_scatter_kernel<<<nblk, kRsThreads, 0, st>>>(kin, vin, E, shift, hist, nblk, p == passes ? nullptr : kout, vout);
+        TFGK_LAUNCH_CHECK();
+        kin = kout;
+        vin = vout;
+    }
+    return TFGK_OK;
+}
+
+// ---- duplicate-edge detection (utils/graph_utils.py:67-125: hash = n*row+col, tf.unique first-occurrence order) ----------
+__global__ void gather2_i32_kernel(const int32_t *__restrict__ a, const int32_t *__restrict__ b,
+                                   const int32_t *__restrict__ perm, int64_t E, int32_t *__restrict__ a_out,
+                                   int32_t *__restrict__ b_out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < E; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t p = perm[i];
+        if (a_out) a_out[i] = a[p];
+        if (b_out) b_out[i] = b[p];
+    }
+}
+
+// in (row, col)-sorted order: flag the first edge of every group of equal (row, col)
+__global__ void group_flag_kernel(const int32_t *__restrict__ sr, const int32_t *__restrict__ sc, int64_t E,
+                                  int32_t *__restrict__ flag) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < E; i += (int64_t)gridDim.x * blockDim.x)
+        flag[i] = (i == 0 || sr[i] != sr[i - 1] || sc[i] != sc[i - 1]) ? 1 : 0;
+}
+
+// group g (sorted order) starts where flag == 1; its first occurrence in the input is the position stored there
+__global__ void group_first_kernel(const int32_t *__restrict__ flag, const int32_t *__restrict__ gid_excl,
+                                   const int32_t *__restrict__ pos_sorted, int64_t E, int32_t *__restrict__ first_pos) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < E; i += (int64_t)gridDim.x * blockDim.x)
+        if (flag[i]) first_pos[gid_excl[i]] = pos_sorted[i];      // stable sort: the group's smallest input position
+}
+
+// rank_of_group[order[j]] = j ; then per edge: unique_of_edge[pos_sorted[i]] = rank_of_group[group(i)], and the unique edge
+// list in first-occurrence order
+__global__ void invert_perm_kernel(const int32_t *__restrict__ order, int64_t n, int32_t *__restrict__ rank) {
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
+        rank[order[j]] = (int32_t)j;
+}
+
+__global__ void unique_emit_kernel(const int32_t *__restrict__ flag, const int32_t *__restrict__ gid_excl,
+                                   const int32_t *__restrict__ rank, const int32_t *__restrict__ pos_sorted,
+                                   const int32_t *__restrict__ sr, const int32_t *__restrict__ sc, int64_t E, int64_t cap,
+                                   int32_t *__restrict__ unique_index, int32_t *__restrict__ unique_of_edge) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < E; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t g = flag[i] ? gid_excl[i] : gid_excl[i] - 1;    // exclusive scan of the flags -> group id
+        const int32_t u = rank[g];
+        unique_of_edge[pos_sorted[i]] = u;
+        if (flag[i]) { unique_index[u] = sr[i]; unique_index[cap + u] = sc[i]; }
+    }
+}
+
+// convert_edge_to_directed (utils/graph_utils.py:181-190): mirrored copies of the non-self-loop upper edges, in order
+__global__ void nonloop_flag_kernel(const int32_t *__restrict__ idx, int64_t U, int64_t ld, int32_t *__restrict__ flag) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < U; i += (int64_t)gridDim.x * blockDim.x)
+        flag[i] = idx[i] != idx[ld + i] ? 1 : 0;
+}
+
+__global__ void directed_emit_kernel(const int32_t *__restrict__ idx, int64_t U, int64_t ld, const int32_t *__restrict__ flag,
+                                     const int32_t *__restrict__ off, int64_t out_ld, int32_t *__restrict__ out,
+                                     int32_t *__restrict__ lower_src) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < U; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t r = idx[i], c = idx[ld + i];
+        out[i] = r;
+        out[out_ld + i] = c;
+        if (flag[i]) {
+            const int64_t j = U + off[i];
+            out[j] = c;
+            out[out_ld + j] = r;
+            lower_src[off[i]] = (int32_t)i;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // work plan: runs of <= rows_per_task light rows, hub rows cut into `chunk`-edge slices
 // ------------------------------------------------------------------------------------------------------------
@@ -473,30 +568,121 @@ int tfgk_csr_build(const int32_t *row, const int32_t *col, int64_t E, int32_t N_
     if (rc != TFGK_OK) return rc;
 
     // 3. stable LSD radix sort of (row, position); the last pass lands in `perm`
-    int bits = 1;
-    while (bits < 31 && (1ll << bits) < (int64_t)N_rows) ++bits;
-    const int passes = (bits + 7) / 8;
-    const int32_t *kin = row;
-    const int32_t *vin = nullptr;   // implicit iota
-    for (int p = 1; p <= passes; ++p) {
-        const bool to_x = ((passes - p) % 2) == 0;        // X = (keys_a, perm), Y = (keys_b, vals_b)
-        int32_t *kout = to_x ? keys_a : keys_b;
-        int32_t *vout = to_x ? perm : vals_b;
-        const int shift = (p - 1) * 8;
-        rs_hist_kernel<<<L.nblk, kRsThreads, 0, st>>>(kin, E, shift, hist, L.nblk);
-        TFGK_LAUNCH_CHECK();
-        const int64_t n_hist = (int64_t)kRadix * L.nblk;
-        rc = exclusive_scan<uint32_t, uint32_t>(hist, n_hist, n_hist, hist, reinterpret_cast<uint32_t *>(sums), st);
-        if (rc != TFGK_OK) return rc;
-        rs_scatter_kernel<<<L.nblk, kRsThreads, 0, st>>>(kin, vin, E, shift, hist, L.nblk,
-                                                         p == passes ? nullptr : kout, vout);
-        TFGK_LAUNCH_CHECK();
-        kin = kout;
-        vin = vout;
-    }
+    rc = stable_sort_positions(row, E, N_rows, perm, keys_a, keys_b, vals_b, hist, sums, L.nblk, st);
+    if (rc != TFGK_OK) return rc;
     // 4. col_sorted = col[perm]
     gather_i32_kernel<<<grid_for(E), 256, 0, st>>>(col, perm, E, col_sorted);
     TFGK_LAUNCH_CHECK();
+    return TFGK_OK;
+}
+
+int tfgk_edge_unique_workspace_bytes(int64_t E, int32_t N, size_t *out_bytes) {
+    TFGK_CHECK_ARG(out_bytes != nullptr, "edge_unique_workspace_bytes: null output");
+    TFGK_CHECK_ARG(E >= 0 && N >= 0 && E < (1ll << 31), "edge_unique_workspace_bytes: need 0 <= E < 2^31, N >= 0");
+    *out_bytes = CsrWorkspace(E, N).total + 9 * align_up((size_t)(E + 1) * 4);
+    return TFGK_OK;
+}
+
+int tfgk_edge_unique(const int32_t *row, const int32_t *col, int64_t E, int32_t N, int32_t *unique_index,
+                     int32_t *unique_of_edge, int32_t *n_unique_host, void *workspace, size_t workspace_bytes, void *stream) {
+    TFGK_CHECK_ARG(E >= 0 && E < (1ll << 31) && N >= 0, "edge_unique: need 0 <= E < 2^31, N >= 0");
+    TFGK_CHECK_ARG(n_unique_host != nullptr, "edge_unique: null count");
+    *n_unique_host = 0;
+    if (E == 0) return TFGK_OK;
+    TFGK_CHECK_ARG(row && col && unique_index && unique_of_edge, "edge_unique: null pointer");
+    size_t need = 0;
+    tfgk_edge_unique_workspace_bytes(E, N, &need);
+    if (workspace == nullptr || workspace_bytes < need)
+        return set_error(TFGK_ERR_WORKSPACE, "edge_unique: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+    cudaStream_t st = as_stream(stream);
+    const CsrWorkspace L(E, N);
+    char *ws = static_cast<char *>(workspace);
+    int32_t *flagv = reinterpret_cast<int32_t *>(ws + L.off_flag);
+    int32_t *keys_a = reinterpret_cast<int32_t *>(ws + L.off_keys_a), *keys_b = reinterpret_cast<int32_t *>(ws + L.off_keys_b);
+    int32_t *vals_b = reinterpret_cast<int32_t *>(ws + L.off_vals_b);
+    uint32_t *hist = reinterpret_cast<uint32_t *>(ws + L.off_hist);
+    void *sums = ws + L.off_sums;
+    const size_t arr = align_up((size_t)(E + 1) * 4);
+    char *extra = ws + L.total;
+    int32_t *perm1 = reinterpret_cast<int32_t *>(extra), *rows1 = reinterpret_cast<int32_t *>(extra + arr);
+    int32_t *perm2 = reinterpret_cast<int32_t *>(extra + 2 * arr), *pos = reinterpret_cast<int32_t *>(extra + 3 * arr);
+    int32_t *sr = reinterpret_cast<int32_t *>(extra + 4 * arr), *sc = reinterpret_cast<int32_t *>(extra + 5 * arr);
+    int32_t *flag = reinterpret_cast<int32_t *>(extra + 6 * arr), *gid = reinterpret_cast<int32_t *>(extra + 7 * arr);
+    int32_t *first_pos = reinterpret_cast<int32_t *>(extra + 8 * arr);
+
+    TFGK_CUDA(cudaMemsetAsync(flagv, 0, 4, st));
+    validate_kernel<<<grid_for(E), 256, 0, st>>>(row, E, N, flagv);
+    TFGK_LAUNCH_CHECK();
+    validate_kernel<<<grid_for(E), 256, 0, st>>>(col, E, N, flagv);
+    TFGK_LAUNCH_CHECK();
+    int32_t bad = 0;
+    TFGK_CUDA(cudaMemcpyAsync(&bad, flagv, 4, cudaMemcpyDeviceToHost, st));
+    TFGK_CUDA(cudaStreamSynchronize(st));
+    if (bad) return set_error(TFGK_ERR_INDEX_OUT_OF_RANGE, "edge_unique: edge_index holds node ids outside [0, N)");
+
+    // sort by (row, col) = by the reference's hash n*row+col: stable by col, then stable by row
+    int rc = stable_sort_positions(col, E, N, perm1, keys_a, keys_b, vals_b, hist, sums, L.nblk, st);
+    if (rc != TFGK_OK) return rc;
+    gather2_i32_kernel<<<grid_for(E), 256, 0, st>>>(row, nullptr, perm1, E, rows1, nullptr);
+    TFGK_LAUNCH_CHECK();
+    rc = stable_sort_positions(rows1, E, N, perm2, keys_a, keys_b, vals_b, hist, sums, L.nblk, st);
+    if (rc != TFGK_OK) return rc;
+    gather2_i32_kernel<<<grid_for(E), 256, 0, st>>>(perm1, nullptr, perm2, E, pos, nullptr);       // input position of sorted slot i
+    TFGK_LAUNCH_CHECK();
+    gather2_i32_kernel<<<grid_for(E), 256, 0, st>>>(row, col, pos, E, sr, sc);
+    TFGK_LAUNCH_CHECK();
+    group_flag_kernel<<<grid_for(E), 256, 0, st>>>(sr, sc, E, flag);
+    TFGK_LAUNCH_CHECK();
+    rc = exclusive_scan<int32_t, int32_t>(flag, E, E + 1, gid, reinterpret_cast<int32_t *>(sums), st);
+    if (rc != TFGK_OK) return rc;
+    int32_t n_unique = 0;
+    TFGK_CUDA(cudaMemcpyAsync(&n_unique, gid + E, 4, cudaMemcpyDeviceToHost, st));
+    TFGK_CUDA(cudaStreamSynchronize(st));
+    *n_unique_host = n_unique;
+    group_first_kernel<<<grid_for(E), 256, 0, st>>>(flag, gid, pos, E, first_pos);
+    TFGK_LAUNCH_CHECK();
+    // rank the groups by their first occurrence (tf.unique order): sort the groups by first_pos (keys < E)
+    int32_t *order = perm1, *rank = rows1;       // scratch reuse: perm1 / rows1 are dead now
+    const int nblk_u = (int)ceil_div64(n_unique, kRsTile);
+    rc = stable_sort_positions(first_pos, n_unique, E, order, keys_a, keys_b, vals_b, hist, sums, nblk_u, st);
+    if (rc != TFGK_OK) return rc;
+    invert_perm_kernel<<<grid_for(n_unique), 256, 0, st>>>(order, n_unique, rank);
+    TFGK_LAUNCH_CHECK();
+    unique_emit_kernel<<<grid_for(E), 256, 0, st>>>(flag, gid, rank, pos, sr, sc, E, E, unique_index, unique_of_edge);
+    TFGK_LAUNCH_CHECK();
+    return TFGK_OK;
+}
+
+int tfgk_directed_workspace_bytes(int64_t U, size_t *out_bytes) {
+    TFGK_CHECK_ARG(out_bytes != nullptr && U >= 0 && U < (1ll << 30), "directed_workspace_bytes: bad argument");
+    *out_bytes = 2 * align_up((size_t)(U + 1) * 4) + align_up((size_t)(ceil_div64(U + 1, kScanTile) + 1) * 8) + 256;
+    return TFGK_OK;
+}
+
+int tfgk_directed_edges(const int32_t *upper_index, int64_t U, int64_t ld, int32_t *out, int64_t out_ld,
+                        int32_t *lower_src, int32_t *n_lower_host, void *workspace, size_t workspace_bytes, void *stream) {
+    TFGK_CHECK_ARG(U >= 0 && U < (1ll << 30) && ld >= U && out_ld >= 2 * U, "directed_edges: bad size");
+    TFGK_CHECK_ARG(n_lower_host != nullptr, "directed_edges: null count");
+    *n_lower_host = 0;
+    if (U == 0) return TFGK_OK;
+    TFGK_CHECK_ARG(upper_index && out && lower_src, "directed_edges: null pointer");
+    size_t need = 0;
+    tfgk_directed_workspace_bytes(U, &need);
+    if (workspace == nullptr || workspace_bytes < need)
+        return set_error(TFGK_ERR_WORKSPACE, "directed_edges: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+    cudaStream_t st = as_stream(stream);
+    char *ws = static_cast<char *>(workspace);
+    const size_t arr = align_up((size_t)(U + 1) * 4);
+    int32_t *flag = reinterpret_cast<int32_t *>(ws), *off = reinterpret_cast<int32_t *>(ws + arr);
+    int32_t *sums = reinterpret_cast<int32_t *>(ws + 2 * arr);
+    nonloop_flag_kernel<<<grid_for(U), 256, 0, st>>>(upper_index, U, ld, flag);
+    TFGK_LAUNCH_CHECK();
+    const int rc = exclusive_scan<int32_t, int32_t>(flag, U, U + 1, off, sums, st);
+    if (rc != TFGK_OK) return rc;
+    TFGK_CUDA(cudaMemcpyAsync(n_lower_host, off + U, 4, cudaMemcpyDeviceToHost, st));
+    directed_emit_kernel<<<grid_for(U), 256, 0, st>>>(upper_index, U, ld, flag, off, out_ld, out, lower_src);
+    TFGK_LAUNCH_CHECK();
+    TFGK_CUDA(cudaStreamSynchronize(st));
     return TFGK_OK;
 }
 

@@ -182,12 +182,51 @@ def build_plan(csr):
     return Plan(arrays, n_tasks, n_hubs, n_slots)
 
 
+def edge_unique(row, col, num_nodes):
+    """Unique (row, col) pairs in first-occurrence order and, per edge, the index of its representative
+    (merge_duplicated_edge's tf.unique step).  Returns (unique_edge_index int32 [2, U], unique_of_edge int32 [E])."""
+    _check(row, torch.int32, "row")
+    _check(col, torch.int32, "col")
+    E = row.numel()
+    dev = row.device
+    need = ctypes.c_size_t()
+    _ffi.call("tfgk_edge_unique_workspace_bytes", E, num_nodes, ctypes.byref(need))
+    ws = torch.empty((max(need.value, 1),), dtype=torch.uint8, device=dev)
+    uniq = torch.empty((2, max(E, 1)), dtype=torch.int32, device=dev)
+    of_edge = torch.empty((E,), dtype=torch.int32, device=dev)
+    n_unique = ctypes.c_int32()
+    _ffi.call("tfgk_edge_unique", _p(row), _p(col), E, num_nodes, _p(uniq), _p(of_edge), ctypes.byref(n_unique), _p(ws),
+              need.value, _stream(row))
+    return uniq[:, :n_unique.value].contiguous(), of_edge
+
+
+def directed_edges(upper_index):
+    """upper edges followed by the mirrored non-self-loop upper edges; also the source column of every mirrored edge."""
+    _check(upper_index, torch.int32, "upper_index")
+    U = upper_index.shape[1]
+    dev = upper_index.device
+    need = ctypes.c_size_t()
+    _ffi.call("tfgk_directed_workspace_bytes", U, ctypes.byref(need))
+    ws = torch.empty((max(need.value, 1),), dtype=torch.uint8, device=dev)
+    out = torch.empty((2, max(2 * U, 1)), dtype=torch.int32, device=dev)
+    lower_src = torch.empty((max(U, 1),), dtype=torch.int32, device=dev)
+    n_lower = ctypes.c_int32()
+    _ffi.call("tfgk_directed_edges", _p(upper_index), U, U, _p(out), max(2 * U, 1), _p(lower_src), ctypes.byref(n_lower),
+              _p(ws), need.value, _stream(upper_index))
+    return out[:, :U + n_lower.value].contiguous(), lower_src[:n_lower.value]
+
+
 def permute(src, perm, inverse=False):
     """COO-order values -> CSR order (dst[i] = src[perm[i]]), or back with inverse=True.  src: [E] or [E, W]."""
     _check(src, torch.float32, "src")
     _check(perm, torch.int32, "perm")
     width = 1 if src.dim() == 1 else src.shape[1]
-    dst = torch.empty_like(src)
+    if inverse:
+        if src.shape[0] != perm.numel():
+            raise ValueError("unpermute: src must have one row per index")
+        dst = torch.empty_like(src)
+    else:                                    # a gather: one output row per index (perm may select a subset of src)
+        dst = torch.empty((perm.numel(),) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
     _ffi.call("tfgk_unpermute_f32" if inverse else "tfgk_permute_f32", _p(src), _p(perm), perm.numel(), width, _p(dst),
               _stream(src))
     return dst

@@ -1,9 +1,10 @@
 # coding=utf-8
 """Edge-index integer preprocessing with the reference's semantics (utils/graph_utils.py of tf_geometric).
 
-Device inputs (torch CUDA tensors) run on the GPU kernels; numpy/list inputs return numpy, like the reference does
-for non-tensor inputs.  The hash/unique based helpers (merge_duplicated_edge, convert_edge_to_upper/directed) are the
-reference's eager, host-side one-off preprocessing and stay on the host in this round.
+Device inputs (torch CUDA tensors) run on the GPU kernels - including the hash/unique based helpers
+(merge_duplicated_edge, convert_edge_to_upper, convert_edge_to_directed: tfgk_edge_unique / tfgk_directed_edges, bit-exact
+with tf.unique's first-occurrence order) - and return device tensors.  numpy / list inputs are processed with numpy and
+return numpy, exactly like the reference does for non-tensor inputs (its eager host path).
 """
 import numpy as np
 import torch
@@ -84,6 +85,8 @@ def merge_duplicated_edge(edge_index, edge_props=None, merge_modes=None):
             merge_modes = ["sum"] * len(edge_props)
         elif type(merge_modes) is not list:
             raise Exception("type error: merge_modes should be a list of strings")
+    if _is_device(edge_index):
+        return _merge_duplicated_edge_device(edge_index, edge_props, merge_modes)
     ei = _to_numpy(edge_index).astype(np.int32)
     edge_hash, hash_n = convert_edge_index_to_edge_hash(ei)
     uniq_hash, uniq_idx = _first_occurrence_unique(edge_hash)
@@ -101,8 +104,34 @@ def merge_duplicated_edge(edge_index, edge_props=None, merge_modes=None):
     return out_index, out_props
 
 
+def _merge_duplicated_edge_device(edge_index, edge_props, merge_modes):
+    from ..nn.kernel.map_reduce import _segment_reduce
+    ei = edge_index if edge_index.dtype == torch.int32 else edge_index.to(torch.int32)
+    ei = ei.contiguous()
+    if ei.shape[1] == 0:
+        return ei, (None if edge_props is None else list(edge_props))
+    hash_n = int(ei.max().item()) + 1                                 # reference: num_nodes = reduce_max(edge_index) + 1
+    uniq_index, of_edge = ops.edge_unique(ei[0].contiguous(), ei[1].contiguous(), hash_n)
+    if edge_props is None:
+        return uniq_index, None
+    out = []
+    for prop, mode in zip(edge_props, merge_modes):
+        if prop is None:
+            out.append(None)
+            continue
+        if mode not in ("sum", "min", "max", "mean"):
+            raise Exception("wrong merge mode: {}".format(mode))
+        p = ops.as_device(prop, torch.float32, device=ei.device)
+        out.append(_segment_reduce(p, of_edge, uniq_index.shape[1], mode))
+    return uniq_index, out
+
+
 def convert_edge_to_upper(edge_index, edge_props=None, merge_modes=None):
     """(min(u,v), max(u,v)) for every edge, then merge duplicates (reference :128-151)."""
+    if _is_device(edge_index):
+        ei = edge_index.to(torch.int32)
+        upper = torch.stack([torch.minimum(ei[0], ei[1]), torch.maximum(ei[0], ei[1])]).contiguous()
+        return merge_duplicated_edge(upper, edge_props, merge_modes)
     ei = _to_numpy(edge_index).astype(np.int32)
     upper = np.stack([ei.min(axis=0), ei.max(axis=0)], axis=0)
     upper_index, upper_props = merge_duplicated_edge(_like(upper, edge_index, torch.int32), edge_props, merge_modes)
@@ -114,6 +143,21 @@ def convert_edge_to_directed(edge_index, edge_props=None, merge_modes=None):
     if edge_props is not None and len(edge_props) > 0 and merge_modes is None:
         merge_modes = ["sum"] * len(edge_props)
     upper_index, upper_props = convert_edge_to_upper(edge_index, edge_props, merge_modes)
+    if _is_device(edge_index):
+        if upper_index.shape[1] == 0:
+            return edge_index, edge_props
+        out_index, lower_src = ops.directed_edges(upper_index.contiguous())
+        if lower_src.numel() == 0:                                     # only self loops: reference returns the inputs
+            return edge_index, edge_props
+        if edge_props is None:
+            return out_index, None
+        out_props = []
+        for prop, up_prop in zip(edge_props, upper_props):
+            if prop is None:
+                out_props.append(None)
+            else:
+                out_props.append(torch.cat([up_prop, ops.permute(up_prop.contiguous(), lower_src)]))
+        return out_index, out_props
     up = _to_numpy(upper_index)
     mask = up[0] != up[1]
     if not mask.any():
