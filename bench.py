@@ -218,7 +218,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": res["edges_per_s"], "unit": "edges/s", "cores": res["cores"], "kind": "port",
                              "sample": sample},
             "e2e": {"value": res["edges_per_s"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world):
@@ -393,7 +393,31 @@ def run_ours(args, rank, world, local_rank):
             "roofline": roofline, "cpu_baseline": cpu_base,
             "breakdown_ms": {"gcn_spmm": spmm_ms, "gat_fused": gat_ms, "dense_projections": gemm_ms,
                              "cache_build_s": t_cache}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+class StdoutToStderr(object):
+    """Routes file descriptor 1 to stderr while the benchmark runs (NCCL / library banners must not pollute the ONE JSON
+    line the driver parses) and restores it for the final print."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+_RESULT_LINES = []
+
+
+def emit(line):
+    """Collect the JSON line; main() prints it once stdout is restored."""
+    _RESULT_LINES.append(json.dumps(line))
 
 
 def main():
@@ -401,13 +425,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device for --impl ours (there is no CPU fallback); "
-                         "use --impl reference for the CPU arm")
-    run_ours(args, rank, world, local_rank)
+    with StdoutToStderr():
+        if args.impl == "reference":
+            run_reference(args, rank, world)
+        else:
+            if not torch.cuda.is_available():
+                raise SystemExit("bench.py needs a CUDA device for --impl ours (there is no CPU fallback); "
+                                 "use --impl reference for the CPU arm")
+            run_ours(args, rank, world, local_rank)
+    for line in _RESULT_LINES:
+        print(line, flush=True)
 
 
 if __name__ == "__main__":

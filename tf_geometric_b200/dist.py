@@ -289,5 +289,5 @@ def bench_partitioned(args, rank, world, device, metric, config):
                              "algorithmic_bytes": gat_bytes, "kernel_ms": gat_ms},
                 "cpu_baseline": None,
                 "exchange": {"collective": "all_gather_into_tensor (NCCL), async: K|V exchange overlaps the GCN aggregation", "halo_bytes_in_per_rank_per_step": halo}}
-        print(json.dumps(line), flush=True)
+        B.emit(line)
     dist.destroy_process_group()
