@@ -412,12 +412,16 @@ class StdoutToStderr(object):
         os.close(self.saved)
 
 
-_RESULT_LINES = []
+def _result_lines():
+    # bench.py runs as __main__ and is also imported as `bench` by tf_geometric_b200.dist: share the list through `sys`
+    if not hasattr(sys, "_tfgk_bench_lines"):
+        sys._tfgk_bench_lines = []
+    return sys._tfgk_bench_lines
 
 
 def emit(line):
     """Collect the JSON line; main() prints it once stdout is restored."""
-    _RESULT_LINES.append(json.dumps(line))
+    _result_lines().append(json.dumps(line))
 
 
 def main():
@@ -433,7 +437,7 @@ def main():
                 raise SystemExit("bench.py needs a CUDA device for --impl ours (there is no CPU fallback); "
                                  "use --impl reference for the CPU arm")
             run_ours(args, rank, world, local_rank)
-    for line in _RESULT_LINES:
+    for line in _result_lines():
         print(line, flush=True)
 
 
