@@ -241,3 +241,64 @@ def test_propagation_layers_sgc_ssgc_tagcn_gin_leconv():
     out = layer([g.x, g.edge_index])
     want = o.gin(x, ei, lambda h: o.relu((h @ mlp_w).astype(np.float32)), eps=0.5)
     assert_close(host(out), want, what="GIN")
+
+
+@pytest.mark.parametrize("sym", [True, False])
+def test_gcn_two_layer_forward_backward(sym):
+    """demo/demo_gcn.py wiring with gradients: loss = sum(logits * G) through two GCN layers (relu between), grads w.r.t. x,
+    both kernels and biases against torch-CPU autograd over the reference's op sequence."""
+    rs = np.random.RandomState(41)
+    n, f, hidden, classes = 2000, 60, 16, 7
+    ei = random_graph(n, 24000, seed=43, symmetric=sym, isolated=3, hub=(5, 2600))
+    w = (rs.rand(ei.shape[1]) + 0.2).astype(np.float32)
+    if sym:
+        w[len(w) // 2:] = w[:len(w) // 2]
+    x = rs.randn(n, f).astype(np.float32)
+    k0, b0, k1, b1 = glorot(rs, f, hidden), rs.randn(hidden).astype(np.float32), glorot(rs, hidden, classes), rs.randn(classes).astype(np.float32)
+    G = rs.randn(n, classes).astype(np.float32)
+    normed = o.gcn_norm_adj(o.SparseMatrix(ei, w, [n, n]), sym=sym)
+    row, col = torch.from_numpy(normed.index[0]).long(), torch.from_numpy(normed.index[1]).long()
+    val = torch.from_numpy(normed.value)
+    tx, tk0, tb0, tk1, tb1 = (torch.tensor(a, requires_grad=True) for a in (x, k0, b0, k1, b1))
+
+    def layer(h, kern, b, relu):
+        hw = h @ kern
+        out = torch.zeros((n, hw.shape[1])).index_add_(0, row, hw.index_select(0, col) * val.unsqueeze(1)) + b
+        return torch.relu(out) if relu else out
+    logits = layer(layer(tx, tk0, tb0, True), tk1, tb1, False)
+    (logits * torch.from_numpy(G)).sum().backward()
+
+    dx, dk0, db0, dk1, db1 = (dev(a).requires_grad_(True) for a in (x, k0, b0, k1, b1))
+    adj = tfg.SparseMatrix(ei, w, [n, n])
+    cache = {}
+    h = tfg.nn.gcn(dx, adj, dk0, db0, tfg.nn.relu, sym=sym, cache=cache)
+    out = tfg.nn.gcn(h, adj, dk1, db1, None, sym=sym, cache=cache)
+    assert out.requires_grad and len(cache) == 1
+    assert_close(host(out), logits.detach().numpy(), what="2-layer gcn fwd (autograd path)")
+    (out * dev(G)).sum().backward()
+    for name, got, want in (("dx", dx.grad, tx.grad), ("dW0", dk0.grad, tk0.grad), ("db0", db0.grad, tb0.grad),
+                            ("dW1", dk1.grad, tk1.grad), ("db1", db1.grad, tb1.grad)):
+        assert_close(host(got), want.numpy(), what="gcn " + name)
+
+
+def test_trainable_gcn_layer_one_sgd_step_reduces_loss():
+    """A GCN layer created with trainable=True: forward, backward and one SGD step through the public layer API."""
+    rs = np.random.RandomState(3)
+    n, f, c = 1500, 40, 5
+    ei = random_graph(n, 18000, seed=4, symmetric=True)
+    x = rs.randn(n, f).astype(np.float32)
+    y = dev(rs.randn(n, c).astype(np.float32))
+    g = tfg.Graph(x, ei).to_device()
+    layer = tfg.layers.GCN(c, seed=5, trainable=True)
+    layer.build_cache_for_graph(g)
+    opt = torch.optim.SGD(layer.parameters(), lr=0.05)
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        out = layer([g.x, g.edge_index, g.edge_weight], cache=g.cache)
+        loss = ((out - y) ** 2).mean()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert losses[2] < losses[1] < losses[0]
+    assert layer.kernel.grad is not None and torch.isfinite(layer.kernel.grad).all()

@@ -89,6 +89,8 @@ def test_model_paths(fake):
     test_gpu_models.test_graph_sage_forward_backward("mean", True, False)
     test_gpu_models.test_graph_sage_forward_backward("sum", True, True)
     test_gpu_models.test_propagation_layers_sgc_ssgc_tagcn_gin_leconv()
+    test_gpu_models.test_gcn_two_layer_forward_backward(True)
+    test_gpu_models.test_gcn_two_layer_forward_backward(False)
 
 
 def test_golden_fixtures_through_public_api(fake):

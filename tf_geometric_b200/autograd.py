@@ -78,5 +78,38 @@ class Dense(torch.autograd.Function):
         return grad_x, grad_w, grad_b, None
 
 
+class SparseMatmul(torch.autograd.Function):
+    """y = act(A @ h + b) for a cached SparseMatrix A (gcn.py:280-288), differentiable w.r.t. h and b.
+    dh = A^T dz runs the same kernel on the transposed structure of A (built once per matrix, values permuted into it);
+    dz = dy * (y > 0) for relu."""
+
+    @staticmethod
+    def forward(ctx, h, bias, adj, act_code):
+        y = ops.spmm(adj.csr, adj.value_csr, h.detach(), reduce="sum", bias=None if bias is None else bias.detach(),
+                     act=act_code)
+        ctx.adj = adj
+        ctx.act_code = act_code
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(y if act_code == ops.ACT_RELU else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        (y,) = ctx.saved_tensors
+        g = grad_y.contiguous()
+        if ctx.act_code == ops.ACT_RELU:
+            g = g * (y > 0).to(g.dtype)
+        adj = ctx.adj
+        csr_t = adj._transposed_csr()
+        if getattr(adj, "_value_csc", None) is None:
+            adj._value_csc = ops.permute(adj.value, csr_t.perm)
+        grad_h = ops.spmm(csr_t, adj._value_csc, g, reduce="sum") if ctx.needs_input_grad[0] else None
+        grad_b = None
+        if ctx.has_bias and ctx.needs_input_grad[1]:
+            ones = torch.ones((g.shape[0], 1), dtype=torch.float32, device=g.device)
+            grad_b = ops.gemm(ones, g, trans_a=True).reshape(-1)
+        return grad_h, grad_b, None, None
+
+
 def needs_grad(*tensors):
     return torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in tensors)

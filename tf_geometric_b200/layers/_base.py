@@ -16,6 +16,9 @@ class Layer(torch.nn.Module):
         super().__init__()
         self.built = False
         self._seed = kwargs.pop("seed", None)
+        # Keras weights are trainable by default; here weights only require grad when asked, so that plain forward calls
+        # take the fused inference kernels.  Backward passes exist for GCN and mean/sum GraphSAGE (autograd.py).
+        self._trainable = bool(kwargs.pop("trainable", False))
 
     def add_weight(self, name, shape, initializer="glorot_uniform", regularizer=None, device=None):
         shape = [int(s) for s in shape]
@@ -32,7 +35,7 @@ class Layer(torch.nn.Module):
             w.copy_((torch.rand(shape, generator=gen, dtype=torch.float32) * 2.0 - 1.0) * limit)
         else:
             raise ValueError("unknown initializer {}".format(initializer))
-        param = torch.nn.Parameter(w, requires_grad=False)
+        param = torch.nn.Parameter(w, requires_grad=self._trainable)
         self.__dict__.pop(name, None)       # __init__ pre-declares the slot as None, like the reference's layers
         self.register_parameter(name, param)
         return param

@@ -10,7 +10,7 @@ with bias + activation fused into its epilogue).
 """
 import torch
 
-from ... import ops
+from ... import ops, autograd
 from ...sparse import SparseMatrix
 from ..kernel.map_reduce import gcn_mapper  # noqa: F401  (re-exported like the reference)
 
@@ -122,9 +122,15 @@ def gcn(x, sparse_adj, kernel, bias=None, activation=None,
     normed = normed.dropout(edge_drop_rate, training=training)
     dev = normed.index.device
     x = ops.as_device(x, torch.float32, device=dev)
-    h = x if kernel is None else ops.gemm(x, ops.as_device(kernel, torch.float32, device=dev))
     act_code, leftover = ops.activation_code(activation)
     bias = None if bias is None else ops.as_device(bias, torch.float32, device=dev)
+    if autograd.needs_grad(x, kernel, bias):
+        # training path (demo/demo_gcn.py:60-75 uses tf.GradientTape): same kernels behind autograd Functions
+        h = x if kernel is None else autograd.Dense.apply(x, ops.as_device(kernel, torch.float32, device=dev), None,
+                                                         ops.ACT_NONE)
+        h = autograd.SparseMatmul.apply(h, bias, normed, act_code)
+        return leftover(h) if leftover is not None else h
+    h = x if kernel is None else ops.gemm(x, ops.as_device(kernel, torch.float32, device=dev))
     h = normed.matmul(h, num_or_size_splits=num_or_size_splits, bias=bias, act=act_code)
     if leftover is not None:
         h = leftover(h)

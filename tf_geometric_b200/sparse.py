@@ -31,6 +31,7 @@ class SparseMatrix(object):
         self._csr = _csr
         self._value_csr = _value_csr
         self._csc = None
+        self._value_csc = None
 
     # ---- structure ----
     @property
