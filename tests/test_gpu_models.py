@@ -291,6 +291,7 @@ def test_trainable_gcn_layer_one_sgd_step_reduces_loss():
     g = tfg.Graph(x, ei).to_device()
     layer = tfg.layers.GCN(c, seed=5, trainable=True)
     layer.build_cache_for_graph(g)
+    out = layer([g.x, g.edge_index, g.edge_weight], cache=g.cache)      # first call builds the weights
     opt = torch.optim.SGD(layer.parameters(), lr=0.05)
     losses = []
     for _ in range(3):

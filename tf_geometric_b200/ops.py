@@ -5,7 +5,6 @@ Nothing here computes with PyTorch: tensors are allocated with torch.empty and h
 the current CUDA stream.  Every function requires CUDA tensors and raises otherwise (no CPU path).
 """
 import ctypes
-import math
 
 import numpy as np
 import torch
