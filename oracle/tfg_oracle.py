@@ -694,6 +694,57 @@ def le_conv(x, edge_index, edge_weight, self_kernel, self_bias, aggr_self_kernel
     return h.astype(F32)
 
 
+def get_laplacian(edge_index, num_nodes, edge_weight, normalization_type, fill_weight=1.0):
+    """utils/graph_utils.py:554-604, literally (for 'sym' it is D^-1/2 A D^-1/2 with self loops appended)."""
+    edge_index = np.asarray(edge_index, dtype=I32)
+    edge_weight = _as_f32(edge_weight)
+    row, col = edge_index
+    deg = unsorted_segment_sum(edge_weight, row, num_nodes)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if normalization_type is None:
+            edge_index, edge_weight = add_self_loop_edge(edge_index, num_nodes, edge_weight, fill_weight=fill_weight)
+            return edge_index, (_remove_inf_and_nan(deg)[edge_index[0]] - edge_weight).astype(F32)
+        if normalization_type == 'sym':
+            dis = _remove_inf_and_nan(np.power(deg, F32(-0.5)))
+            normed = (dis[row] * edge_weight * dis[col]).astype(F32)
+        else:
+            inv = _remove_inf_and_nan((F32(1.0) / deg).astype(F32))
+            normed = (inv[row] * edge_weight).astype(F32)
+    return add_self_loop_edge(edge_index, num_nodes, normed, fill_weight=fill_weight)
+
+
+def chebynet_norm_edge(edge_index, num_nodes, edge_weight, normalization_type="sym", lambda_max=2.0):
+    """nn/conv/chebynet.py:17-43 (lambda_max passed in: 2.0 unless the caller computed the dynamic one)."""
+    ei, w = remove_self_loop_edge(np.asarray(edge_index, dtype=I32), _as_f32(edge_weight))
+    upd_index, upd_w = get_laplacian(ei, num_nodes, w, normalization_type)
+    return upd_index, ((F32(2.0) * upd_w) / F32(lambda_max)).astype(F32)
+
+
+def chebynet(x, edge_index, edge_weight, k, kernels, bias=None, activation=None, normalization_type="sym", lambda_max=2.0):
+    """nn/conv/chebynet.py:63-137."""
+    x = _as_f32(x)
+    n = x.shape[0]
+    if edge_weight is None:
+        edge_weight = np.ones([np.asarray(edge_index).shape[1]], dtype=F32)
+    ni, nw = chebynet_norm_edge(edge_index, n, edge_weight, normalization_type, lambda_max)
+    adj = SparseMatrix(ni, nw, [n, n])
+    t0 = x
+    out = (t0 @ _as_f32(kernels[0])).astype(F32)
+    if k > 1:
+        t1 = adj.matmul(x)
+        out = out + (t1 @ _as_f32(kernels[1])).astype(F32)
+    if k > 2:
+        for i in range(2, k):
+            t2 = (adj.matmul(t1) * F32(2.0) - t0).astype(F32)
+            out = out + (t2 @ _as_f32(kernels[i])).astype(F32)
+            t0, t1 = t1, t2
+    if bias is not None:
+        out = out + _as_f32(bias)
+    if activation is not None:
+        out = activation(out)
+    return out.astype(F32)
+
+
 # --------------------------------------------------------------------------------------------------------------
 # nn/pool/common_pool.py  (SURVEY.md section 8f-2)
 # --------------------------------------------------------------------------------------------------------------

@@ -60,7 +60,7 @@ class ProductApi(object):
                      "mean_reducer", "max_reducer", "sum_updater", "identity_updater", "segment_softmax", "segment_count",
                      "gcn", "gat", "mean_graph_sage", "sum_graph_sage", "gcn_graph_sage", "mean_pool_graph_sage",
                      "max_pool_graph_sage", "appnp", "sgc", "ssgc", "tagcn", "gin", "le_conv", "mean_pool", "sum_pool",
-                     "max_pool", "min_pool"):
+                     "max_pool", "min_pool", "chebynet", "chebynet_norm_edge"):
             setattr(self, name, getattr(tfg.nn, name))
         for name in ("convert_edge_to_directed", "merge_duplicated_edge", "add_self_loop_edge", "remove_self_loop_edge",
                      "adj_norm_edge"):
@@ -223,3 +223,16 @@ def _replay_pool(d, api):
         got = O(getattr(api, name)(A(d["x"]), A(d["gi"]), g))
         _eq(got, d[name], name)                       # bit-exact: sequential fp32 sums in node order
     _eq(O(api.mean_pool(A(d["x"]), A(d["gi"]))), d["mean_pool_auto"], "mean_pool (num_graphs inferred)")
+
+
+def _replay_chebynet(d, api):
+    A, O = api.arr, api.out
+    n = int(d["n"])
+    tol = dict(rtol=0, atol_scale=0) if api.exact_float else dict(rtol=1e-4, atol_scale=1e-4)
+    ks = [A(d["k0"]), A(d["k1"]), A(d["k2"]), A(d["k3"])]
+    for tag, kk, nt in (("k1_sym", 1, "sym"), ("k2_sym", 2, "sym"), ("k4_sym", 4, "sym"), ("k3_rw", 3, "rw"), ("k3_none", 3, None)):
+        got = api.chebynet(A(d["x"]), A(d["ei"]), A(d["w"]), kk, ks[:kk], A(d["bias"]), api.relu, normalization_type=nt)
+        _close(O(got), d["cheb_" + tag], "chebynet " + tag, **tol)
+    ni, nw = api.chebynet_norm_edge(A(d["ei"]), n, A(d["w"]), "sym")
+    _eq(O(ni), d["norm_index"], "chebynet_norm_edge index")
+    _close(O(nw), d["norm_w"], "chebynet_norm_edge weight", rtol=0 if api.exact_float else 6e-7, atol_scale=0)

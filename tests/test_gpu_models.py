@@ -303,3 +303,26 @@ def test_trainable_gcn_layer_one_sgd_step_reduces_loss():
         losses.append(float(loss))
     assert losses[2] < losses[1] < losses[0]
     assert layer.kernel.grad is not None and torch.isfinite(layer.kernel.grad).all()
+
+
+def test_chebynet_layer_static_and_dynamic_lambda():
+    rs = np.random.RandomState(51)
+    n, f, u, k = 1800, 24, 16, 4
+    ei = random_graph(n, 20000, seed=53, symmetric=True)
+    w = (rs.rand(ei.shape[1]) + 0.3).astype(np.float32)
+    w[len(w) // 2:] = w[:len(w) // 2]
+    x = rs.randn(n, f).astype(np.float32)
+    g = tfg.Graph(x, ei, edge_weight=w).to_device()
+    layer = tfg.layers.ChebyNet(u, k, activation=tfg.nn.relu, seed=7)
+    layer.build_cache_for_graph(g)
+    out = layer([g.x, g.edge_index, g.edge_weight], cache=g.cache)
+    p = {kk: host(v) for kk, v in layer.named_parameters()}
+    assert sorted(p) == ["bias", "kernel0", "kernel1", "kernel2", "kernel3"] and "chebynet_normed_edge_sym" in g.cache
+    kernels = [p["kernel{}".format(i)] for i in range(k)]
+    assert_close(host(out), o.chebynet(x, ei, w, k, kernels, p["bias"], o.relu), what="ChebyNet (lambda_max = 2)")
+    # dynamic lambda_max: host-side scipy eigsh in both the product and the reference
+    lam = tfg.nn.conv.propagation.laplacian_max_eigenvalue(dev(ei), n, dev(w), "sym")
+    got = tfg.nn.chebynet(dev(x), dev(ei), dev(w), k, [dev(a) for a in kernels], dev(p["bias"]), None,
+                          use_dynamic_lambda_max=True)
+    assert_close(host(got), o.chebynet(x, ei, w, k, kernels, p["bias"], None, lambda_max=lam), what="ChebyNet (dynamic lambda)")
+    assert 0.5 < lam < 2.5

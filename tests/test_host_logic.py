@@ -91,6 +91,7 @@ def test_model_paths(fake):
     test_gpu_models.test_propagation_layers_sgc_ssgc_tagcn_gin_leconv()
     test_gpu_models.test_gcn_two_layer_forward_backward(True)
     test_gpu_models.test_gcn_two_layer_forward_backward(False)
+    test_gpu_models.test_chebynet_layer_static_and_dynamic_lambda()
 
 
 def test_golden_fixtures_through_public_api(fake):

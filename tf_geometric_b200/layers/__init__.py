@@ -4,4 +4,4 @@ from .conv.gcn import GCN
 from .conv.gat import GAT
 from .conv.graph_sage import MeanGraphSage, SumGraphSage, GCNGraphSage, MeanPoolGraphSage, MaxPoolGraphSage
 from .conv.appnp import APPNP
-from .conv.propagation import SGC, SSGC, TAGCN, GIN, LEConv
+from .conv.propagation import SGC, SSGC, TAGCN, GIN, LEConv, ChebyNet

@@ -4,7 +4,7 @@ import torch
 
 from ... import ops
 from ...nn.conv.gcn import gcn_build_cache_for_graph, gcn_build_cache_by_adj
-from ...nn.conv.propagation import sgc, ssgc, tagcn, gin, le_conv
+from ...nn.conv.propagation import sgc, ssgc, tagcn, gin, le_conv, chebynet, chebynet_norm_edge
 from .._base import Layer
 
 
@@ -135,3 +135,33 @@ class LEConv(Layer):
         x, edge_index, edge_weight = _unpack(inputs)
         return le_conv(x, edge_index, edge_weight, self.self_kernel, self.self_bias, self.aggr_self_kernel,
                        self.aggr_self_bias, self.aggr_neighbor_kernel, self.aggr_neighbor_bias, activation=self.activation)
+
+
+class ChebyNet(Layer):
+    """tfg.layers.ChebyNet (reference layers/conv/chebynet.py): weights kernel0..kernel{k-1}, bias."""
+
+    def __init__(self, units, k, activation=None, use_bias=True, normalization_type="sym", use_dynamic_lambda_max=False,
+                 kernel_regularizer=None, bias_regularizer=None, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.units, self.k, self.activation, self.use_bias = units, k, activation, use_bias
+        self.normalization_type, self.use_dynamic_lambda_max = normalization_type, use_dynamic_lambda_max
+        self.kernels = []
+        self.bias = None
+
+    def build(self, input_shapes, device=None):
+        f = input_shapes[0][-1]
+        for i in range(self.k):
+            self.kernels.append(self.add_weight("kernel{}".format(i), [f, self.units], device=device))
+        if self.use_bias:
+            self.bias = self.add_weight("bias", [self.units], "zeros", device=device)
+
+    def build_cache_for_graph(self, graph, override=False):
+        if override:
+            graph.cache["chebynet_normed_edge_{}".format(self.normalization_type)] = None
+        chebynet_norm_edge(graph.edge_index, graph.num_nodes, graph.edge_weight, self.normalization_type,
+                           use_dynamic_lambda_max=self.use_dynamic_lambda_max, cache=graph.cache)
+
+    def call(self, inputs, cache=None, training=None, mask=None):
+        x, edge_index, edge_weight = _unpack(inputs)
+        return chebynet(x, edge_index, edge_weight, self.k, self.kernels, self.bias, self.activation,
+                        self.normalization_type, use_dynamic_lambda_max=self.use_dynamic_lambda_max, cache=cache)

@@ -9,6 +9,7 @@ from .conv.gat import gat
 from .conv.graph_sage import (mean_graph_sage, sum_graph_sage, gcn_graph_sage, mean_pool_graph_sage,
                               max_pool_graph_sage)
 from .conv.appnp import appnp
-from .conv.propagation import sgc, ssgc, tagcn, gin, gin_updater, le_conv
+from .conv.propagation import (sgc, ssgc, tagcn, gin, gin_updater, le_conv, chebynet, chebynet_norm_edge,
+                               get_laplacian)
 from .pool.common_pool import mean_pool, sum_pool, max_pool, min_pool
 from ..ops import relu

@@ -116,3 +116,101 @@ def le_conv(x, edge_index, edge_weight, self_kernel, self_bias, aggr_self_kernel
     act_code, leftover = ops.activation_code(activation)
     h = ops.spmm(csr, w_csr, diff, reduce="sum", alpha=1.0, addend=self_h, beta=1.0, act=act_code)
     return leftover(h) if leftover is not None else h
+
+
+# ---- ChebyNet (reference nn/conv/chebynet.py, utils/graph_utils.py:554-604,884-911) -------------------------------------
+
+CACHE_KEY_CHEBYNET_NORMED_EDGE_TEMPLATE = "chebynet_normed_edge_{}"
+
+
+def get_laplacian(edge_index, num_nodes, edge_weight, normalization_type, fill_weight=1.0):
+    """The reference's `get_laplacian`, literally: for 'sym' it returns D^-1/2 A D^-1/2 with `fill_weight` self loops appended
+    (positive off-diagonals - not I - D^-1/2 A D^-1/2), for 'rw' D^-1 A + loops, for None (deg[row] - w) with loops."""
+    if normalization_type is not None:
+        assert normalization_type in [None, 'sym', 'rw']
+    edge_index = ops.as_device(edge_index, torch.int32)
+    dev = edge_index.device
+    w = _f32(edge_weight, dev)
+    adj = SparseMatrix(edge_index, w, [num_nodes, num_nodes])
+    deg = adj.segment_sum(axis=-1)
+    row, col = edge_index[0].contiguous(), edge_index[1].contiguous()
+    if normalization_type is None:
+        looped = adj.add_diag(fill_weight)
+        deg_clean = torch.where(torch.isinf(deg) | torch.isnan(deg), torch.zeros_like(deg), deg)
+        return looped.index, deg_clean[looped.index[0].long()] - looped.value
+    if normalization_type == 'sym':
+        dis = ops.deg_inv(deg, ops.POW_INV_SQRT)
+        normed = ops.scale_edges(row, col, w, dl=dis, dr=dis)
+    else:
+        normed = ops.scale_edges(row, None, w, dl=ops.deg_inv(deg, ops.POW_INV))
+    looped = SparseMatrix(edge_index, normed, [num_nodes, num_nodes]).add_diag(fill_weight)
+    return looped.index, looped.value
+
+
+def laplacian_max_eigenvalue(edge_index, num_nodes, edge_weight, normalization_type='sym', is_undirected=True):
+    """LaplacianMaxEigenvalue(...)(normalization_type): host-side scipy eigs/eigsh, as in the reference (:884-911, including
+    its quirk of building the operator from the edges WITH self loops while the weights had them removed)."""
+    import numpy as np
+    import scipy.sparse
+    from scipy.sparse.linalg import eigs, eigsh
+    from ...utils.graph_utils import remove_self_loop_edge
+    ei = edge_index.detach().cpu().numpy() if torch.is_tensor(edge_index) else np.asarray(edge_index)
+    w = (edge_weight.detach().cpu().numpy() if torch.is_tensor(edge_weight) else
+         (np.ones([ei.shape[1]], np.float32) if edge_weight is None else np.asarray(edge_weight)))
+    _, w_nl = remove_self_loop_edge(ei, w)
+    lap_index, lap_w = get_laplacian(ei, num_nodes, w_nl, normalization_type)
+    li, lw = lap_index.cpu().numpy(), lap_w.cpu().numpy()
+    L = scipy.sparse.coo_matrix((lw, (li[0], li[1])), shape=(num_nodes, num_nodes))
+    fn = eigsh if (is_undirected and normalization_type) else eigs
+    return float(fn(L, k=1, which='LM', return_eigenvectors=False).real)
+
+
+def chebynet_norm_edge(edge_index, num_nodes, edge_weight=None, normalization_type="sym", use_dynamic_lambda_max=False,
+                       cache=None):
+    """reference chebynet.py:17-43."""
+    if cache is not None:
+        cache_key = CACHE_KEY_CHEBYNET_NORMED_EDGE_TEMPLATE.format(normalization_type)
+        if cache.get(cache_key, None) is not None:
+            return cache[cache_key]
+    from ...utils.graph_utils import remove_self_loop_edge
+    edge_index = ops.as_device(edge_index, torch.int32)
+    edge_weight = _f32(edge_weight, edge_index.device)
+    ei_nl, w_nl = remove_self_loop_edge(edge_index, edge_weight)
+    assert w_nl is not None
+    upd_index, upd_w = get_laplacian(ei_nl, num_nodes, w_nl, normalization_type)
+    lambda_max = laplacian_max_eigenvalue(ei_nl, num_nodes, w_nl, normalization_type) if use_dynamic_lambda_max else 2.0
+    scaled = (2.0 * upd_w) / lambda_max
+    if cache is not None:
+        cache[cache_key] = upd_index, scaled
+    return upd_index, scaled
+
+
+def chebynet(x, edge_index, edge_weight, k, kernels, bias=None, activation=None, normalization_type="sym",
+             use_dynamic_lambda_max=False, cache=None):
+    """sum_i T_i(L~) x K_i with T_0 = x, T_1 = L~ x, T_i = 2 L~ T_{i-1} - T_{i-2}: the recurrence is the aggregation kernel's
+    axpby epilogue, the projections accumulate into `out` through the GEMM's beta (reference chebynet.py:63-137)."""
+    edge_index = ops.as_device(edge_index, torch.int32)
+    dev = edge_index.device
+    x = _f32(x, dev)
+    n = x.shape[0]
+    if edge_weight is None:
+        edge_weight = torch.ones([edge_index.shape[1]], dtype=torch.float32, device=dev)
+    n_index, n_weight = chebynet_norm_edge(edge_index, n, edge_weight, normalization_type,
+                                           use_dynamic_lambda_max=use_dynamic_lambda_max, cache=cache)
+    adj = SparseMatrix(n_index, n_weight, [n, n]) if cache is None else cache.setdefault(
+        "tfgk_chebynet_adj_{}".format(normalization_type), SparseMatrix(n_index, n_weight, [n, n]))
+    t0 = x
+    out = ops.gemm(t0, _f32(kernels[0], dev))
+    if k > 1:
+        t1 = adj.matmul(x)
+        ops.gemm(t1, _f32(kernels[1], dev), beta=1.0, out=out)
+    if k > 2:
+        for i in range(2, k):
+            t2 = adj.matmul(t1, alpha=2.0, addend=t0, beta=-1.0)          # (L~ @ T1) * 2.0 - T0
+            ops.gemm(t2, _f32(kernels[i], dev), beta=1.0, out=out)
+            t0, t1 = t1, t2
+    if bias is not None:
+        out = out + _f32(bias, dev)
+    if activation is not None:
+        out = activation(out)
+    return out

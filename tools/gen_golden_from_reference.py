@@ -36,6 +36,7 @@ le_m = importlib.import_module("tf_geometric.nn.conv.le_conv")
 sys.modules["tf_geometric.nn.pool"] = type(sys)("tf_geometric.nn.pool")
 sys.modules["tf_geometric.nn.pool"].__path__ = [os.path.join(REFERENCE, "tf_geometric", "nn", "pool")]
 pool_m = importlib.import_module("tf_geometric.nn.pool.common_pool")
+cheb_m = importlib.import_module("tf_geometric.nn.conv.chebynet")
 
 
 def glorot(rs, a, b):
@@ -217,6 +218,23 @@ def main():
         out[name] = getattr(pool_m, name)(T(x), T(gi), g)
     out["mean_pool_auto"] = pool_m.mean_pool(T(x), T(gi))
     save("pool", **out)
+
+    # ---- chebynet ------------------------------------------------------------------------------------------------------------
+    n, f, u = 44, 8, 5
+    ei = graph(n, 380, 17, True)
+    ei = np.concatenate([ei, np.array([[3, 9], [3, 9]], np.int32)], axis=1)      # self loops, removed by chebynet_norm_edge
+    w = rs.rand(ei.shape[1]).astype(np.float32) + 0.2
+    half = (ei.shape[1] - 2) // 2
+    w[half:2 * half] = w[:half]
+    x = rs.randn(n, f).astype(np.float32)
+    ks = [glorot(rs, f, u) for _ in range(4)]
+    bias = rs.randn(u).astype(np.float32)
+    out = {"n": n, "ei": ei, "w": w, "x": x, "bias": bias, "k0": ks[0], "k1": ks[1], "k2": ks[2], "k3": ks[3]}
+    for tag, kk, nt in (("k1_sym", 1, "sym"), ("k2_sym", 2, "sym"), ("k4_sym", 4, "sym"), ("k3_rw", 3, "rw"), ("k3_none", 3, None)):
+        out["cheb_" + tag] = cheb_m.chebynet(T(x), T(ei), T(w), kk, [T(a) for a in ks[:kk]], T(bias), tf.nn.relu, normalization_type=nt)
+    ni, nw = cheb_m.chebynet_norm_edge(T(ei), n, T(w), "sym")
+    out["norm_index"], out["norm_w"] = ni, nw
+    save("chebynet", **out)
 
 
 if __name__ == "__main__":
