@@ -326,3 +326,30 @@ def test_chebynet_layer_static_and_dynamic_lambda():
                           use_dynamic_lambda_max=True)
     assert_close(host(got), o.chebynet(x, ei, w, k, kernels, p["bias"], None, lambda_max=lam), what="ChebyNet (dynamic lambda)")
     assert 0.5 < lam < 2.5
+
+
+def test_degenerate_graphs_empty_edges_single_node():
+    """Empty / ragged inputs: an edge list with zero columns (every row empty), a one-node graph, a graph whose only edges are
+    pre-existing self loops.  The reference proceeds normally for edge_index of shape [2, 0] (map_reduce.py:57 only tests dim 0)."""
+    rs = np.random.RandomState(61)
+    for n, ei in ((7, np.zeros((2, 0), np.int32)), (1, np.zeros((2, 0), np.int32)), (1, np.array([[0, 0], [0, 0]], np.int32)),
+                  (5, np.array([[2, 2, 4], [2, 2, 4]], np.int32))):
+        f, u = 6, 8
+        x = rs.randn(n, f).astype(np.float32)
+        w = np.ones(ei.shape[1], np.float32)
+        k, b = glorot(rs, f, u), rs.randn(u).astype(np.float32)
+        what = "n={} e={}".format(n, ei.shape[1])
+        got = tfg.nn.aggregate_neighbors(dev(x), dev(ei), None, tfg.nn.identity_mapper, tfg.nn.mean_reducer, tfg.nn.sum_updater)
+        np.testing.assert_array_equal(host(got), o.aggregate_neighbors(x, ei, None, o.identity_mapper, o.mean_reducer, o.sum_updater))
+        got = tfg.nn.aggregate_neighbors(dev(x), dev(ei), None, tfg.nn.identity_mapper, tfg.nn.max_reducer, tfg.nn.identity_updater)
+        np.testing.assert_array_equal(host(got), o.aggregate_neighbors(x, ei, None, o.identity_mapper, o.max_reducer, o.identity_updater))
+        assert_close(host(tfg.nn.gcn(dev(x), tfg.SparseMatrix(ei, w, [n, n]), dev(k), dev(b), tfg.nn.relu)),
+                     o.gcn(x, o.SparseMatrix(ei, w, [n, n]), k, b, o.relu), what="gcn " + what)
+        wq, wk, wv = glorot(rs, f, u), glorot(rs, f, u), glorot(rs, f, u)
+        z = np.zeros(u, np.float32)
+        assert_close(host(tfg.nn.gat(dev(x), dev(ei), dev(wq), dev(z), tfg.nn.relu, dev(wk), dev(z), tfg.nn.relu, dev(wv), dev(b),
+                                     None, num_heads=2)),
+                     o.gat(x, ei, wq, z, o.relu, wk, z, o.relu, wv, b, None, num_heads=2), what="gat " + what)
+        assert_close(host(tfg.nn.mean_graph_sage(dev(x), dev(ei), None, dev(k), dev(k), dev(np.concatenate([b, b])), tfg.nn.relu)),
+                     o.mean_graph_sage(x, ei, None, k, k, np.concatenate([b, b]), o.relu), what="sage " + what)
+        assert host(tfg.nn.segment_count(dev(ei[0]), n)).tolist() == np.bincount(ei[0], minlength=n).tolist()

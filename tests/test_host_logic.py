@@ -92,6 +92,7 @@ def test_model_paths(fake):
     test_gpu_models.test_gcn_two_layer_forward_backward(True)
     test_gpu_models.test_gcn_two_layer_forward_backward(False)
     test_gpu_models.test_chebynet_layer_static_and_dynamic_lambda()
+    test_gpu_models.test_degenerate_graphs_empty_edges_single_node()
 
 
 def test_golden_fixtures_through_public_api(fake):

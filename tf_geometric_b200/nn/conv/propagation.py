@@ -162,7 +162,7 @@ def laplacian_max_eigenvalue(edge_index, num_nodes, edge_weight, normalization_t
     li, lw = lap_index.cpu().numpy(), lap_w.cpu().numpy()
     L = scipy.sparse.coo_matrix((lw, (li[0], li[1])), shape=(num_nodes, num_nodes))
     fn = eigsh if (is_undirected and normalization_type) else eigs
-    return float(fn(L, k=1, which='LM', return_eigenvectors=False).real)
+    return float(np.real(fn(L, k=1, which='LM', return_eigenvectors=False))[0])
 
 
 def chebynet_norm_edge(edge_index, num_nodes, edge_weight=None, normalization_type="sym", use_dynamic_lambda_max=False,
