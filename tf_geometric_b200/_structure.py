@@ -73,8 +73,12 @@ def csr_for_segment_ids(segment_ids, num_segments):
 
 
 def weights_in_csr_order(edge_weight, csr):
+    """edge_weight permuted into the order of `csr`, memoised per (weight tensor, CSR object); the CSR is held by weak
+    reference so that a recycled id() can never alias another structure."""
     tag = ("wcsr", id(csr))
     hit = _lookup(edge_weight, tag)
-    if hit is None:
-        hit = _store(edge_weight, tag, ops.permute(edge_weight, csr.perm))
-    return hit
+    if hit is not None and hit[0]() is csr:
+        return hit[1]
+    value = ops.permute(edge_weight, csr.perm)
+    _store(edge_weight, tag, (weakref.ref(csr), value))
+    return value

@@ -97,7 +97,7 @@ class CSR(object):
     """Destination-sorted CSR of a COO edge list (stable by row): rowptr int64 [n_rows+1], col int32 [nnz],
     perm int32 [nnz] (position of each CSR slot in the original edge list); `plan` is set when the graph has hub rows."""
 
-    __slots__ = ("rowptr", "col", "perm", "n_rows", "n_cols", "nnz", "plan")
+    __slots__ = ("rowptr", "col", "perm", "n_rows", "n_cols", "nnz", "plan", "__weakref__")
 
     def __init__(self, rowptr, col, perm, n_rows, n_cols):
         self.rowptr, self.col, self.perm = rowptr, col, perm
