@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TFGK_ABI_VERSION 2
+#define TFGK_ABI_VERSION 3
 
 enum tfgk_status {
     TFGK_OK = 0,
@@ -40,6 +40,9 @@ enum tfgk_status {
 enum tfgk_reduce { TFGK_REDUCE_SUM = 0, TFGK_REDUCE_MEAN = 1, TFGK_REDUCE_MAX = 2 };
 enum tfgk_act { TFGK_ACT_NONE = 0, TFGK_ACT_RELU = 1 };
 enum tfgk_deg_power { TFGK_POW_INV_SQRT = 0, TFGK_POW_INV = 1 };
+enum tfgk_heads_mode { TFGK_HEADS_SPLIT = 0, TFGK_HEADS_BROADCAST = 1, TFGK_HEADS_REDUCE = 2 };
+enum tfgk_edge_flag { TFGK_FLAG_ALL = 0, TFGK_FLAG_UPPER = 1, TFGK_FLAG_MAPPED = 2 };
+enum tfgk_bernoulli { TFGK_BERNOULLI_NONE = 0, TFGK_BERNOULLI_DROPOUT = 1, TFGK_BERNOULLI_KEEP = 2 };
 
 int tfgk_version(void);
 const char *tfgk_last_error(void);
@@ -173,6 +176,69 @@ int tfgk_gemm_f32(const float *A, int64_t lda, int transA, const float *B, int64
 
 /* tf.nn.l2_normalize(x, axis=-1) (graph_sage.py:57-58): out = x * rsqrt(max(sum(x^2), 1e-12)). */
 int tfgk_l2_normalize_f32(const float *x, int64_t ldx, int32_t N, int32_t D, float *out, int64_t ldo, void *stream);
+
+/* ---- training-mode extras -------------------------------------------------------------------
+ * Randomness is counter-based (Philox4x32-10): draw i of (seed, rng_stream) is a pure function of its arguments,
+ * u_i = (philox(counter = (i >> 2, rng_stream, 0), key = seed)[i & 3] >> 8) * 2^-24.  Parity with TensorFlow's own
+ * generator is statistical only; parity with oracle/tfg_oracle.py (same generator) is bit-exact. */
+
+/* tf.nn.dropout (gcn.py:262 via tf_sparse dropout on the adjacency values, gat.py:85 on the attention coefficients):
+ * out[i] = u_i >= rate ? x[i] * (1 / (1 - rate)) : 0.   x NULL = ones (a scaled keep mask). */
+int tfgk_dropout_f32(const float *x, int64_t n, float rate, uint64_t seed, uint32_t rng_stream, float *out, void *stream);
+
+/* Aggregation with one weight per (edge, head): the value half of gat.py:87-114 when the coefficients are already
+ * known (attention dropout), and the three scatter-shaped gradients of the fused GAT kernel when run on the
+ * transposed CSR.  weight(e, h) = w[pos*H + h] * dropout(pos*H + h), pos = emap ? emap[e] : e.
+ *   TFGK_HEADS_SPLIT     out[r, h*dh+u] = alpha * sum_e weight(e,h) * src[col_e, h*dh+u]
+ *   TFGK_HEADS_BROADCAST out[r, h*dh+u] = alpha * sum_e weight(e,h) * src[col_e, u]            (src has dh columns)
+ *   TFGK_HEADS_REDUCE    out[r, u]      = alpha * sum_h sum_e weight(e,h) * src[col_e, h*dh+u]  (out has dh columns)
+ * then + bias, activation.  Sequential in CSR order per row (deterministic). */
+int tfgk_spmm_heads_f32(const int64_t *rowptr, const int32_t *col, const int32_t *emap, const float *w,
+                        const float *src, int64_t lds, int32_t n_dst, int32_t H, int32_t dh, int mode,
+                        float drop_rate, uint64_t seed, uint32_t rng_stream, float alpha,
+                        const float *bias, int act, float *out, int64_t ldo, void *stream);
+
+/* Gradient of gat.py:83-114 w.r.t. the scaled scores, given G = dL/d(aggregated rows before bias/activation):
+ *   da_e,h = <G[r,h,:], V[col_e,h,:]> * dropout(e*H+h)   (split_value_heads=0: <G[r,:], V[col_e,h,:]> / H)
+ *   ds_e,h = a_e,h * (da_e,h - sum_f a_f,h da_f,h)
+ * att: [E, H] softmax coefficients BEFORE dropout, CSR order (tfgk_gat_fused_f32 with write_att); ds: [E, H] out.
+ * The 1e-8 in segment.py:31 makes d a/d max non-zero by ~1e-8 relative in TF autodiff; that term is dropped. */
+int tfgk_gat_softmax_bwd_f32(const int64_t *rowptr, const int32_t *col, const float *att,
+                             const float *G, int64_t ldg, const float *V, int64_t ldv,
+                             int32_t n_dst, int32_t H, int32_t dv, int split_value_heads,
+                             float drop_rate, uint64_t seed, uint32_t rng_stream, float *ds, void *stream);
+
+/* ---- device-side edge sampling -------------------------------------------------------------- */
+
+/* flag[e] = structural(e) && bernoulli(e):
+ *   structural: ALL | UPPER row<col (drop_edge.py:35 force_undirected) | MAPPED row_map[row]>=0 && col_map[col]>=0
+ *               (graph_utils.py:826-832 virtual node filter)
+ *   bernoulli : NONE | DROPOUT u_e >= prob (drop_edge.py:36,41: tf.nn.dropout(ones, rate) > 0) | KEEP u_e <= prob
+ *               (graph_utils.py:808-809,841-842 UniformNeighborSampler) */
+int tfgk_edge_flags_i32(const int32_t *row, const int32_t *col, int64_t E, int mode,
+                        const int32_t *row_map, const int32_t *col_map,
+                        int bernoulli, float prob, uint64_t seed, uint32_t rng_stream, int32_t *flag, void *stream);
+
+/* tf.boolean_mask(tf.range(n), flag): ascending positions of the non-zero flags; *n_out_host = how many.
+ * Synchronises the stream. */
+int tfgk_select_workspace_bytes(int64_t n, size_t *out_bytes);
+int tfgk_select_flagged_i32(const int32_t *flag, int64_t n, int32_t *out_index, int64_t *n_out_host,
+                            void *workspace, size_t workspace_bytes, void *stream);
+
+/* RandomNeighborSampler.sample (graph_utils.py:669-776) on a CSR whose rows are the source nodes in ascending order
+ * with neighbours in edge order (= the reference's neighbor_dict).  k < 0 and ratio < 0: every neighbour; ratio < 0:
+ * k per row (all of them in order when k >= degree and !padding; k draws WITH replacement when padding and
+ * k >= degree); otherwise ceil(degree * ratio) without replacement.  Rows without neighbours emit nothing.
+ * _count writes the [n_rows + 1] offsets of the sampled edges and their total (synchronises); _fill writes, per sampled
+ * edge, its row and the CSR position it was taken from (gather col / weights with tfgk_permute_f32).  Without
+ * replacement = reservoir sampling with draws (seed, rng_stream, row << 32 | i). */
+int tfgk_neighbor_sample_workspace_bytes(int32_t n_rows, size_t *out_bytes);
+int tfgk_neighbor_sample_count(const int64_t *rowptr, int32_t n_rows, int32_t k, double ratio, int padding,
+                               int64_t *out_rowptr, int64_t *total_host, void *workspace, size_t workspace_bytes,
+                               void *stream);
+int tfgk_neighbor_sample_fill(const int64_t *rowptr, int32_t n_rows, int32_t k, double ratio, int padding,
+                              uint64_t seed, uint32_t rng_stream, const int64_t *out_rowptr,
+                              int32_t *out_row, int32_t *out_pos, void *stream);
 
 #ifdef __cplusplus
 }

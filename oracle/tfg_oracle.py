@@ -781,3 +781,252 @@ def dense_spmm_f64(index, value, shape, h):
     a = np.zeros(shape, dtype=np.float64)
     np.add.at(a, (index[0], index[1]), np.asarray(value, dtype=np.float64))
     return a @ np.asarray(h, dtype=np.float64)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Training-mode extras and samplers.
+# The reference draws from TensorFlow's / numpy's global generators (tf.nn.dropout, tf.random.uniform,
+# np.random.choice), which cannot be reproduced; the product uses the counter-based Philox4x32-10 generator instead
+# and this section restates it, so that masks and samples are bit-exact oracle <-> kernels while the parity with the
+# reference is about SEMANTICS (which elements may be kept, scaling, with/without replacement, output layout).
+# Philox is pinned by the Random123 known-answer vectors in tests/test_oracle.py.
+# --------------------------------------------------------------------------------------------------------------
+
+_PHILOX_M0, _PHILOX_M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+_PHILOX_W0, _PHILOX_W1 = np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
+_MASK32 = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32(counter, key, rounds=10):
+    """Philox4x32 (Salmon et al., SC'11).  counter: uint32 [..., 4], key: uint32 [..., 2] -> uint32 [..., 4]."""
+    c = [np.asarray(counter[..., i], dtype=np.uint32).copy() for i in range(4)]
+    k0 = np.asarray(key[..., 0], dtype=np.uint32).copy()
+    k1 = np.asarray(key[..., 1], dtype=np.uint32).copy()
+    with np.errstate(over="ignore"):
+        for _ in range(rounds):
+            p0 = _PHILOX_M0 * c[0].astype(np.uint64)
+            p1 = _PHILOX_M1 * c[2].astype(np.uint64)
+            hi0, lo0 = (p0 >> np.uint64(32)).astype(np.uint32), (p0 & _MASK32).astype(np.uint32)
+            hi1, lo1 = (p1 >> np.uint64(32)).astype(np.uint32), (p1 & _MASK32).astype(np.uint32)
+            c = [hi1 ^ c[1] ^ k0, lo1, hi0 ^ c[3] ^ k1, lo0]
+            k0 = (k0 + _PHILOX_W0).astype(np.uint32)
+            k1 = (k1 + _PHILOX_W1).astype(np.uint32)
+    return np.stack(c, axis=-1)
+
+
+def random_u32(seed, stream, idx):
+    """Draw `idx` (uint64 array) of (seed, stream): counter = (idx >> 2 [lo, hi], stream, 0), lane idx & 3
+    (tf_geometric_b200/csrc/rng.cuh random_u32)."""
+    idx = np.asarray(idx, dtype=np.uint64)
+    blk = idx >> np.uint64(2)
+    counter = np.stack([(blk & _MASK32).astype(np.uint32), (blk >> np.uint64(32)).astype(np.uint32),
+                        np.full(idx.shape, stream, np.uint32), np.zeros(idx.shape, np.uint32)], axis=-1)
+    seed = int(seed)
+    key = np.empty(idx.shape + (2,), np.uint32)
+    key[..., 0] = seed & 0xFFFFFFFF
+    key[..., 1] = (seed >> 32) & 0xFFFFFFFF
+    out = philox4x32(counter, key)
+    lane = (idx & np.uint64(3)).astype(np.int64)
+    return np.take_along_axis(out, lane[..., None], axis=-1)[..., 0]
+
+
+def random_uniform(seed, stream, idx):
+    """uniform [0, 1) with 24 random bits, exactly representable in float32."""
+    return (random_u32(seed, stream, idx) >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+
+
+def random_below(seed, stream, idx, n):
+    return ((random_u32(seed, stream, idx).astype(np.uint64) * np.asarray(n, dtype=np.uint64)) >> np.uint64(32)).astype(np.int64)
+
+
+RNG_STREAM_DROPOUT, RNG_STREAM_SAMPLER = 0, 1
+
+
+def dropout_scale(n, rate, seed, stream=RNG_STREAM_DROPOUT):
+    """tf.nn.dropout's multiplier per element: 1/(1-rate) where u >= rate, else 0."""
+    if rate <= 0.0:
+        return np.ones(n, F32)
+    scale = F32(1.0) / (F32(1.0) - F32(rate))
+    u = random_uniform(seed, stream, np.arange(n, dtype=np.uint64))
+    return np.where(u >= F32(rate), scale, F32(0.0)).astype(F32)
+
+
+def dropout(x, rate, seed, stream=RNG_STREAM_DROPOUT):
+    """tf.nn.dropout(x, rate) (gcn.py:262 through tf_sparse's SparseMatrix.dropout, gat.py:85)."""
+    x = _as_f32(x)
+    return (x.reshape(-1) * dropout_scale(x.size, rate, seed, stream)).reshape(x.shape).astype(F32)
+
+
+def drop_edge(inputs, rate=0.5, force_undirected=False, training=None, seed=0):
+    """nn/sampling/drop_edge.py:6-52 with the counter-based mask: edge e survives iff u(seed, e) >= rate."""
+    if not training:
+        return inputs
+    if rate < 0.0 or rate > 1.0:
+        raise ValueError("Dropout probability has to be between 0 and 1, but got {}".format(rate))
+    edge_index, edge_attrs = np.asarray(inputs[0]), [np.asarray(a) for a in inputs[1:]]
+    row, col = edge_index[0], edge_index[1]
+    E = row.shape[0]
+    keep = random_uniform(seed, RNG_STREAM_SAMPLER, np.arange(E, dtype=np.uint64)) >= F32(rate)
+    if force_undirected:
+        index = np.nonzero((row < col) & keep)[0]                       # drop_edge.py:35-36
+        dropped = edge_index[:, index]
+        dropped = np.concatenate([dropped, dropped[[1, 0]]], axis=-1)    # drop_edge.py:38
+        index = np.concatenate([index, index])
+    else:
+        index = np.nonzero(keep)[0]                                      # drop_edge.py:41-43
+        dropped = edge_index[:, index]
+    return [dropped] + [np.take(a, index, axis=-1) for a in edge_attrs]
+
+
+def uniform_neighbor_sample(edge_index, edge_weight, prob, sampled_node_index=None, seed=0):
+    """UniformNeighborSampler.sample (utils/graph_utils.py:801-846): keep edge e iff u(seed, e) <= prob, after the
+    optional restriction to (and relabelling into) the virtual node set."""
+    edge_index = np.asarray(edge_index, I32)
+    E = edge_index.shape[1]
+    w = np.ones(E, F32) if edge_weight is None else _as_f32(edge_weight)
+    keep = random_uniform(seed, RNG_STREAM_SAMPLER, np.arange(E, dtype=np.uint64)) <= F32(prob)
+    if sampled_node_index is None:
+        return edge_index[:, keep], w[keep]
+    virtual, vw, mask = _virtual_edges(edge_index, w, sampled_node_index)
+    sel = keep[mask]                                  # the draw of an edge is indexed by its ORIGINAL position
+    return virtual[:, sel], vw[sel]
+
+
+def _virtual_edges(edge_index, w, sampled_node_index):
+    """Restriction to / relabelling into a sampled node set (graph_utils.py:690-733): virtual id = position in the
+    sampled list; edges with an end outside the set are dropped, edge order is kept."""
+    if isinstance(sampled_node_index, tuple):
+        rows, cols = sampled_node_index
+    else:
+        rows = cols = sampled_node_index
+    n_row, n_col = int(edge_index[0].max()) + 1, int(edge_index[1].max()) + 1
+    row_map = -np.ones(n_row, np.int64)
+    row_map[np.asarray(rows)] = np.arange(len(rows))
+    if isinstance(sampled_node_index, tuple) or n_col != n_row:
+        col_map = -np.ones(n_col, np.int64)
+        cols = np.asarray(cols)
+        ok = cols < n_col
+        col_map[cols[ok]] = np.arange(len(cols))[ok]
+    else:
+        col_map = row_map
+    vr, vc = row_map[edge_index[0]], col_map[edge_index[1]]
+    mask = (vr >= 0) & (vc >= 0)
+    return np.stack([vr[mask], vc[mask]]).astype(I32), w[mask], mask
+
+
+def random_neighbor_sample(edge_index, edge_weight=None, k=None, ratio=None, padding=False, seed=0,
+                           sampled_node_index=None):
+    """RandomNeighborSampler(edge_index, edge_weight).sample(k, ratio, sampled_node_index, padding)
+    (utils/graph_utils.py:631-776): rows in ascending (virtual) order, neighbours in edge order; per row either all
+    neighbours, k draws with replacement (padding and k >= degree), or a reservoir sample without replacement.
+    Returns (sampled_edge_index [2, S], sampled_edge_weight [S]) or (None, None) when nothing is sampled."""
+    if k is not None and ratio is not None:
+        raise Exception("k and ratio cannot be provided simultaneously")
+    edge_index = np.asarray(edge_index, I32)
+    E = edge_index.shape[1]
+    w = np.ones(E, F32) if edge_weight is None else _as_f32(edge_weight)
+    if sampled_node_index is not None:
+        edge_index, w, _ = _virtual_edges(edge_index, w, sampled_node_index)
+        E = edge_index.shape[1]
+    n_rows = int(edge_index[0].max()) + 1 if E else 0
+    rowptr, col_sorted, perm = csr_build(edge_index[0], edge_index[1], n_rows)
+    out_row, pos, _ = neighbor_sample_csr(rowptr, k, ratio, padding, seed)
+    if len(pos) == 0:
+        return None, None
+    return np.stack([out_row, col_sorted[pos]]).astype(I32), w[perm[pos]]
+
+
+def neighbor_sample_csr(rowptr, k=None, ratio=None, padding=False, seed=0, stream=RNG_STREAM_SAMPLER):
+    """Restatement of tfgk_neighbor_sample_count/_fill: (row int32 [S], CSR position int64 [S], offsets int64 [n+1])."""
+    rowptr = np.asarray(rowptr, np.int64)
+    n_rows = len(rowptr) - 1
+    out_row, out_pos, counts = [], [], np.zeros(n_rows, np.int64)
+    for r in range(n_rows):
+        start, deg = int(rowptr[r]), int(rowptr[r + 1] - rowptr[r])
+        if deg == 0:
+            continue
+        base = np.uint64(r) << np.uint64(32)
+        if (k is None and ratio is None) or (ratio is None and not padding and k >= deg):
+            pos = start + np.arange(deg)
+        elif ratio is None and padding and k >= deg:
+            pos = start + random_below(seed, stream, base + np.arange(k, dtype=np.uint64), deg)
+        else:
+            num = k if ratio is None else int(np.ceil(deg * ratio).astype(np.int32))
+            res = start + np.arange(num)
+            if deg > num:
+                i = np.arange(num, deg, dtype=np.uint64)
+                j = random_below(seed, stream, base + i, i + np.uint64(1))
+                for ii, jj in zip(i.astype(np.int64), j):
+                    if jj < num:
+                        res[jj] = start + ii
+            pos = res
+        counts[r] = len(pos)
+        out_row.append(np.full(len(pos), r, I32))
+        out_pos.append(np.asarray(pos, np.int64))
+    out_rowptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    if not out_row:
+        return np.zeros(0, I32), np.zeros(0, np.int64), out_rowptr
+    return np.concatenate(out_row), np.concatenate(out_pos), out_rowptr
+
+
+def _row_ids(rowptr):
+    rowptr = np.asarray(rowptr, np.int64)
+    return np.repeat(np.arange(len(rowptr) - 1), np.diff(rowptr))
+
+
+def spmm_heads(rowptr, col, w, src, num_heads, mode="split", emap=None, drop_rate=0.0, seed=0, alpha=1.0, bias=None,
+               act=None):
+    """Restatement of tfgk_spmm_heads_f32 (include/tfgk.h): per row, fp32 products added in CSR order.
+    mode 'split': out[r, h*dh+u] = alpha sum_e W(e,h) src[col_e, h*dh+u]; 'broadcast': src has dh columns;
+    'reduce': out[r, u] = alpha sum_h sum_e W(e,h) src[col_e, h*dh+u] (heads added in order, tf.add_n, gat.py:114).
+    W(e,h) = w[pos, h] * dropout multiplier of element pos*H+h, pos = emap[e] if given."""
+    rowptr, col = np.asarray(rowptr, np.int64), np.asarray(col, np.int64)
+    w, src = _as_f32(w), _as_f32(src)
+    H = int(num_heads)
+    n = len(rowptr) - 1
+    pos = np.arange(len(col)) if emap is None else np.asarray(emap, np.int64)
+    mult = dropout_scale(w.size, drop_rate, seed).reshape(w.shape)
+    W = np.where(mult[pos] == 0, F32(0), (w[pos] * mult[pos]) if drop_rate > 0 else w[pos]).astype(F32)   # [E, H]
+    dh = src.shape[1] if mode == "broadcast" else src.shape[1] // H
+    out_w = dh if mode == "reduce" else H * dh
+    out = np.zeros((n, out_w), F32)
+    for r in range(n):
+        if mode == "reduce":
+            tot = None
+            for h in range(H):
+                acc = np.zeros(dh, F32)
+                for e in range(rowptr[r], rowptr[r + 1]):
+                    acc = acc + src[col[e], h * dh:(h + 1) * dh] * W[e, h]
+                tot = acc if tot is None else tot + acc
+            out[r] = tot * F32(alpha)
+        else:
+            acc = np.zeros(H * dh, F32)
+            for e in range(rowptr[r], rowptr[r + 1]):
+                row = np.tile(src[col[e]], H) if mode == "broadcast" else src[col[e]]
+                acc = acc + row * np.repeat(W[e], dh)
+            out[r] = acc * F32(alpha)
+    if bias is not None:
+        out = out + _as_f32(bias)
+    if act == "relu":
+        out = np.maximum(out, F32(0))
+    return out.astype(F32)
+
+
+def gat_softmax_bwd(rowptr, col, att, G, V, num_heads, split_value_heads=True, drop_rate=0.0, seed=0):
+    """Restatement of tfgk_gat_softmax_bwd_f32: gradient of gat.py:83-114 w.r.t. the scaled scores, [E, H] CSR order.
+    (float64 accumulation here: the kernel's dot products are compared with a tolerance, not bit for bit.)"""
+    rowptr, col = np.asarray(rowptr, np.int64), np.asarray(col, np.int64)
+    H = int(num_heads)
+    att64, G64, V64 = np.asarray(att, np.float64), np.asarray(G, np.float64), np.asarray(V, np.float64)
+    E = len(col)
+    dv = V64.shape[1] // H
+    rows = _row_ids(rowptr)
+    Vh = V64[col].reshape(E, H, dv)
+    if split_value_heads:
+        da = np.einsum("ehd,ehd->eh", G64[rows].reshape(E, H, dv), Vh)
+    else:
+        da = np.einsum("ed,ehd->eh", G64[rows], Vh) / H
+    da = da * dropout_scale(E * H, drop_rate, seed).reshape(E, H).astype(np.float64)
+    delta = np.zeros((len(rowptr) - 1, H))
+    np.add.at(delta, rows, att64 * da)
+    return (att64 * (da - delta[rows])).astype(F32)

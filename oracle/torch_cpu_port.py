@@ -44,8 +44,11 @@ def gcn_forward(x, row, col, normed_value, kernel, bias, relu=True):
     return torch.relu(h) if relu else h
 
 
-def gat_forward(x, row, col, wq, bq, wk, bk, wv, bias, num_heads, relu=True):
-    """nn/conv/gat.py:43-120; row/col already hold the appended self loops (gat.py:43)."""
+def gat_forward(x, row, col, wq, bq, wk, bk, wv, bias, num_heads, relu=True, split_value_heads=True, att_scale=None):
+    """nn/conv/gat.py:43-120; row/col already hold the appended self loops (gat.py:43).
+    att_scale: optional [num_heads * E'] multiplier standing in for tf.nn.dropout on the attention values (gat.py:85),
+    in the virtual-graph order the reference uses (head-major).  Differentiable: torch autograd over this function is
+    the stand-in for TensorFlow autodiff over the reference in the backward-pass tests."""
     n = x.shape[0]
     Q = torch.relu(x @ wq + bq).index_select(0, row)
     K = torch.relu(x @ wk + bk).index_select(0, col)
@@ -56,7 +59,14 @@ def gat_forward(x, row, col, wq, bq, wk, bk, wv, bias, num_heads, relu=True):
     cols_ = torch.cat([col + i * n for i in range(num_heads)])
     att = (Q_ * K_).sum(-1) / (Q_.shape[-1] ** 0.5)
     att = segment_softmax(att, rows_, n * num_heads)
+    if att_scale is not None:
+        att = att * att_scale
     V_ = torch.cat(torch.split(V, V.shape[1] // num_heads, dim=-1), dim=0)
     h_ = spmm(rows_, cols_, att, V_, n * num_heads)
-    h = torch.cat(torch.split(h_, n, dim=0), dim=-1) + bias
+    if split_value_heads:
+        h = torch.cat(torch.split(h_, n, dim=0), dim=-1)                          # gat.py:112
+    else:
+        h = torch.stack(torch.split(h_, n, dim=0)).sum(0) / num_heads             # gat.py:114 (add_n / num_heads)
+    if bias is not None:
+        h = h + bias
     return torch.relu(h) if relu else h

@@ -135,6 +135,46 @@ def install(monkeypatch):
         lower = np.stack([up[1][mask], up[0][mask]])
         return _t(np.concatenate([up, lower], axis=1).astype(np.int32)), _t(np.nonzero(mask)[0].astype(np.int32))
 
+    _MODES = {ops.HEADS_SPLIT: "split", ops.HEADS_BROADCAST: "broadcast", ops.HEADS_REDUCE: "reduce"}
+
+    def dropout(x, rate, seed, rng_stream=0, out=None):
+        return _t(o.dropout(_np(x), rate, seed, rng_stream))
+
+    def spmm_heads(csr, w, src, num_heads, mode=ops.HEADS_SPLIT, emap=None, drop_rate=0.0, seed=0, rng_stream=0,
+                   alpha=1.0, bias=None, act=0, out=None):
+        return _t(o.spmm_heads(_np(csr.rowptr), _np(csr.col), _np(w), _np(src), num_heads, _MODES[mode], _np(emap),
+                               drop_rate, seed, alpha, _np(bias), "relu" if act == ops.ACT_RELU else None))
+
+    def gat_softmax_bwd(csr, att, G, V, num_heads, split_value_heads=True, drop_rate=0.0, seed=0, rng_stream=0):
+        return _t(o.gat_softmax_bwd(_np(csr.rowptr), _np(csr.col), _np(att), _np(G), _np(V), num_heads,
+                                    split_value_heads, drop_rate, seed))
+
+    def edge_flags(row, col, num_edges, mode=ops.FLAG_ALL, row_map=None, col_map=None, bernoulli=ops.BERNOULLI_NONE,
+                   prob=0.0, seed=0, rng_stream=1, device=None):
+        keep = np.ones(num_edges, bool)
+        if mode == ops.FLAG_UPPER:
+            keep = _np(row) < _np(col)
+        elif mode == ops.FLAG_MAPPED:
+            keep = (_np(row_map)[_np(row)] >= 0) & (_np(col_map)[_np(col)] >= 0)
+        if bernoulli != ops.BERNOULLI_NONE:
+            u = o.random_uniform(seed, rng_stream, np.arange(num_edges, dtype=np.uint64))
+            keep = keep & ((u >= np.float32(prob)) if bernoulli == ops.BERNOULLI_DROPOUT else (u <= np.float32(prob)))
+        return _t(keep.astype(np.int32))
+
+    def select_flagged(flag):
+        return _t(np.nonzero(_np(flag))[0].astype(np.int32))
+
+    def gather_i32(src, index):
+        return _t(_np(src)[_np(index)])
+
+    def neighbor_sample(csr, k=None, ratio=None, padding=False, seed=0, rng_stream=1):
+        r, p, rp = o.neighbor_sample_csr(_np(csr.rowptr), k, ratio, padding, seed, rng_stream)
+        return _t(r), _t(p.astype(np.int32)), _t(rp)
+
+    for name, fn in dict(dropout=dropout, spmm_heads=spmm_heads, gat_softmax_bwd=gat_softmax_bwd, edge_flags=edge_flags,
+                         select_flagged=select_flagged, gather_i32=gather_i32, neighbor_sample=neighbor_sample).items():
+        monkeypatch.setattr(ops, name, fn)
+
     from tf_geometric_b200.utils import graph_utils as gu
     monkeypatch.setattr(gu, "_is_device", lambda t: torch.is_tensor(t))     # CPU tensors take the device code path
     monkeypatch.setattr(ops, "edge_unique", edge_unique)

@@ -47,6 +47,9 @@ class OracleApi(object):
     def gcn_graph_sage(self, *a, **k):
         return self.o.gcn_graph_sage(*a, **k)
 
+    def neighbor_sample(self, ei, w, **kw):
+        return self.o.random_neighbor_sample(ei, w, seed=1, **kw)
+
 
 class ProductApi(object):
     exact_float = False
@@ -81,6 +84,9 @@ class ProductApi(object):
     def gcn_norm(self, adj, norm, loop, sym, renorm, improved):
         m = self.tfg.nn.gcn_norm_adj(adj, norm, loop, sym, renorm, improved)
         return m.index, m.value
+
+    def neighbor_sample(self, ei, w, **kw):
+        return self.tfg.utils.RandomNeighborSampler(ei, w).sample(seed=1, **kw)
 
 
 def replay(fname, data, api):
@@ -236,3 +242,20 @@ def _replay_chebynet(d, api):
     ni, nw = api.chebynet_norm_edge(A(d["ei"]), n, A(d["w"]), "sym")
     _eq(O(ni), d["norm_index"], "chebynet_norm_edge index")
     _close(O(nw), d["norm_w"], "chebynet_norm_edge weight", rtol=0 if api.exact_float else 6e-7, atol_scale=0)
+
+
+def _replay_sampler(d, api):
+    """RandomNeighborSampler (graph_utils.py:630-776): deterministic branches bit for bit; for the random branches the
+    per-row sample counts the reference produced (they do not depend on its generator)."""
+    A, O = api.arr, api.out
+    ei, w = A(d["ei"]), A(d["w"])
+    for tag, kw in (("all", {}), ("k_big", {"k": 1000}), ("subset_all", {"sampled_node_index": d["subset"]}),
+                    ("pair_k_big", {"sampled_node_index": (d["rows_sub"], d["cols_sub"]), "k": 1000})):
+        si, sw = api.neighbor_sample(ei, w, **kw)
+        _eq(O(si), d[tag + "_index"], "sampler " + tag)
+        _eq(O(sw), d[tag + "_w"], "sampler weights " + tag)
+    for tag, kw in (("k3", {"k": 3}), ("k3_pad", {"k": 3, "padding": True}), ("k9_pad", {"k": 9, "padding": True}),
+                    ("ratio", {"ratio": 0.4}), ("subset_k2", {"k": 2, "sampled_node_index": d["subset"]})):
+        si, _ = api.neighbor_sample(ei, w, **kw)
+        rows = O(si)[0]
+        _eq(np.bincount(rows, minlength=int(rows.max()) + 1), d[tag + "_counts"], "sampler counts " + tag)

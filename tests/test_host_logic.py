@@ -12,6 +12,7 @@ import test_gpu_index
 import test_gpu_spmm
 import test_gpu_gat
 import test_gpu_models
+import test_gpu_train
 
 
 @pytest.fixture
@@ -104,3 +105,27 @@ def test_golden_fixtures_through_public_api(fake):
     assert len(files) >= 6
     for f in files:
         golden_cases.replay(f, np.load(os.path.join(golden, f), allow_pickle=False), golden_cases.ProductApi())
+
+
+def test_training_extras_and_samplers(fake):
+    """dropout / GAT backward / drop_edge / samplers: host logic over the numpy restatements of the kernels."""
+    test_gpu_train.test_dropout_mask_bit_exact(4099, 0.9)
+    test_gpu_train.test_spmm_heads_bit_exact(3, 5, "split", True, 0.0)
+    test_gpu_train.test_gat_gradients_match_reference_autodiff(24, 64, 128, 8, True, True, 0.4)
+    test_gpu_train.test_gat_gradients_match_reference_autodiff(10, 12, 20, 4, True, False, 0.0)
+    test_gpu_train.test_gat_gradients_match_reference_autodiff(10, 12, 6, 3, False, True, 0.0)
+    test_gpu_train.test_gat_gradients_match_reference_autodiff(10, 12, 6, 3, False, False, 0.3)
+    test_gpu_train.test_gcn_edge_dropout_forward_and_gradients()
+    test_gpu_train.test_appnp_training_gradients_and_dense_dropout()
+    test_gpu_train.test_drop_edge_matches_oracle(False)
+    test_gpu_train.test_drop_edge_matches_oracle(True)
+    test_gpu_train.test_uniform_neighbor_sampler_matches_oracle()
+    test_gpu_train.test_random_neighbor_sampler_matches_oracle(5, None, False)
+    test_gpu_train.test_random_neighbor_sampler_matches_oracle(40, None, True)
+    test_gpu_train.test_random_neighbor_sampler_matches_oracle(None, 0.3, False)
+    import golden_cases
+    golden_cases.replay("ref_exec_sampler.npz", np.load(test_gpu_train.GOLDEN + "/ref_exec_sampler.npz"), golden_cases.ProductApi())
+
+
+def test_gat_layer_trains_on_the_fake_backend(fake):
+    test_gpu_train.test_gat_layer_learns()

@@ -233,3 +233,37 @@ def test_golden_reference_execution_files_match_oracle():
     for f in files:
         data = np.load(os.path.join(GOLDEN, f), allow_pickle=False)
         replay_with_oracle(f, data)
+
+
+def test_philox_known_answers_and_uniform_draws():
+    """Philox4x32-10 against the Random123 known-answer vectors (counter, key -> output); the kernels in
+    tf_geometric_b200/csrc/rng.cuh implement the same function and are compared with the oracle bit for bit on the GPU."""
+    counter = np.array([[0, 0, 0, 0], [0xFFFFFFFF] * 4, [0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344]], np.uint32)
+    key = np.array([[0, 0], [0xFFFFFFFF] * 2, [0xA4093822, 0x299F31D0]], np.uint32)
+    want = np.array([[0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8], [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD],
+                     [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]], np.uint32)
+    np.testing.assert_array_equal(o.philox4x32(counter, key), want)
+    idx = np.arange(200000, dtype=np.uint64)
+    u = o.random_uniform(42, 0, idx)
+    assert u.dtype == np.float32 and u.min() >= 0.0 and u.max() < 1.0
+    assert abs(u.mean() - 0.5) < 5e-3 and abs((u < 0.1).mean() - 0.1) < 5e-3
+    assert abs(np.corrcoef(u[:-1], u[1:])[0, 1]) < 0.01
+    assert not np.array_equal(u, o.random_uniform(43, 0, idx)) and not np.array_equal(u, o.random_uniform(42, 1, idx))
+    np.testing.assert_array_equal(o.random_u32(42, 0, idx[4:8]), o.philox4x32(np.array([[1, 0, 0, 0]], np.uint32),
+                                                                            np.array([[42, 0]], np.uint32))[0])
+    b = o.random_below(7, 1, idx, 10)
+    assert b.min() == 0 and b.max() == 9 and abs(np.bincount(b).std() / np.bincount(b).mean()) < 0.02
+
+
+def test_dropout_and_drop_edge_semantics():
+    x = np.random.RandomState(0).randn(50000).astype(np.float32)
+    y = o.dropout(x, 0.2, seed=9)
+    kept = y != 0
+    assert abs(kept.mean() - 0.8) < 0.01
+    np.testing.assert_array_equal(y[kept], (x * (np.float32(1) / np.float32(0.8)))[kept])
+    np.testing.assert_array_equal(o.dropout(x, 0.0, seed=9), x)
+    ei = np.array([[0, 1, 1, 2, 3, 0], [1, 0, 2, 1, 3, 3]], np.int32)
+    out = o.drop_edge([ei, np.arange(6)], 0.0, force_undirected=True, training=True)
+    np.testing.assert_array_equal(out[0], [[0, 1, 0, 1, 2, 3], [1, 2, 3, 0, 1, 0]])       # row<col edges, then mirrored
+    np.testing.assert_array_equal(out[1], [0, 2, 5, 0, 2, 5])
+    assert o.drop_edge([ei], 0.5, training=False)[0] is ei

@@ -14,5 +14,6 @@ works without a GPU, calling any operator does not (there is no CPU fallback).
 from . import _ffi, ops, nn, layers, utils
 from .data.graph import Graph
 from .sparse import SparseMatrix
+from ._rng import set_seed
 
 __version__ = "0.1.0"

@@ -1,6 +1,6 @@
 # coding=utf-8
-"""Backward passes for the GraphSAGE path (mean/sum_graph_sage forward + backward; the reference gets
-them from TensorFlow autodiff, demo/demo_graph_sage.py:100-106).
+"""Backward passes (mean/sum_graph_sage forward + backward; 8(f)4: GCN and GAT training); the reference
+gets them from TensorFlow autodiff (demo/demo_graph_sage.py:100-106, demo/demo_gcn.py:60-75, demo/demo_gat.py).
 
     d(unsorted_segment_mean(x[col] * w, row)) / dx  =  scatter-add by col of  (w_e / max(cnt[row_e], 1)) * g[row_e]
 
@@ -9,6 +9,9 @@ destination-sorted CSR of the reversed edges) with rescaled weights; it is built
 to the forward CSR.  Dense layers: dX = dY W^T and dW = X^T dY are tfgk_gemm_f32 with transposes (deterministic split-K
 over the node dimension), db = 1^T dY through the same kernel.
 """
+import weakref
+
+import numpy as np
 import torch
 
 from . import ops, _structure
@@ -109,6 +112,92 @@ class SparseMatmul(torch.autograd.Function):
             ones = torch.ones((g.shape[0], 1), dtype=torch.float32, device=g.device)
             grad_b = ops.gemm(ones, g, trans_a=True).reshape(-1)
         return grad_h, grad_b, None, None
+
+
+def _transposed_of_csr(csr, edge_index_used):
+    """(csr_t, emap) for a forward CSR: csr_t has one row per SOURCE node, its columns are the destination rows, and
+    emap[p] is the forward-CSR position of transposed slot p (per-edge tables such as the attention coefficients are
+    stored in forward-CSR order).  Built once per CSR object."""
+    hit = _structure._lookup(csr.col, ("csr_t",))
+    if hit is not None and hit[0]() is csr:
+        return hit[1], hit[2]
+    row_of_pos = ops.gather_i32(edge_index_used[0].contiguous(), csr.perm)        # destination row of every CSR slot
+    csr_t = ops.csr_build(csr.col, row_of_pos, csr.n_cols, csr.n_rows)
+    _structure._store(csr.col, ("csr_t",), (weakref.ref(csr), csr_t, csr_t.perm))
+    return csr_t, csr_t.perm
+
+
+class GatAttention(torch.autograd.Function):
+    """y = act(softmax-attention aggregate(Q, K, V) + b) (gat.py:73-120) with gradients for Q, K, V and b.
+
+    forward : tfgk_gat_fused_f32 (coefficients kept for the backward); with attention dropout (gat.py:85) the
+              coefficients are re-aggregated by tfgk_spmm_heads_f32 under a counter-based mask.
+    backward: G = dy * act'(y);  ds = tfgk_gat_softmax_bwd_f32(att, G, V);
+              dQ = sum_e ds K[col] / scale                       forward CSR
+              dK = sum_e ds Q[row] / scale,  dV = sum_e a' G[row] transposed CSR (gather instead of scatter-add)
+    The mask is regenerated from (seed, edge, head) in every kernel, never stored."""
+
+    @staticmethod
+    def forward(ctx, Q, K, V, bias, csr, edge_index_used, num_heads, split, act_code, drop_rate, seed):
+        Qd, Kd, Vd = Q.detach(), K.detach(), V.detach()
+        b = None if bias is None else bias.detach()
+        H = int(num_heads)
+        if drop_rate > 0.0:
+            _, att = ops.gat_fused(csr, Qd, Kd, Vd, H, split_value_heads=split, return_attention=True)
+            y = ops.spmm_heads(csr, att, Vd, H, mode=ops.HEADS_SPLIT if split else ops.HEADS_REDUCE,
+                               drop_rate=drop_rate, seed=seed, alpha=1.0 if split else 1.0 / H, bias=b, act=act_code)
+        else:
+            y, att = ops.gat_fused(csr, Qd, Kd, Vd, H, split_value_heads=split, bias=b, act=act_code,
+                                   return_attention=True)
+        ctx.save_for_backward(Qd, Kd, Vd, att, y if act_code == ops.ACT_RELU else None)
+        ctx.meta = (csr, edge_index_used, H, bool(split), act_code, float(drop_rate), seed, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        Q, K, V, att, y = ctx.saved_tensors
+        csr, edge_index_used, H, split, act_code, drop_rate, seed, has_bias = ctx.meta
+        g = grad_y.contiguous()
+        if act_code == ops.ACT_RELU:
+            g = g * (y > 0).to(g.dtype)
+        inv_scale = 1.0 / float(np.sqrt(np.float32(Q.shape[1] // H)))
+        ds = ops.gat_softmax_bwd(csr, att, g, V, H, split_value_heads=split, drop_rate=drop_rate, seed=seed)
+        grad_q = grad_k = grad_v = grad_b = None
+        if ctx.needs_input_grad[0]:
+            grad_q = ops.spmm_heads(csr, ds, K, H, alpha=inv_scale)
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            csr_t, emap = _transposed_of_csr(csr, edge_index_used)
+            if ctx.needs_input_grad[1]:
+                grad_k = ops.spmm_heads(csr_t, ds, Q, H, emap=emap, alpha=inv_scale)
+            if ctx.needs_input_grad[2]:
+                grad_v = ops.spmm_heads(csr_t, att, g, H, mode=ops.HEADS_SPLIT if split else ops.HEADS_BROADCAST,
+                                        emap=emap, drop_rate=drop_rate, seed=seed, alpha=1.0 if split else 1.0 / H)
+        if has_bias and ctx.needs_input_grad[3]:
+            ones = torch.ones((g.shape[0], 1), dtype=torch.float32, device=g.device)
+            grad_b = ops.gemm(ones, g, trans_a=True).reshape(-1)
+        return grad_q, grad_k, grad_v, grad_b, None, None, None, None, None, None, None
+
+
+class Dropout(torch.autograd.Function):
+    """tf.nn.dropout on dense activations (appnp.py:75-79, ssgc.py:84-88); the backward re-applies the same
+    counter-based mask to the incoming gradient."""
+
+    @staticmethod
+    def forward(ctx, x, rate, seed):
+        ctx.rate, ctx.seed = float(rate), int(seed)
+        return ops.dropout(x.detach().contiguous(), ctx.rate, ctx.seed)
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        return ops.dropout(grad_y.contiguous(), ctx.rate, ctx.seed), None, None
+
+
+def dropout(x, rate, training, seed=None):
+    """Functional helper: identity unless training and rate > 0."""
+    if not training or rate <= 0.0:
+        return x
+    from . import _rng
+    return Dropout.apply(x, float(rate), _rng.resolve(seed))
 
 
 def needs_grad(*tensors):

@@ -13,3 +13,4 @@ from .conv.propagation import (sgc, ssgc, tagcn, gin, gin_updater, le_conv, cheb
                                get_laplacian)
 from .pool.common_pool import mean_pool, sum_pool, max_pool, min_pool
 from ..ops import relu
+from .sampling.drop_edge import drop_edge

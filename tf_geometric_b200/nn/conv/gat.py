@@ -7,14 +7,14 @@ segment_softmax over H*E' scores and finally a SpMM.  Here: three dense projecti
 """
 import torch
 
-from ... import ops, _structure
+from ... import ops, _structure, _rng, autograd
 
 
 def gat(x, edge_index,
         query_kernel, query_bias, query_activation,
         key_kernel, key_bias, key_activation,
         kernel, bias=None, activation=None, num_heads=1,
-        split_value_heads=True, edge_drop_rate=0.0, training=False, cache=None, return_attention=False):
+        split_value_heads=True, edge_drop_rate=0.0, training=False, cache=None, return_attention=False, seed=None):
     """
     :param x: [num_nodes, num_features]
     :param edge_index: [2, num_edges]; self loops are appended (never de-duplicated), reference gat.py:43
@@ -23,16 +23,23 @@ def gat(x, edge_index,
     :param num_heads: heads; attention_units (and units when splitting) must be divisible by it
     :param split_value_heads: True: heads own slices of V and are concatenated; False: every head sees a full V and
         the head outputs are averaged
+    :param edge_drop_rate: dropout on the attention coefficients while training (gat.py:85)
     :param cache: optional dict (e.g. graph.cache) memoising the self-looped CSR; an extension of the reference API
+    :param seed: optional 64-bit key pinning the dropout mask (extension; default: a fresh key per call)
     :return: [num_nodes, units]
     """
-    if training and edge_drop_rate > 0.0:
-        raise NotImplementedError("attention dropout (TF RNG stream) is outside the forward hot path of this backend")
     edge_index = ops.as_device(edge_index, torch.int32)
     dev = edge_index.device
     x = ops.as_device(x, torch.float32, device=dev)
     num_nodes = x.shape[0]
-    csr, _ = _structure.csr_for_edge_index(edge_index, num_nodes, add_self_loop=True, cache=cache)
+    csr, edge_index_used = _structure.csr_for_edge_index(edge_index, num_nodes, add_self_loop=True, cache=cache)
+    drop_rate = float(edge_drop_rate) if training else 0.0
+    if drop_rate > 0.0 or autograd.needs_grad(x, query_kernel, query_bias, key_kernel, key_bias, kernel, bias):
+        if return_attention:
+            raise NotImplementedError("return_attention is an inference-path extension")
+        return _gat_training(x, csr, edge_index_used, query_kernel, query_bias, query_activation, key_kernel, key_bias,
+                             key_activation, kernel, bias, activation, num_heads, split_value_heads, drop_rate,
+                             _rng.resolve(seed) if drop_rate > 0.0 else 0)
 
     q_act, q_left = ops.activation_code(query_activation)
     k_act, k_left = ops.activation_code(key_activation)
@@ -62,3 +69,26 @@ def gat(x, edge_index,
     if return_attention:
         return h, ops.permute(att, csr.perm, inverse=True)     # [E', H] in edge_index-with-self-loops order
     return h
+
+
+def _gat_training(x, csr, edge_index_used, query_kernel, query_bias, query_activation, key_kernel, key_bias,
+                  key_activation, kernel, bias, activation, num_heads, split_value_heads, drop_rate, seed):
+    """The same layer behind autograd Functions (demo/demo_gat.py trains through tf.GradientTape): dense projections
+    with dX/dW/db GEMMs, then GatAttention."""
+    dev = x.device
+
+    def dense(w, b, act):
+        code, left = ops.activation_code(act)
+        w = ops.as_device(w, torch.float32, device=dev)
+        b = None if b is None else ops.as_device(b, torch.float32, device=dev)
+        y = autograd.Dense.apply(x, w, b, code)
+        return left(y) if left is not None else y
+
+    Q = dense(query_kernel, query_bias, query_activation)
+    K = dense(key_kernel, key_bias, key_activation)
+    V = dense(kernel, None, None)
+    act_code, leftover = ops.activation_code(activation)
+    bias = None if bias is None else ops.as_device(bias, torch.float32, device=dev)
+    h = autograd.GatAttention.apply(Q, K, V, bias, csr, edge_index_used, int(num_heads), bool(split_value_heads),
+                                    act_code, drop_rate, seed)
+    return leftover(h) if leftover is not None else h

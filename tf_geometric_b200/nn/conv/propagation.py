@@ -4,7 +4,7 @@ Each one is the K1 kernel (tfgk_spmm_f32) in a loop with the per-layer arithmeti
 reference's rounding order allows it; signatures follow tf_geometric/nn/conv/{sgc,ssgc,tagcn,gin,le_conv}.py."""
 import torch
 
-from ... import ops, _structure
+from ... import ops, _structure, autograd
 from ...sparse import SparseMatrix
 from .gcn import gcn_norm_adj
 
@@ -39,13 +39,12 @@ def sgc(x, edge_index, edge_weight, k, kernel, bias=None, activation=None, renor
 def ssgc(x, edge_index, edge_weight, kernels=None, biases=None, k=10, alpha=0.1, dense_activation=ops.relu,
          activation=None, dense_drop_rate=0.0, last_dense_drop_rate=0.0, edge_drop_rate=0.0, cache=None, training=False):
     """Simple Spectral Graph Convolution: alpha * h + (1 - alpha)/k * sum_{i=1..k} norm(A)^i h   (reference ssgc.py:11-99)."""
-    if training and (dense_drop_rate > 0.0 or last_dense_drop_rate > 0.0 or edge_drop_rate > 0.0):
-        raise NotImplementedError("dropout (TF RNG stream) is outside the forward hot path of this backend")
     edge_index = ops.as_device(edge_index, torch.int32)
     dev = edge_index.device
     h = _f32(x, dev)
     n = h.shape[0]
     normed = gcn_norm_adj(SparseMatrix(edge_index, edge_weight, [n, n]), cache=cache)
+    normed = normed.dropout(edge_drop_rate, training=training)                          # ssgc.py:60-61
     if kernels is not None:
         num_dense = len(kernels)
         for i, (kern, b) in enumerate(zip(kernels, biases)):
@@ -53,6 +52,7 @@ def ssgc(x, edge_index, edge_weight, kernels=None, biases=None, k=10, alpha=0.1,
             h = ops.gemm(h, _f32(kern, dev), bias=_f32(b, dev), act=act_code)
             if leftover is not None:
                 h = leftover(h)
+            h = autograd.dropout(h, dense_drop_rate if i < num_dense - 1 else last_dense_drop_rate, training)  # :84-88
     output = h * alpha                                    # elementwise glue in the reference's rounding order (:91-94)
     for _ in range(k):
         h = normed.matmul(h)

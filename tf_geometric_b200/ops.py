@@ -10,7 +10,9 @@ import numpy as np
 import torch
 
 from . import _ffi
-from ._ffi import (REDUCE_SUM, REDUCE_MEAN, REDUCE_MAX, ACT_NONE, ACT_RELU, POW_INV_SQRT, POW_INV)  # noqa: F401
+from ._ffi import (REDUCE_SUM, REDUCE_MEAN, REDUCE_MAX, ACT_NONE, ACT_RELU, POW_INV_SQRT, POW_INV,  # noqa: F401
+                   HEADS_SPLIT, HEADS_BROADCAST, HEADS_REDUCE, FLAG_ALL, FLAG_UPPER, FLAG_MAPPED,
+                   BERNOULLI_NONE, BERNOULLI_DROPOUT, BERNOULLI_KEEP)
 
 _REDUCE_CODES = {"sum": REDUCE_SUM, "mean": REDUCE_MEAN, "max": REDUCE_MAX}
 
@@ -335,6 +337,118 @@ def gat_fused(csr, Q, K, V, num_heads, split_value_heads=True, bias=None, act=AC
     if return_attention:
         return out, att[:csr.nnz]
     return out
+
+
+# ---- training-mode extras: dropout, per-head aggregation, GAT softmax backward -----------------------------------
+
+RNG_STREAM_DROPOUT, RNG_STREAM_SAMPLER = 0, 1      # rng_stream ids: independent draws for the same (seed, element)
+
+
+def dropout(x, rate, seed, rng_stream=RNG_STREAM_DROPOUT, out=None):
+    """tf.nn.dropout with a counter-based mask: element i is kept iff u(seed, i) >= rate, kept values * 1/(1-rate)."""
+    _check(x, torch.float32, "x")
+    if out is None:
+        out = torch.empty_like(x)
+    _ffi.call("tfgk_dropout_f32", _p(x), x.numel(), float(rate), int(seed), int(rng_stream), _p(out), _stream(x))
+    return out
+
+
+def spmm_heads(csr, w, src, num_heads, mode=HEADS_SPLIT, emap=None, drop_rate=0.0, seed=0,
+               rng_stream=RNG_STREAM_DROPOUT, alpha=1.0, bias=None, act=ACT_NONE, out=None):
+    """Per-(edge, head) weighted aggregation over `csr`; see tfgk_spmm_heads_f32.  w: [E, H] (looked up through `emap`
+    when the CSR is a transposed view of the structure w was computed on)."""
+    _check(w, torch.float32, "w")
+    if not (src.is_cuda and src.dtype == torch.float32):
+        raise TypeError("src must be a float32 CUDA tensor")
+    if emap is not None:
+        _check(emap, torch.int32, "emap")
+    H = int(num_heads)
+    lds = _row_major_2d(src, "src")
+    if mode == HEADS_BROADCAST:
+        dh = src.shape[1]
+        out_w = H * dh
+    else:
+        if src.shape[1] % H:
+            raise ValueError("spmm_heads: {} source columns are not divisible by {} heads".format(src.shape[1], H))
+        dh = src.shape[1] // H
+        out_w = dh if mode == HEADS_REDUCE else H * dh
+    if out is None:
+        out = torch.empty((csr.n_rows, out_w), dtype=torch.float32, device=src.device)
+    if bias is not None:
+        _check(bias, torch.float32, "bias")
+    _ffi.call("tfgk_spmm_heads_f32", _p(csr.rowptr), _p(csr.col), _p(emap), _p(w), _p(src), lds, csr.n_rows, H, dh,
+              int(mode), float(drop_rate), int(seed), int(rng_stream), float(alpha), _p(bias), act, _p(out),
+              _row_major_2d(out, "out"), _stream(src))
+    return out
+
+
+def gat_softmax_bwd(csr, att, G, V, num_heads, split_value_heads=True, drop_rate=0.0, seed=0,
+                    rng_stream=RNG_STREAM_DROPOUT):
+    """d loss / d scaled scores [E, H] (CSR order) from G = d loss / d aggregated rows; see tfgk_gat_softmax_bwd_f32."""
+    _check(att, torch.float32, "att")
+    H = int(num_heads)
+    dv = V.shape[1] // H
+    ds = torch.empty((csr.nnz, H), dtype=torch.float32, device=att.device)
+    _ffi.call("tfgk_gat_softmax_bwd_f32", _p(csr.rowptr), _p(csr.col), _p(att), _p(G), _row_major_2d(G, "G"), _p(V),
+              _row_major_2d(V, "V"), csr.n_rows, H, dv, 1 if split_value_heads else 0, float(drop_rate), int(seed),
+              int(rng_stream), _p(ds), _stream(att))
+    return ds
+
+
+# ---- device-side edge sampling -----------------------------------------------------------------------------------
+
+def edge_flags(row, col, num_edges, mode=FLAG_ALL, row_map=None, col_map=None, bernoulli=BERNOULLI_NONE, prob=0.0,
+               seed=0, rng_stream=RNG_STREAM_SAMPLER, device=None):
+    """int32 [E] keep flags: structural rule AND Bernoulli rule (tfgk_edge_flags_i32)."""
+    for t, n in ((row, "row"), (col, "col"), (row_map, "row_map"), (col_map, "col_map")):
+        if t is not None:
+            _check(t, torch.int32, n)
+    dev = device if row is None else row.device
+    flag = torch.empty((num_edges,), dtype=torch.int32, device=dev)
+    _ffi.call("tfgk_edge_flags_i32", _p(row), _p(col), num_edges, int(mode), _p(row_map), _p(col_map), int(bernoulli),
+              float(prob), int(seed), int(rng_stream), _p(flag), _stream(flag))
+    return flag
+
+
+def select_flagged(flag):
+    """Ascending positions of the non-zero flags (tf.boolean_mask(tf.range(n), flag)), int32 [n_selected]."""
+    _check(flag, torch.int32, "flag")
+    n = flag.numel()
+    need = ctypes.c_size_t()
+    _ffi.call("tfgk_select_workspace_bytes", n, ctypes.byref(need))
+    ws = torch.empty((max(need.value, 1),), dtype=torch.uint8, device=flag.device)
+    out = torch.empty((max(n, 1),), dtype=torch.int32, device=flag.device)
+    n_out = ctypes.c_int64()
+    _ffi.call("tfgk_select_flagged_i32", _p(flag), n, _p(out), ctypes.byref(n_out), _p(ws), need.value, _stream(flag))
+    return out[:n_out.value]
+
+
+def gather_i32(src, index):
+    """src[index] for int32 vectors: a bit copy through tfgk_permute_f32 (the kernel moves 4-byte words)."""
+    _check(src, torch.int32, "src")
+    return permute(src.view(torch.float32), index).view(torch.int32)
+
+
+def neighbor_sample(csr, k=None, ratio=None, padding=False, seed=0, rng_stream=RNG_STREAM_SAMPLER):
+    """Fan-out sampling over the rows of `csr` (tfgk_neighbor_sample_*).  Returns (row int32 [S], pos int32 [S],
+    out_rowptr int64 [n_rows+1]): the row of every sampled edge and the CSR position it was drawn from."""
+    dev = csr.rowptr.device
+    kk = -1 if k is None else int(k)
+    rr = -1.0 if ratio is None else float(ratio)
+    need = ctypes.c_size_t()
+    _ffi.call("tfgk_neighbor_sample_workspace_bytes", csr.n_rows, ctypes.byref(need))
+    ws = torch.empty((max(need.value, 1),), dtype=torch.uint8, device=dev)
+    out_rowptr = torch.empty((csr.n_rows + 1,), dtype=torch.int64, device=dev)
+    total = ctypes.c_int64()
+    _ffi.call("tfgk_neighbor_sample_count", _p(csr.rowptr), csr.n_rows, kk, rr, 1 if padding else 0, _p(out_rowptr),
+              ctypes.byref(total), _p(ws), need.value, _stream(out_rowptr))
+    S = total.value
+    out_row = torch.empty((S,), dtype=torch.int32, device=dev)
+    out_pos = torch.empty((S,), dtype=torch.int32, device=dev)
+    if S:
+        _ffi.call("tfgk_neighbor_sample_fill", _p(csr.rowptr), csr.n_rows, kk, rr, 1 if padding else 0, int(seed),
+                  int(rng_stream), _p(out_rowptr), _p(out_row), _p(out_pos), _stream(out_rowptr))
+    return out_row, out_pos, out_rowptr
 
 
 # ---- K4 ----------------------------------------------------------------------------------------------------------

@@ -9,7 +9,7 @@ values are built lazily, once per object, and reused by every product - this is 
 """
 import torch
 
-from . import ops
+from . import ops, _rng
 
 
 class SparseMatrix(object):
@@ -97,10 +97,14 @@ class SparseMatrix(object):
         value = ops.self_loop_weights(self.value, self.nnz, n, diag_value, self.index.device)
         return SparseMatrix(index, value, self._shape)
 
-    def dropout(self, rate, training=False):
-        if training and rate > 0.0:
-            raise NotImplementedError("edge dropout (TF RNG stream) is outside the forward hot path of this backend")
-        return self
+    def dropout(self, rate, training=False, seed=None):
+        """tf.nn.dropout on the stored values (gcn.py:262, appnp.py:84): the pattern is unchanged, dropped entries
+        become explicit zeros and the kept ones are scaled by 1/(1-rate).  `seed` (an extension) pins the mask."""
+        if not training or rate <= 0.0:
+            return self
+        out = SparseMatrix(self.index, ops.dropout(self.value, rate, _rng.resolve(seed)), self._shape, _csr=self._csr)
+        out._csc = self._csc
+        return out
 
     def matmul(self, h, num_or_size_splits=None, **epilogue):
         """A @ h (gcn.py:280).  `num_or_size_splits` is accepted for signature parity; the fused kernel never

@@ -240,3 +240,7 @@ def compute_num_or_size_splits(num_h_features, num_splits):
         raise Exception("cannot split H of shape [None, {}] into {} matrices, please provide a valid num_splits"
                         .format(num_h_features, num_splits))
     return sizes
+
+
+# samplers live in utils/sampling.py; re-exported here because the reference defines them in this module (:630-846)
+from .sampling import RandomNeighborSampler, UniformNeighborSampler  # noqa: E402,F401

@@ -236,6 +236,27 @@ def main():
     out["norm_index"], out["norm_w"] = ni, nw
     save("chebynet", **out)
 
+    # ---- RandomNeighborSampler: the deterministic branches, and the per-row COUNTS of the random ones ----------------------
+    n = 40
+    ei = graph(n, 260, 23, False)
+    ei[0][ei[0] == 7] = 8                              # node 7 has no neighbours
+    w = rs.rand(ei.shape[1]).astype(np.float32)
+    sampler = gu.RandomNeighborSampler(ei, w)
+    subset = np.array([9, 4, 30, 12, 8, 21, 3, 17, 5, 33], np.int32)
+    rows_sub, cols_sub = np.array([8, 3, 11, 30, 25], np.int32), np.array([1, 2, 3, 4, 5, 6, 10, 20, 30], np.int32)
+    out = {"n": n, "ei": ei, "w": w, "subset": subset, "rows_sub": rows_sub, "cols_sub": cols_sub}
+    for tag, kw in (("all", {}), ("k_big", {"k": 1000}), ("subset_all", {"sampled_node_index": subset}),
+                    ("pair_k_big", {"sampled_node_index": (rows_sub, cols_sub), "k": 1000})):
+        si, sw = sampler.sample(**kw)
+        out[tag + "_index"], out[tag + "_w"] = si, sw
+    np.random.seed(0)
+    for tag, kw in (("k3", {"k": 3}), ("k3_pad", {"k": 3, "padding": True}), ("k9_pad", {"k": 9, "padding": True}),
+                    ("ratio", {"ratio": 0.4}), ("subset_k2", {"k": 2, "sampled_node_index": subset})):
+        si, _ = sampler.sample(**kw)
+        rows_out = int(si[0].max()) + 1
+        out[tag + "_counts"] = np.bincount(si[0], minlength=rows_out)
+    save("sampler", **out)
+
 
 if __name__ == "__main__":
     main()
