@@ -214,9 +214,7 @@ __global__ void __launch_bounds__(kTrainThreads) gat_softmax_bwd128_kernel(const
     const int32_t *col = p.col + start;
     const float4 g = *reinterpret_cast<const float4 *>(p.G + r * p.ldg + lane * 4);
     float dacc = 0.0f;
-    for (int e = 0; e < deg; ++e) {
-        const float4 v = *reinterpret_cast<const float4 *>(p.V + (int64_t)col[e] * p.ldv + lane * 4);
-        float d = g.x * v.x + g.y * v.y + g.z * v.z + g.w * v.w;
+    auto finish = [&](float d, int e) {
         for (int off = group >> 1; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
         if (leader) {
             const int64_t idx = (int64_t)e * H + h;
@@ -224,6 +222,18 @@ __global__ void __launch_bounds__(kTrainThreads) gat_softmax_bwd128_kernel(const
             ds[idx] = d;
             dacc += att[idx] * d;
         }
+    };
+    int e = 0;
+    for (; e + 4 <= deg; e += 4) {                  // four gathered value rows in flight
+        float4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4 *>(p.V + (int64_t)col[e + i] * p.ldv + lane * 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) finish(g.x * v[i].x + g.y * v[i].y + g.z * v[i].z + g.w * v[i].w, e + i);
+    }
+    for (; e < deg; ++e) {
+        const float4 v = *reinterpret_cast<const float4 *>(p.V + (int64_t)col[e] * p.ldv + lane * 4);
+        finish(g.x * v.x + g.y * v.y + g.z * v.z + g.w * v.w, e);
     }
     if (leader) delta[h] = dacc;
     __syncwarp();

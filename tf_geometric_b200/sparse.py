@@ -32,6 +32,7 @@ class SparseMatrix(object):
         self._value_csr = _value_csr
         self._csc = None
         self._value_csc = None
+        self._pattern_of = None           # matrix with the same pattern whose transposed CSR is shared (dropout)
 
     # ---- structure ----
     @property
@@ -64,6 +65,8 @@ class SparseMatrix(object):
         return self._value_csr
 
     def _transposed_csr(self):
+        if self._csc is None and self._pattern_of is not None:
+            self._csc = self._pattern_of._transposed_csr()
         if self._csc is None:
             self._csc = ops.csr_build(self.index[1].contiguous(), self.index[0].contiguous(), self._shape[1],
                                       self._shape[0])
@@ -103,7 +106,7 @@ class SparseMatrix(object):
         if not training or rate <= 0.0:
             return self
         out = SparseMatrix(self.index, ops.dropout(self.value, rate, _rng.resolve(seed)), self._shape, _csr=self._csr)
-        out._csc = self._csc
+        out._pattern_of = self            # the transposed structure (backward) is built once, on the cached parent
         return out
 
     def matmul(self, h, num_or_size_splits=None, **epilogue):
