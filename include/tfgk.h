@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TFGK_ABI_VERSION 3
+#define TFGK_ABI_VERSION 4
 
 enum tfgk_status {
     TFGK_OK = 0,
@@ -43,6 +43,7 @@ enum tfgk_deg_power { TFGK_POW_INV_SQRT = 0, TFGK_POW_INV = 1 };
 enum tfgk_heads_mode { TFGK_HEADS_SPLIT = 0, TFGK_HEADS_BROADCAST = 1, TFGK_HEADS_REDUCE = 2 };
 enum tfgk_edge_flag { TFGK_FLAG_ALL = 0, TFGK_FLAG_UPPER = 1, TFGK_FLAG_MAPPED = 2 };
 enum tfgk_bernoulli { TFGK_BERNOULLI_NONE = 0, TFGK_BERNOULLI_DROPOUT = 1, TFGK_BERNOULLI_KEEP = 2 };
+enum tfgk_sample_padding { TFGK_SAMPLE_NO_PADDING = 0, TFGK_SAMPLE_PADDING = 1, TFGK_SAMPLE_HEAD = 2 };
 
 int tfgk_version(void);
 const char *tfgk_last_error(void);
@@ -225,13 +226,24 @@ int tfgk_select_workspace_bytes(int64_t n, size_t *out_bytes);
 int tfgk_select_flagged_i32(const int32_t *flag, int64_t n, int32_t *out_index, int64_t *n_out_host,
                             void *workspace, size_t workspace_bytes, void *stream);
 
+/* Building blocks of nn/pool/topk_pool.py:31-58 (tf.argsort by source, per-source descending tf.argsort of the scores):
+ * keys[i] = order-preserving 32-bit pattern of score[i] (complemented for descending; -0.0 ties with +0.0), and a
+ * stable LSD radix argsort of 32-bit patterns read as unsigned numbers (only the low key_bits are examined):
+ * perm_out[j] = position of the j-th smallest key, equal keys in input order. */
+int tfgk_sort_keys_f32(const float *score, int64_t n, int descending, int32_t *keys, void *stream);
+int tfgk_argsort_workspace_bytes(int64_t n, size_t *out_bytes);
+int tfgk_stable_argsort_u32(const int32_t *keys, int64_t n, int key_bits, int32_t *perm_out,
+                            void *workspace, size_t workspace_bytes, void *stream);
+
 /* RandomNeighborSampler.sample (graph_utils.py:669-776) on a CSR whose rows are the source nodes in ascending order
  * with neighbours in edge order (= the reference's neighbor_dict).  k < 0 and ratio < 0: every neighbour; ratio < 0:
  * k per row (all of them in order when k >= degree and !padding; k draws WITH replacement when padding and
  * k >= degree); otherwise ceil(degree * ratio) without replacement.  Rows without neighbours emit nothing.
  * _count writes the [n_rows + 1] offsets of the sampled edges and their total (synchronises); _fill writes, per sampled
  * edge, its row and the CSR position it was taken from (gather col / weights with tfgk_permute_f32).  Without
- * replacement = reservoir sampling with draws (seed, rng_stream, row << 32 | i). */
+ * replacement = reservoir sampling with draws (seed, rng_stream, row << 32 | i).
+ * padding = TFGK_SAMPLE_HEAD is the deterministic rule of nn/pool/topk_pool.py:59-82: the FIRST min(k, degree) (or
+ * ceil(float(degree) * float(ratio)), float32 like the reference) entries of every row, in order. */
 int tfgk_neighbor_sample_workspace_bytes(int32_t n_rows, size_t *out_bytes);
 int tfgk_neighbor_sample_count(const int64_t *rowptr, int32_t n_rows, int32_t k, double ratio, int padding,
                                int64_t *out_rowptr, int64_t *total_host, void *workspace, size_t workspace_bytes,

@@ -946,7 +946,10 @@ def neighbor_sample_csr(rowptr, k=None, ratio=None, padding=False, seed=0, strea
         if deg == 0:
             continue
         base = np.uint64(r) << np.uint64(32)
-        if (k is None and ratio is None) or (ratio is None and not padding and k >= deg):
+        if padding == "head":                                   # topk_pool.py:59-82: the first node_k entries, in order
+            num = min(int(k), deg) if ratio is None else int(np.ceil(F32(deg) * F32(ratio)))
+            pos = start + np.arange(max(min(num, deg), 0))
+        elif (k is None and ratio is None) or (ratio is None and not padding and k >= deg):
             pos = start + np.arange(deg)
         elif ratio is None and padding and k >= deg:
             pos = start + random_below(seed, stream, base + np.arange(k, dtype=np.uint64), deg)
@@ -1030,3 +1033,101 @@ def gat_softmax_bwd(rowptr, col, att, G, V, num_heads, split_value_heads=True, d
     delta = np.zeros((len(rowptr) - 1, H))
     np.add.at(delta, rows, att64 * da)
     return (att64 * (da - delta[rows])).astype(F32)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Pooling beyond the plain segment reductions: set2set, topk_pool, sag_pool, induced subgraphs
+# --------------------------------------------------------------------------------------------------------------
+
+def set2set(x, node_graph_index, lstm, num_iterations, training=None):
+    """nn/pool/set2set.py:8-44.  `lstm` keeps the Keras calling convention (inputs [1, G, 2F], initial_state=[h, c]) ->
+    (sequence [1, G, F], h, c); it is an argument of the reference too."""
+    x = _as_f32(x)
+    gi = np.asarray(node_graph_index, I32)
+    num_graphs = int(gi.max()) + 1
+    units = x.shape[-1]
+    h = np.zeros((num_graphs, units * 2), F32)
+    state = [np.zeros((1, units), F32), np.zeros((1, units), F32)]
+    for _ in range(num_iterations):
+        h, state_h, state_c = lstm(h[None], initial_state=state, training=training)       # :30-33
+        state = [state_h, state_c]
+        h = np.asarray(h, F32)[0]
+        repeated_h = gather(h, gi)                                                         # :35
+        att_score = np.sum(x * repeated_h, axis=-1, keepdims=True).astype(F32)             # :37
+        normed = segment_softmax(att_score, gi, num_graphs)                                # :38
+        att_h = unsorted_segment_sum((x * normed).astype(F32), gi, num_graphs)             # :39
+        h = np.concatenate([h, att_h], axis=-1).astype(F32)                                # :40
+    return h
+
+
+def topk_pool(source_index, score, k=None, ratio=None):
+    """nn/pool/topk_pool.py:6-88: indices of the node_k best-scored targets of every source, sources ascending, best
+    first.  tf.argsort is restated as a STABLE sort (equal keys keep their order; TF leaves it unspecified)."""
+    if k is None and ratio is None:
+        raise Exception("you should provide either k or ratio for topk_pool")
+    elif k is not None and ratio is not None:
+        raise Exception("you should provide either k or ratio for topk_pool, not both of them")
+    source_index = np.asarray(source_index, np.int64).reshape(-1)
+    score = _as_f32(score).reshape(-1)
+    perm = np.argsort(source_index, kind="stable")                                         # :31-33
+    sorted_source, sorted_score = source_index[perm], score[perm]
+    counts = np.bincount(sorted_source)                                                    # :38 segment_sum(ones)
+    before = np.concatenate([[0], np.cumsum(counts)[:-1]])                                 # :46-49
+    out = []
+    for s in range(len(counts)):
+        cnt = int(counts[s])
+        seg = sorted_score[before[s]:before[s] + cnt]
+        order = np.argsort(-seg, kind="stable")                                            # :58 DESCENDING
+        node_k = min(int(k), cnt) if k is not None else int(np.ceil(F32(cnt) * F32(ratio)))  # :60-68 (float32)
+        out.append(before[s] + order[:node_k])
+    topk = np.concatenate(out).astype(np.int64) if out else np.zeros(0, np.int64)
+    return perm[topk].astype(I32)                                                          # :87
+
+
+def sample_new_graph_by_node_index(x, edge_index, edge_weight, sampled_node_index, node_graph_index=None, y=None):
+    """data/graph.py:276-359: (x, edge_index, edge_weight, node_graph_index, y) of the induced subgraph; nodes are
+    relabelled by their position in sampled_node_index, edges keep their order."""
+    idx = np.asarray(sampled_node_index, np.int64).reshape(-1)
+    edge_index = np.asarray(edge_index, I32)
+    n_ids = max(int(edge_index.max()) if edge_index.size else 0, int(idx.max()) if idx.size else 0) + 1
+    reverse = -np.ones(n_ids, np.int64)
+    reverse[idx] = np.arange(len(idx))
+    mask = (reverse[edge_index[0]] >= 0) & (reverse[edge_index[1]] >= 0)
+    new_ei = np.stack([reverse[edge_index[0][mask]], reverse[edge_index[1][mask]]]).astype(I32)
+    return (np.asarray(x)[idx], new_ei, None if edge_weight is None else np.asarray(edge_weight)[mask],
+            None if node_graph_index is None else np.asarray(node_graph_index)[idx], None if y is None else np.asarray(y)[idx])
+
+
+def sag_pool(x, edge_index, edge_weight, node_graph_index, score_gnn, k=None, ratio=None, score_activation=None):
+    """nn/pool/sag_pool.py:7-47."""
+    x = _as_f32(x)
+    node_score = _as_f32(score_gnn([x, edge_index, edge_weight]))
+    topk_node_index = topk_pool(node_graph_index, node_score, k=k, ratio=ratio)
+    if score_activation is not None:
+        node_score = score_activation(node_score)
+    px, pei, pw, pgi, _ = sample_new_graph_by_node_index((x * node_score).astype(F32), edge_index, edge_weight, topk_node_index,
+                                                         node_graph_index)
+    return px, pei, pw, pgi
+
+
+def numpy_lstm(kernel, recurrent_kernel, bias):
+    """A plain LSTM (gate order i, f, c, o; sigmoid gates, tanh cell - tf.keras.layers.LSTM's defaults) with the Keras
+    calling convention, used as the `lstm` ARGUMENT of set2set in the tests and the golden generator."""
+    kernel, recurrent_kernel, bias = _as_f32(kernel), _as_f32(recurrent_kernel), _as_f32(bias)
+    units = recurrent_kernel.shape[0]
+
+    def sigmoid(v):
+        return (F32(1) / (F32(1) + np.exp(-v))).astype(F32)
+
+    def lstm(inputs, initial_state=None, training=None):
+        inputs = _as_f32(inputs)
+        h, c = _as_f32(initial_state[0]), _as_f32(initial_state[1])
+        seq = []
+        for t in range(inputs.shape[1]):
+            z = (inputs[:, t] @ kernel + h @ recurrent_kernel + bias).astype(F32)
+            i, f, g, o = (z[:, j * units:(j + 1) * units] for j in range(4))
+            c = (sigmoid(f) * c + sigmoid(i) * np.tanh(g)).astype(F32)
+            h = (sigmoid(o) * np.tanh(c)).astype(F32)
+            seq.append(h)
+        return np.stack(seq, axis=1).astype(F32), h, c
+    return lstm

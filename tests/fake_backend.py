@@ -96,9 +96,12 @@ def install(monkeypatch):
         return _t(c_oracle.segment_softmax(_np(score), ids, csr.n_rows))
 
     def gat_fused(csr, Q, K, V, num_heads, split_value_heads=True, bias=None, act=0, return_attention=False,
-                  att_buffer=None, out=None):
+                  att_buffer=None, out=None, scale=None):
         ids = np.repeat(np.arange(csr.n_rows), np.diff(_np(csr.rowptr))).astype(np.int32)
-        res, att = c_oracle.gat_core(ids, _np(csr.col), _np(Q), _np(K), _np(V), num_heads, split_value_heads, True)
+        q = _np(Q)
+        if scale is not None:       # the C restatement divides by sqrt(dqk); fold the requested divisor into Q
+            q = (q * np.float32(np.sqrt(np.float32(q.shape[1] // num_heads)) / np.float32(scale))).astype(np.float32)
+        res, att = c_oracle.gat_core(ids, _np(csr.col), q, _np(K), _np(V), num_heads, split_value_heads, True)
         if bias is not None:
             res = res + _np(bias)
         if act == ops.ACT_RELU:
@@ -168,11 +171,23 @@ def install(monkeypatch):
         return _t(_np(src)[_np(index)])
 
     def neighbor_sample(csr, k=None, ratio=None, padding=False, seed=0, rng_stream=1):
+        if not isinstance(padding, bool) and padding == ops.SAMPLE_HEAD:
+            padding = "head"
         r, p, rp = o.neighbor_sample_csr(_np(csr.rowptr), k, ratio, padding, seed, rng_stream)
         return _t(r), _t(p.astype(np.int32)), _t(rp)
 
+    def sort_keys_f32(score, descending=False):
+        u = (_np(score) + np.float32(0)).view(np.uint32)
+        u = np.where(u & np.uint32(0x80000000), ~u, u | np.uint32(0x80000000)).astype(np.uint32)
+        return _t((~u if descending else u).view(np.int32))
+
+    def stable_argsort(keys, key_bits=32):
+        mask = np.uint32(0xFFFFFFFF >> (32 - key_bits))
+        return _t(np.argsort(_np(keys).view(np.uint32) & mask, kind="stable").astype(np.int32))
+
     for name, fn in dict(dropout=dropout, spmm_heads=spmm_heads, gat_softmax_bwd=gat_softmax_bwd, edge_flags=edge_flags,
-                         select_flagged=select_flagged, gather_i32=gather_i32, neighbor_sample=neighbor_sample).items():
+                         select_flagged=select_flagged, gather_i32=gather_i32, neighbor_sample=neighbor_sample,
+                         sort_keys_f32=sort_keys_f32, stable_argsort=stable_argsort).items():
         monkeypatch.setattr(ops, name, fn)
 
     from tf_geometric_b200.utils import graph_utils as gu

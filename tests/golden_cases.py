@@ -50,6 +50,9 @@ class OracleApi(object):
     def neighbor_sample(self, ei, w, **kw):
         return self.o.random_neighbor_sample(ei, w, seed=1, **kw)
 
+    def lstm(self, kernel, recurrent_kernel, bias):
+        return self.o.numpy_lstm(kernel, recurrent_kernel, bias)
+
 
 class ProductApi(object):
     exact_float = False
@@ -63,7 +66,7 @@ class ProductApi(object):
                      "mean_reducer", "max_reducer", "sum_updater", "identity_updater", "segment_softmax", "segment_count",
                      "gcn", "gat", "mean_graph_sage", "sum_graph_sage", "gcn_graph_sage", "mean_pool_graph_sage",
                      "max_pool_graph_sage", "appnp", "sgc", "ssgc", "tagcn", "gin", "le_conv", "mean_pool", "sum_pool",
-                     "max_pool", "min_pool", "chebynet", "chebynet_norm_edge"):
+                     "max_pool", "min_pool", "chebynet", "chebynet_norm_edge", "topk_pool", "set2set"):
             setattr(self, name, getattr(tfg.nn, name))
         for name in ("convert_edge_to_directed", "merge_duplicated_edge", "add_self_loop_edge", "remove_self_loop_edge",
                      "adj_norm_edge"):
@@ -87,6 +90,24 @@ class ProductApi(object):
 
     def neighbor_sample(self, ei, w, **kw):
         return self.tfg.utils.RandomNeighborSampler(ei, w).sample(seed=1, **kw)
+
+    def lstm(self, kernel, recurrent_kernel, bias):
+        """The same LSTM cell as oracle.numpy_lstm, on torch tensors (it is the caller-supplied ARGUMENT of set2set)."""
+        torch = self.torch
+        k, r, b = (self.arr(a) for a in (kernel, recurrent_kernel, bias))
+        units = r.shape[0]
+
+        def lstm(inputs, initial_state=None, training=None):
+            h, c = initial_state
+            seq = []
+            for t in range(inputs.shape[1]):
+                z = inputs[:, t] @ k + h @ r + b
+                i, f, g, o = (z[:, j * units:(j + 1) * units] for j in range(4))
+                c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+                h = torch.sigmoid(o) * torch.tanh(c)
+                seq.append(h)
+            return torch.stack(seq, dim=1), h, c
+        return lstm
 
 
 def replay(fname, data, api):
@@ -259,3 +280,16 @@ def _replay_sampler(d, api):
         si, _ = api.neighbor_sample(ei, w, **kw)
         rows = O(si)[0]
         _eq(np.bincount(rows, minlength=int(rows.max()) + 1), d[tag + "_counts"], "sampler counts " + tag)
+
+
+def _replay_pool2(d, api):
+    """topk_pool (integer output: bit-exact) and set2set with a caller-supplied LSTM."""
+    A, O = api.arr, api.out
+    gi, score = A(d["gi"]), A(d["score"])
+    for tag, kw in (("k1", {"k": 1}), ("k5", {"k": 5}), ("k1000", {"k": 1000}), ("r30", {"ratio": 0.3}), ("r100", {"ratio": 1.0})):
+        _eq(O(api.topk_pool(gi, score, **kw)), d["topk_" + tag], "topk_pool " + tag)
+    _eq(O(api.topk_pool(gi, A(d["score"].reshape(-1, 1)), ratio=0.5)), d["topk_col_r50"], "topk_pool column scores")
+    lstm = api.lstm(d["lstm_k"], d["lstm_r"], d["lstm_b"])
+    tol = dict(rtol=1e-6, atol_scale=1e-6) if api.exact_float else dict(rtol=1e-4, atol_scale=1e-4)
+    _close(O(api.set2set(A(d["x"]), A(d["gi_sorted"]), lstm, 3)), d["set2set_it3"], "set2set 3 iterations", **tol)
+    _close(O(api.set2set(A(d["x"]), gi, lstm, 2)), d["set2set_unsorted_it2"], "set2set unsorted graph ids", **tol)

@@ -1,0 +1,158 @@
+# coding=utf-8
+"""GPU parity for the pooling family beyond the plain segment reductions: radix argsort building
+blocks, topk_pool, set2set (attention read-out on the fused kernel), induced subgraphs / BatchGraph and sag_pool.
+Integer outputs are compared bit for bit with the oracle; the reference's own outputs are in
+tests/golden/ref_exec_pool2.npz (replayed by test_gpu_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+import tf_geometric_b200 as tfg
+from tf_geometric_b200 import ops
+from oracle import tfg_oracle as o
+from conftest import random_graph, assert_close, glorot
+import golden_cases
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a, dtype=None):
+    return ops.as_device(a, dtype)
+
+
+def host(t):
+    return t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
+
+
+def test_sort_keys_and_stable_argsort():
+    rs = np.random.RandomState(0)
+    x = np.concatenate([rs.randn(20000), [0.0, -0.0, np.inf, -np.inf, 1e-45, -1e-45, 3.5, 3.5, 3.5],
+                        np.round(rs.randn(5000), 1)]).astype(np.float32)
+    x = x[rs.permutation(len(x))]
+    for descending in (False, True):
+        perm = host(ops.stable_argsort(ops.sort_keys_f32(dev(x), descending=descending)))
+        want = np.argsort(-(x + np.float32(0)) if descending else x + np.float32(0), kind="stable")
+        np.testing.assert_array_equal(perm, want)
+    keys = rs.randint(0, 1 << 16, 70000).astype(np.int32)
+    np.testing.assert_array_equal(host(ops.stable_argsort(dev(keys), key_bits=16)), np.argsort(keys, kind="stable"))
+    wide = rs.randint(-2 ** 31, 2 ** 31 - 1, 30000, dtype=np.int64).astype(np.int32)
+    np.testing.assert_array_equal(host(ops.stable_argsort(dev(wide))), np.argsort(wide.view(np.uint32), kind="stable"))
+    assert host(ops.stable_argsort(dev(np.zeros(0, np.int32)))).shape == (0,)
+
+
+@pytest.mark.parametrize("k,ratio", [(1, None), (7, None), (100000, None), (None, 0.25), (None, 0.5), (None, 1.0)])
+def test_topk_pool_matches_oracle(k, ratio):
+    rs = np.random.RandomState(5)
+    n, sources = 60000, 400
+    src = rs.randint(0, sources, n).astype(np.int32)
+    src[src == 17] = 18                                               # an empty source
+    src[:5] = sources - 1
+    score = np.round(rs.randn(n), 2).astype(np.float32)               # plenty of ties
+    got = host(tfg.nn.topk_pool(dev(src), dev(score), k=k, ratio=ratio))
+    want = o.topk_pool(src, score, k=k, ratio=ratio)
+    np.testing.assert_array_equal(got, want)
+    assert got.dtype == np.int32
+    sel_src = src[got]
+    assert (np.diff(sel_src) >= 0).all()                              # grouped by ascending source
+    same = np.diff(sel_src) == 0
+    assert (np.diff(score[got])[same] <= 0).all()                     # best score first inside a source
+    with pytest.raises(Exception):
+        tfg.nn.topk_pool(dev(src), dev(score))
+    with pytest.raises(Exception):
+        tfg.nn.topk_pool(dev(src), dev(score), k=1, ratio=0.5)
+
+
+@pytest.mark.parametrize("d,graphs,n", [(6, 9, 200), (64, 40, 5000), (128, 3, 9000)])
+def test_set2set_matches_oracle(d, graphs, n):
+    rs = np.random.RandomState(d)
+    gi = np.sort(rs.randint(0, graphs, n)).astype(np.int32)
+    gi[-1] = graphs - 1
+    if d == 128:
+        gi[: n * 2 // 3] = 0                                          # one graph with > 2048 nodes: a hub row
+        gi = np.sort(gi)
+    x = (rs.randn(n, d) * 0.5).astype(np.float32)
+    k, r, b = glorot(rs, 2 * d, 4 * d), glorot(rs, d, 4 * d), (rs.randn(4 * d) * 0.1).astype(np.float32)
+    want = o.set2set(x, gi, o.numpy_lstm(k, r, b), 3)
+    api = golden_cases.ProductApi()
+    got = tfg.nn.set2set(dev(x), dev(gi), api.lstm(k, r, b), 3)
+    assert_close(host(got), want, what="set2set d={}".format(d))
+    layer = tfg.layers.Set2Set(num_iterations=2)
+    out = layer([dev(x), dev(gi)])
+    assert tuple(out.shape) == (graphs, 2 * d)
+    np.testing.assert_array_equal(host(layer([dev(x), dev(gi)])), host(out))
+
+
+def test_induced_subgraph_and_batch_graph():
+    rs = np.random.RandomState(9)
+    n = 3000
+    ei = random_graph(n, 40000, seed=10)
+    w = rs.rand(ei.shape[1]).astype(np.float32)
+    x = rs.randn(n, 5).astype(np.float32)
+    y = rs.randint(0, 7, n)
+    gi = np.sort(rs.randint(0, 12, n)).astype(np.int32)
+    keep = rs.permutation(n)[:1100].astype(np.int32)
+    wx, wei, ww, wgi, wy = o.sample_new_graph_by_node_index(x, ei, w, keep, gi, y)
+    batch = tfg.BatchGraph(x, ei, gi, None, y=y, edge_weight=w)
+    for g, on_device in ((batch.to_device(), True), (batch, False)):
+        sub = g.sample_new_graph_by_node_index(dev(keep) if on_device else keep)
+        assert isinstance(sub, tfg.BatchGraph) and torch.is_tensor(sub.edge_index) == on_device
+        np.testing.assert_array_equal(host(sub.x), wx)
+        np.testing.assert_array_equal(host(sub.edge_index), wei)
+        np.testing.assert_array_equal(host(sub.edge_weight), ww)
+        np.testing.assert_array_equal(host(sub.node_graph_index), wgi)
+        np.testing.assert_array_equal(host(sub.y), wy)
+    plain = tfg.Graph(x, ei, edge_weight=w).to_device().sample_new_graph_by_node_index(dev(keep))
+    assert type(plain) is tfg.Graph
+    np.testing.assert_array_equal(host(plain.edge_index), wei)
+
+    # from_graphs / to_graphs round trip on the device, with an interleaved (unsorted) batch in between
+    parts = []
+    for i, size in enumerate((5, 1, 9, 4)):
+        pe = random_graph(size, 3 * size, seed=20 + i) if size > 1 else np.zeros((2, 0), np.int32)
+        parts.append(tfg.Graph(rs.randn(size, 3).astype(np.float32), pe, y=np.arange(size) + 100 * i,
+                               edge_weight=rs.rand(pe.shape[1]).astype(np.float32)).to_device())
+    bg = tfg.BatchGraph.from_graphs(parts)
+    assert bg.num_graphs == 4 and bg.num_nodes == 19
+    np.testing.assert_array_equal(host(bg.node_graph_index), np.repeat(np.arange(4), [5, 1, 9, 4]))
+    shuffle_n, shuffle_e = rs.permutation(bg.num_nodes), rs.permutation(bg.num_edges)
+    inv = np.empty_like(shuffle_n)
+    inv[shuffle_n] = np.arange(len(shuffle_n))
+    mixed = tfg.BatchGraph(host(bg.x)[shuffle_n], inv[host(bg.edge_index)[:, shuffle_e]],
+                           host(bg.node_graph_index)[shuffle_n], host(bg.edge_graph_index)[shuffle_e],
+                           y=host(bg.y)[shuffle_n], edge_weight=host(bg.edge_weight)[shuffle_e]).to_device()
+    ordered = mixed.reorder()
+    assert (np.diff(host(ordered.node_graph_index)) >= 0).all() and (np.diff(host(ordered.edge_graph_index)) >= 0).all()
+    back = bg.to_graphs()
+    for a, b_ in zip(parts, back):
+        np.testing.assert_array_equal(host(a.x), host(b_.x))
+        np.testing.assert_array_equal(host(a.edge_index), host(b_.edge_index))
+        np.testing.assert_array_equal(host(a.edge_weight), host(b_.edge_weight))
+        np.testing.assert_array_equal(host(a.y), host(b_.y))
+
+
+@pytest.mark.parametrize("k,ratio", [(3, None), (None, 0.4)])
+def test_sag_pool_matches_oracle(k, ratio):
+    rs = np.random.RandomState(31)
+    n, graphs = 1500, 25
+    ei = random_graph(n, 12000, seed=32, symmetric=True)
+    w = (rs.rand(ei.shape[1]) + 0.1).astype(np.float32)
+    x = rs.randn(n, 8).astype(np.float32)
+    gi = np.sort(rs.randint(0, graphs, n)).astype(np.int32)
+    gi[-1] = graphs - 1
+    score_gnn = tfg.layers.GCN(1, seed=3)
+    xd, eid, wd, gid = dev(x), dev(ei, torch.int32), dev(w), dev(gi)
+    px, pei, pw, pgi = tfg.nn.sag_pool(xd, eid, wd, gid, score_gnn, k=k, ratio=ratio, score_activation=torch.tanh)
+    scores = host(score_gnn([xd, eid, wd]))                             # feed the SAME scores to the oracle
+    wx, wei, ww, wgi = o.sag_pool(x, ei, w, gi, lambda inputs: scores, k=k, ratio=ratio, score_activation=np.tanh)
+    np.testing.assert_array_equal(host(pei), wei)
+    np.testing.assert_array_equal(host(pgi), wgi)
+    np.testing.assert_array_equal(host(pw), ww)
+    assert_close(host(px), wx, rtol=1e-6, atol_scale=1e-6, what="pooled x")
+    layer = tfg.layers.SAGPool(score_gnn, k=k, ratio=ratio, score_activation=torch.tanh)
+    lx, lei, lw, lgi = layer([xd, eid, wd, gid])
+    np.testing.assert_array_equal(host(lei), wei)
+    np.testing.assert_array_equal(host(lx), host(px))
+    pooled = tfg.layers.MaxPool()([lx, lgi])
+    assert tuple(pooled.shape) == (graphs, 8)
+    np.testing.assert_array_equal(host(pooled), host(tfg.nn.max_pool(lx, lgi)))
+    np.testing.assert_array_equal(host(tfg.layers.MeanPool()([lx, lgi, graphs])), host(tfg.nn.mean_pool(lx, lgi, graphs)))

@@ -13,6 +13,7 @@ import test_gpu_spmm
 import test_gpu_gat
 import test_gpu_models
 import test_gpu_train
+import test_gpu_pool2
 
 
 @pytest.fixture
@@ -129,3 +130,15 @@ def test_training_extras_and_samplers(fake):
 
 def test_gat_layer_trains_on_the_fake_backend(fake):
     test_gpu_train.test_gat_layer_learns()
+
+
+def test_pooling_family_on_the_fake_backend(fake):
+    import golden_cases
+    test_gpu_pool2.test_sort_keys_and_stable_argsort()
+    test_gpu_pool2.test_topk_pool_matches_oracle(7, None)
+    test_gpu_pool2.test_topk_pool_matches_oracle(None, 0.25)
+    test_gpu_pool2.test_set2set_matches_oracle(6, 9, 200)
+    test_gpu_pool2.test_induced_subgraph_and_batch_graph()
+    test_gpu_pool2.test_sag_pool_matches_oracle(3, None)
+    test_gpu_pool2.test_sag_pool_matches_oracle(None, 0.4)
+    golden_cases.replay("ref_exec_pool2.npz", np.load(test_gpu_train.GOLDEN + "/ref_exec_pool2.npz"), golden_cases.ProductApi())

@@ -12,7 +12,7 @@ Scope: the gather -> edge-apply -> segment-aggregate path under tfg.nn.gcn / gat
 works without a GPU, calling any operator does not (there is no CPU fallback).
 """
 from . import _ffi, ops, nn, layers, utils
-from .data.graph import Graph
+from .data.graph import Graph, BatchGraph
 from .sparse import SparseMatrix
 from ._rng import set_seed
 

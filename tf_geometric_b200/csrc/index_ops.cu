@@ -217,6 +217,16 @@ static int stable_sort_positions(const int32_t *keys, int64_t E, int64_t max_key
     return TFGK_OK;
 }
 
+// order-preserving 32-bit key of a float (IEEE trick: flip all bits of negatives, the sign bit of non-negatives);
+// -0.0 is folded into +0.0 first so that numerically equal scores tie.  descending = complement.
+__global__ void sort_keys_f32_kernel(const float *__restrict__ score, int64_t n, int descending, int32_t *__restrict__ keys) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t u = __float_as_uint(score[i] + 0.0f);
+        u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+        keys[i] = (int32_t)(descending ? ~u : u);
+    }
+}
+
 // ---- duplicate-edge detection (utils/graph_utils.py:67-125: hash = n*row+col, tf.unique first-occurrence order) ----------
 __global__ void gather2_i32_kernel(const int32_t *__restrict__ a, const int32_t *__restrict__ b,
                                    const int32_t *__restrict__ perm, int64_t E, int32_t *__restrict__ a_out,
@@ -466,6 +476,38 @@ int tfgk_csr_build(const int32_t *row, const int32_t *col, int64_t E, int32_t N_
     gather_i32_kernel<<<grid_for(E), 256, 0, st>>>(col, perm, E, col_sorted);
     TFGK_LAUNCH_CHECK();
     return TFGK_OK;
+}
+
+int tfgk_sort_keys_f32(const float *score, int64_t n, int descending, int32_t *keys, void *stream) {
+    TFGK_CHECK_ARG(n >= 0, "sort_keys: negative size");
+    if (n == 0) return TFGK_OK;
+    TFGK_CHECK_ARG(score && keys, "sort_keys: null pointer");
+    sort_keys_f32_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(score, n, descending, keys);
+    TFGK_LAUNCH_CHECK();
+    return TFGK_OK;
+}
+
+int tfgk_argsort_workspace_bytes(int64_t n, size_t *out_bytes) {
+    TFGK_CHECK_ARG(out_bytes != nullptr && n >= 0 && n < (1ll << 31), "argsort_workspace_bytes: bad argument");
+    *out_bytes = CsrWorkspace(n, 0).total;
+    return TFGK_OK;
+}
+
+int tfgk_stable_argsort_u32(const int32_t *keys, int64_t n, int key_bits, int32_t *perm_out,
+                            void *workspace, size_t workspace_bytes, void *stream) {
+    TFGK_CHECK_ARG(n >= 0 && n < (1ll << 31), "stable_argsort: need 0 <= n < 2^31");
+    TFGK_CHECK_ARG(key_bits >= 1 && key_bits <= 32, "stable_argsort: key_bits must be in [1, 32]");
+    if (n == 0) return TFGK_OK;
+    TFGK_CHECK_ARG(keys && perm_out, "stable_argsort: null pointer");
+    const CsrWorkspace L(n, 0);
+    if (workspace == nullptr || workspace_bytes < L.total)
+        return set_error(TFGK_ERR_WORKSPACE, "stable_argsort: workspace too small (%zu < %zu bytes)", workspace_bytes, L.total);
+    char *ws = static_cast<char *>(workspace);
+    // every pass looks at one byte of the bit pattern, so 4 passes order all 32 bits as an unsigned number
+    return stable_sort_positions(keys, n, 1ll << (key_bits > 31 ? 31 : key_bits), perm_out,
+                                 reinterpret_cast<int32_t *>(ws + L.off_keys_a), reinterpret_cast<int32_t *>(ws + L.off_keys_b),
+                                 reinterpret_cast<int32_t *>(ws + L.off_vals_b), reinterpret_cast<uint32_t *>(ws + L.off_hist),
+                                 ws + L.off_sums, L.nblk, as_stream(stream));
 }
 
 int tfgk_edge_unique_workspace_bytes(int64_t E, int32_t N, size_t *out_bytes) {

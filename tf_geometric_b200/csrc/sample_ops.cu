@@ -36,6 +36,12 @@ enum { kSampleAll = 0, kSampleReplace = 1, kSampleReservoir = 2 };
 // how many neighbours row r contributes and by which rule (graph_utils.py:741-756)
 __device__ __forceinline__ int sample_rule(int deg, int k, double ratio, int padding, int &num) {
     if (deg == 0) { num = 0; return kSampleAll; }
+    if (padding == TFGK_SAMPLE_HEAD) {              // topk_pool.py:59-67: the first node_k entries of the row, in order
+        num = ratio < 0.0 ? (k < deg ? k : deg) : (int)ceilf((float)deg * (float)ratio);
+        if (num > deg) num = deg;
+        if (num < 0) num = 0;
+        return kSampleAll;
+    }
     if ((k < 0 && ratio < 0.0) || (ratio < 0.0 && !padding && k >= deg)) { num = deg; return kSampleAll; }
     if (ratio < 0.0) { num = k; return (padding && k >= deg) ? kSampleReplace : kSampleReservoir; }
     num = (int)ceil((double)deg * ratio);
@@ -148,11 +154,18 @@ static int check_sample_args(const char *fn, int32_t n_rows, int32_t k, double r
     return TFGK_OK;
 }
 
+static int check_sample_mode(const char *fn, int32_t k, double ratio, int padding) {
+    TFGK_CHECK_ARG(padding == 0 || padding == 1 || padding == TFGK_SAMPLE_HEAD, "%s: unknown padding mode %d", fn, padding);
+    TFGK_CHECK_ARG(padding != TFGK_SAMPLE_HEAD || k >= 0 || ratio >= 0.0, "%s: the head rule needs k or ratio", fn);
+    return TFGK_OK;
+}
+
 int tfgk_neighbor_sample_count(const int64_t *rowptr, int32_t n_rows, int32_t k, double ratio, int padding,
                                int64_t *out_rowptr, int64_t *total_host, void *workspace, size_t workspace_bytes,
                                void *stream) {
     int rc = check_sample_args("neighbor_sample_count", n_rows, k, ratio);
     if (rc != TFGK_OK) return rc;
+    if ((rc = check_sample_mode("neighbor_sample_count", k, ratio, padding)) != TFGK_OK) return rc;
     TFGK_CHECK_ARG(total_host != nullptr && out_rowptr != nullptr, "neighbor_sample_count: null pointer");
     *total_host = 0;
     cudaStream_t st = as_stream(stream);
@@ -181,8 +194,9 @@ int tfgk_neighbor_sample_count(const int64_t *rowptr, int32_t n_rows, int32_t k,
 int tfgk_neighbor_sample_fill(const int64_t *rowptr, int32_t n_rows, int32_t k, double ratio, int padding,
                               uint64_t seed, uint32_t rng_stream, const int64_t *out_rowptr,
                               int32_t *out_row, int32_t *out_pos, void *stream) {
-    const int rc = check_sample_args("neighbor_sample_fill", n_rows, k, ratio);
+    int rc = check_sample_args("neighbor_sample_fill", n_rows, k, ratio);
     if (rc != TFGK_OK) return rc;
+    if ((rc = check_sample_mode("neighbor_sample_fill", k, ratio, padding)) != TFGK_OK) return rc;
     if (n_rows == 0) return TFGK_OK;
     TFGK_CHECK_ARG(rowptr && out_rowptr, "neighbor_sample_fill: null pointer");
     sample_fill_kernel<<<(unsigned)ceil_div64(n_rows, 128), 128, 0, as_stream(stream)>>>(rowptr, n_rows, k, ratio, padding, seed,

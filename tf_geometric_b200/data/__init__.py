@@ -1,2 +1,2 @@
 # coding=utf-8
-from .graph import Graph
+from .graph import Graph, BatchGraph

@@ -1,7 +1,8 @@
 # coding=utf-8
 """Graph container with the reference's surface (data/graph.py:20-359 of tf_geometric): x, edge_index (int32 [2,E]),
-edge_weight (float32, ones by default), y, `cache` dict, adj(), to_directed().  BatchGraph / HeteroGraph are out
-of scope.  Data may be numpy (kept as numpy, like the reference) or torch tensors; the kernels
+edge_weight (float32, ones by default), y, `cache` dict, adj(), to_directed(), sample_new_graph_by_node_index(), and
+BatchGraph (data/graph.py:362-621; what the pooling layers need).  HeteroGraph is out of scope.
+Data may be numpy (kept as numpy, like the reference) or torch tensors; the kernels
 receive CUDA tensors - call `to_device()` (the analogue of `convert_data_to_tensor`) once to avoid per-call copies.
 """
 import types
@@ -134,3 +135,154 @@ class Graph(object):
 
     def convert_edge_to_directed(self, merge_mode="sum"):
         return self.to_directed(merge_mode=merge_mode, inplace=True)
+
+    def sample_new_graph_by_node_index(self, sampled_node_index):
+        """The subgraph induced by `sampled_node_index`, nodes relabelled by their position in that list, edge order
+        kept (reference :276-359).  Device data: Bernoulli-free edge flags + stable compaction + gathers
+        (tfgk_edge_flags_i32 / tfgk_select_flagged_i32); numpy data: numpy, like the reference's eager path."""
+        is_batch = isinstance(self, BatchGraph)
+        on_device = torch.is_tensor(self.edge_index) or torch.is_tensor(self.x)
+        if on_device:
+            dev = self.edge_index.device if torch.is_tensor(self.edge_index) else self.x.device
+            idx = ops.as_device(sampled_node_index, torch.int32, device=dev).reshape(-1)
+            take = lambda d: None if d is None else _take_rows(ops.as_device(d, device=dev), idx)      # noqa: E731
+        else:
+            idx = np.asarray(sampled_node_index).reshape(-1)
+            take = lambda d: None if d is None else np.asarray(d)[idx]                                  # noqa: E731
+        x, y = take(self.x), take(self.y)
+        node_graph_index = take(self.node_graph_index) if is_batch else None
+        edge_index, edge_weight = self.edge_index, self.edge_weight
+        edge_graph_index = self.edge_graph_index if is_batch else None
+        if edge_index is not None and self.num_edges > 0:
+            if on_device:
+                ei = ops.as_device(edge_index, torch.int32, device=dev)
+                row, col = ei[0].contiguous(), ei[1].contiguous()
+                n_ids = max(int(ei.max().item()), int(idx.max().item()) if idx.numel() else 0) + 1
+                reverse = torch.full((n_ids,), -1, dtype=torch.int32, device=dev)
+                reverse[idx.long()] = torch.arange(idx.numel(), dtype=torch.int32, device=dev)
+                kept = ops.select_flagged(ops.edge_flags(row, col, row.numel(), mode=ops.FLAG_MAPPED, row_map=reverse,
+                                                         col_map=reverse))
+                edge_index = torch.stack([ops.gather_i32(reverse, ops.gather_i32(row, kept)),
+                                          ops.gather_i32(reverse, ops.gather_i32(col, kept))])
+                by_edge = lambda d: None if d is None else _take_rows(ops.as_device(d, device=dev), kept)  # noqa: E731
+            else:
+                ei = np.asarray(edge_index)
+                n_ids = max(int(ei.max()), int(idx.max()) if idx.size else 0) + 1
+                reverse = -np.ones(n_ids, np.int32)
+                reverse[idx] = np.arange(idx.size, dtype=np.int32)
+                mask = (reverse[ei[0]] >= 0) & (reverse[ei[1]] >= 0)
+                edge_index = np.stack([reverse[ei[0][mask]], reverse[ei[1][mask]]]).astype(np.int32)
+                by_edge = lambda d: None if d is None else np.asarray(d)[mask]                           # noqa: E731
+            edge_weight, edge_graph_index = by_edge(edge_weight), by_edge(edge_graph_index)
+        if is_batch:
+            return BatchGraph(x=x, edge_index=edge_index, node_graph_index=node_graph_index,
+                              edge_graph_index=edge_graph_index, y=y, edge_weight=edge_weight)
+        return Graph(x=x, edge_index=edge_index, y=y, edge_weight=edge_weight)
+
+
+def _take_rows(data, index):
+    """data[index] along axis 0 on the device: float32 / int32 through the gather kernel, other dtypes through torch."""
+    if data.dtype == torch.float32 and data.dim() <= 2 and data.is_contiguous():
+        return ops.permute(data, index)
+    if data.dtype == torch.int32 and data.dim() == 1 and data.is_contiguous():
+        return ops.gather_i32(data, index)
+    return data.index_select(0, index.long())
+
+
+class BatchGraph(Graph):
+    """A batch of graphs stored as one graph: every node carries the id of its graph (`node_graph_index`), every edge
+    optionally too (`edge_graph_index`); reference data/graph.py:362-621."""
+
+    def __init__(self, x, edge_index, node_graph_index, edge_graph_index, y=None, edge_weight=None, graphs=None):
+        super().__init__(x, edge_index, y, edge_weight)
+        self.node_graph_index = node_graph_index
+        self.edge_graph_index = edge_graph_index
+        self.graphs = graphs
+
+    @property
+    def num_graphs(self):
+        gi = self.node_graph_index
+        return int(gi.max().item() if torch.is_tensor(gi) else np.max(gi)) + 1
+
+    def to_device(self, device=None, inplace=False):
+        dev = device if device is not None else ops.default_device()
+        base = Graph.to_device(self, device=dev, inplace=inplace)
+        g = self if inplace else BatchGraph(base._x, base.edge_index, self.node_graph_index, self.edge_graph_index, y=base.y,
+                                            edge_weight=base.edge_weight, graphs=self.graphs)
+        g.node_graph_index = ops.as_device(g.node_graph_index, torch.int32, device=dev)
+        if g.edge_graph_index is not None:
+            g.edge_graph_index = ops.as_device(g.edge_graph_index, torch.int32, device=dev)
+        return g
+
+    convert_data_to_tensor = to_device
+
+    def reorder(self):
+        """Nodes and edges sorted by graph id (reference :396-415), stable; device data uses the radix argsort."""
+        def order_of(ids):
+            if torch.is_tensor(ids):
+                return ops.stable_argsort(ops.as_device(ids, torch.int32)), True
+            return np.argsort(np.asarray(ids), kind="stable"), False
+
+        def take(d, order, dev_path):
+            if d is None:
+                return None
+            if dev_path:
+                return _take_rows(ops.as_device(d, device=order.device), order)
+            return np.asarray(d)[order]
+
+        n_order, n_dev = order_of(self.node_graph_index)
+        e_order, e_dev = order_of(self.edge_graph_index)
+        if e_dev:
+            ei = ops.as_device(self.edge_index, torch.int32, device=e_order.device)
+            edge_index = torch.stack([ops.gather_i32(ei[0].contiguous(), e_order), ops.gather_i32(ei[1].contiguous(), e_order)])
+        else:
+            edge_index = np.asarray(self.edge_index)[:, e_order]
+        return BatchGraph(take(self.x, n_order, n_dev), edge_index, take(self.node_graph_index, n_order, n_dev),
+                          take(self.edge_graph_index, e_order, e_dev), y=take(self.y, n_order, n_dev),
+                          edge_weight=take(self.edge_weight, e_order, e_dev))
+
+    def to_graphs(self):
+        """Split back into Graph objects (reference :417-461); offsets come from the per-graph node / edge counts."""
+        batch = self.reorder()
+        num_graphs = batch.num_graphs
+
+        def offsets(ids, n):
+            if torch.is_tensor(ids):
+                counts = ops.segment_count(ops.as_device(ids, torch.int32), num_graphs).cpu().numpy()
+            else:
+                counts = np.bincount(np.asarray(ids), minlength=num_graphs)
+            return np.concatenate([[0], np.cumsum(counts)]).astype(np.int64).tolist()
+
+        node_off = offsets(batch.node_graph_index, batch.num_nodes)
+        edge_off = offsets(batch.edge_graph_index, batch.num_edges)
+        graphs = []
+        for i in range(num_graphs):
+            n0, n1, e0, e1 = node_off[i], node_off[i + 1], edge_off[i], edge_off[i + 1]
+            graphs.append(Graph(x=batch.x[n0:n1], edge_index=batch.edge_index[:, e0:e1] - n0,
+                                y=None if batch.y is None else batch.y[n0:n1],
+                                edge_weight=None if batch.edge_weight is None else batch.edge_weight[e0:e1]))
+        return graphs
+
+    @classmethod
+    def from_graphs(cls, graphs):
+        """Concatenate graphs, shifting node ids by the number of nodes before each graph (reference :463-560)."""
+        on_device = torch.is_tensor(graphs[0].edge_index)
+        cat = (lambda xs, axis=0: torch.cat(list(xs), dim=axis)) if on_device else \
+            (lambda xs, axis=0: np.concatenate(list(xs), axis=axis))
+
+        def full(n, v):
+            if on_device:
+                return torch.full((n,), v, dtype=torch.int32, device=graphs[0].edge_index.device)
+            return np.full([n], v, dtype=np.int32)
+
+        node_graph_index = cat(full(g.num_nodes, i) for i, g in enumerate(graphs))
+        edge_graph_index = cat(full(g.num_edges, i) for i, g in enumerate(graphs))
+        shifted, before = [], 0
+        for g in graphs:
+            shifted.append(g.edge_index + before)
+            before += g.num_nodes
+        x = cat(g.x for g in graphs)
+        y = None if graphs[0].y is None else cat(g.y for g in graphs)
+        edge_weight = None if graphs[0].edge_weight is None else cat(g.edge_weight for g in graphs)
+        return BatchGraph(x=x, edge_index=cat(shifted, axis=1), node_graph_index=node_graph_index,
+                          edge_graph_index=edge_graph_index, graphs=graphs, y=y, edge_weight=edge_weight)

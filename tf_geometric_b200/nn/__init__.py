@@ -12,5 +12,8 @@ from .conv.appnp import appnp
 from .conv.propagation import (sgc, ssgc, tagcn, gin, gin_updater, le_conv, chebynet, chebynet_norm_edge,
                                get_laplacian)
 from .pool.common_pool import mean_pool, sum_pool, max_pool, min_pool
+from .pool.set2set import set2set
+from .pool.topk_pool import topk_pool
+from .pool.sag_pool import sag_pool
 from ..ops import relu
 from .sampling.drop_edge import drop_edge

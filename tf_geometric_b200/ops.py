@@ -12,7 +12,7 @@ import torch
 from . import _ffi
 from ._ffi import (REDUCE_SUM, REDUCE_MEAN, REDUCE_MAX, ACT_NONE, ACT_RELU, POW_INV_SQRT, POW_INV,  # noqa: F401
                    HEADS_SPLIT, HEADS_BROADCAST, HEADS_REDUCE, FLAG_ALL, FLAG_UPPER, FLAG_MAPPED,
-                   BERNOULLI_NONE, BERNOULLI_DROPOUT, BERNOULLI_KEEP)
+                   BERNOULLI_NONE, BERNOULLI_DROPOUT, BERNOULLI_KEEP, SAMPLE_NO_PADDING, SAMPLE_PADDING, SAMPLE_HEAD)
 
 _REDUCE_CODES = {"sum": REDUCE_SUM, "mean": REDUCE_MEAN, "max": REDUCE_MAX}
 
@@ -294,7 +294,7 @@ def segment_softmax_csr(csr, score_csr):
 
 
 def gat_fused(csr, Q, K, V, num_heads, split_value_heads=True, bias=None, act=ACT_NONE, return_attention=False,
-              att_buffer=None, out=None):
+              att_buffer=None, out=None, scale=None):
     for t, n in ((Q, "Q"), (K, "K"), (V, "V")):
         if not (t.is_cuda and t.dtype == torch.float32):
             raise TypeError("{} must be a float32 CUDA tensor".format(n))
@@ -314,8 +314,8 @@ def gat_fused(csr, Q, K, V, num_heads, split_value_heads=True, bias=None, act=AC
         att = torch.empty((csr.nnz, H), dtype=torch.float32, device=Q.device)
     if bias is not None:
         _check(bias, torch.float32, "bias")
-    # gat.py:78  scale = sqrt(cast(shape(Q_)[-1], float32))
-    scale = float(np.sqrt(np.float32(dqk)))
+    # gat.py:78  scale = sqrt(cast(shape(Q_)[-1], float32)); set2set.py:37 uses raw dot products (scale = 1)
+    scale = float(np.sqrt(np.float32(dqk))) if scale is None else float(scale)
 
     plan = getattr(csr, "plan", None)
     plan_struct = plan.struct(VW + 64, Q.device) if plan is not None else None
@@ -429,24 +429,49 @@ def gather_i32(src, index):
     return permute(src.view(torch.float32), index).view(torch.int32)
 
 
+def sort_keys_f32(score, descending=False):
+    """Order-preserving int32 bit patterns of float32 scores (to be sorted as unsigned numbers)."""
+    _check(score, torch.float32, "score")
+    keys = torch.empty((score.numel(),), dtype=torch.int32, device=score.device)
+    _ffi.call("tfgk_sort_keys_f32", _p(score), score.numel(), 1 if descending else 0, _p(keys), _stream(score))
+    return keys
+
+
+def stable_argsort(keys, key_bits=32):
+    """Stable argsort of int32 bit patterns read as unsigned numbers (LSD radix, ceil(key_bits / 8) passes)."""
+    _check(keys, torch.int32, "keys")
+    n = keys.numel()
+    need = ctypes.c_size_t()
+    _ffi.call("tfgk_argsort_workspace_bytes", n, ctypes.byref(need))
+    ws = torch.empty((max(need.value, 1),), dtype=torch.uint8, device=keys.device)
+    perm = torch.empty((n,), dtype=torch.int32, device=keys.device)
+    _ffi.call("tfgk_stable_argsort_u32", _p(keys), n, int(key_bits), _p(perm), _p(ws), need.value, _stream(keys))
+    return perm
+
+
 def neighbor_sample(csr, k=None, ratio=None, padding=False, seed=0, rng_stream=RNG_STREAM_SAMPLER):
     """Fan-out sampling over the rows of `csr` (tfgk_neighbor_sample_*).  Returns (row int32 [S], pos int32 [S],
-    out_rowptr int64 [n_rows+1]): the row of every sampled edge and the CSR position it was drawn from."""
+    out_rowptr int64 [n_rows+1]): the row of every sampled edge and the CSR position it was drawn from.
+    padding: False | True | SAMPLE_HEAD (deterministic: the first k / ceil(degree*ratio) entries of every row)."""
     dev = csr.rowptr.device
     kk = -1 if k is None else int(k)
     rr = -1.0 if ratio is None else float(ratio)
+    if padding == "head" or (not isinstance(padding, bool) and padding == SAMPLE_HEAD):
+        padding = SAMPLE_HEAD
+    else:
+        padding = SAMPLE_PADDING if padding else SAMPLE_NO_PADDING
     need = ctypes.c_size_t()
     _ffi.call("tfgk_neighbor_sample_workspace_bytes", csr.n_rows, ctypes.byref(need))
     ws = torch.empty((max(need.value, 1),), dtype=torch.uint8, device=dev)
     out_rowptr = torch.empty((csr.n_rows + 1,), dtype=torch.int64, device=dev)
     total = ctypes.c_int64()
-    _ffi.call("tfgk_neighbor_sample_count", _p(csr.rowptr), csr.n_rows, kk, rr, 1 if padding else 0, _p(out_rowptr),
+    _ffi.call("tfgk_neighbor_sample_count", _p(csr.rowptr), csr.n_rows, kk, rr, padding, _p(out_rowptr),
               ctypes.byref(total), _p(ws), need.value, _stream(out_rowptr))
     S = total.value
     out_row = torch.empty((S,), dtype=torch.int32, device=dev)
     out_pos = torch.empty((S,), dtype=torch.int32, device=dev)
     if S:
-        _ffi.call("tfgk_neighbor_sample_fill", _p(csr.rowptr), csr.n_rows, kk, rr, 1 if padding else 0, int(seed),
+        _ffi.call("tfgk_neighbor_sample_fill", _p(csr.rowptr), csr.n_rows, kk, rr, padding, int(seed),
                   int(rng_stream), _p(out_rowptr), _p(out_row), _p(out_pos), _stream(out_rowptr))
     return out_row, out_pos, out_rowptr
 

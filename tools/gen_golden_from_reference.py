@@ -257,6 +257,32 @@ def main():
         out[tag + "_counts"] = np.bincount(si[0], minlength=rows_out)
     save("sampler", **out)
 
+    # ---- pooling beyond the segment reductions: topk_pool, set2set (the LSTM is an ARGUMENT of the reference function) ---
+    topk_m = importlib.import_module("tf_geometric.nn.pool.topk_pool")
+    s2s_m = importlib.import_module("tf_geometric.nn.pool.set2set")
+    from oracle import tfg_oracle as oracle_mod
+    n, g, d = 180, 9, 6
+    gi = rs.randint(0, g, n).astype(np.int32)
+    gi[gi == 4] = 3                                            # graph 4 is empty
+    gi[:3] = g - 1                                             # the last graph exists
+    score = rs.randn(n).astype(np.float32)
+    out = {"gi": gi, "score": score}
+    for tag, kw in (("k1", {"k": 1}), ("k5", {"k": 5}), ("k1000", {"k": 1000}), ("r30", {"ratio": 0.3}), ("r100", {"ratio": 1.0})):
+        out["topk_" + tag] = topk_m.topk_pool(T(gi), T(score), **kw)
+    out["topk_col_r50"] = topk_m.topk_pool(T(gi), T(score.reshape(-1, 1)), ratio=0.5)
+    x = rs.randn(n, d).astype(np.float32)
+    gi_sorted = np.sort(gi)
+    lstm_k, lstm_r, lstm_b = glorot(rs, 2 * d, 4 * d), glorot(rs, d, 4 * d), (rs.randn(4 * d) * 0.1).astype(np.float32)
+    np_lstm = oracle_mod.numpy_lstm(lstm_k, lstm_r, lstm_b)
+
+    def shim_lstm(inputs, initial_state=None, training=None):
+        seq, h, c = np_lstm(np.asarray(inputs), [np.asarray(s) for s in initial_state], training)
+        return T(seq), T(h), T(c)
+    out.update(x=x, gi_sorted=gi_sorted, lstm_k=lstm_k, lstm_r=lstm_r, lstm_b=lstm_b)
+    out["set2set_it3"] = s2s_m.set2set(T(x), T(gi_sorted), shim_lstm, 3)
+    out["set2set_unsorted_it2"] = s2s_m.set2set(T(x), T(gi), shim_lstm, 2)
+    save("pool2", **out)
+
 
 if __name__ == "__main__":
     main()

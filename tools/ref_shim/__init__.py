@@ -64,6 +64,38 @@ def build_tensorflow():
     tf.reduce_mean = lambda x, axis=None: _red(np.mean, x, axis)
     tf.reduce_max = lambda x, axis=None: _red(np.max, x, axis)
     tf.reduce_any = lambda x, axis=None: bool(np.any(np.asarray(x)))
+    tf.reduce_min = lambda x, axis=None: _red(np.min, x, axis)
+    tf.squeeze = lambda x, axis=None: T(np.squeeze(np.asarray(x), axis=axis))
+    tf.minimum = lambda a, b: T(np.minimum(np.asarray(a), np.asarray(b)))
+    tf.greater_equal = lambda a, b: T(np.greater_equal(np.asarray(a), np.asarray(b)))
+    tf.logical_and = lambda a, b: T(np.logical_and(np.asarray(a), np.asarray(b)))
+    tf.gather_nd = lambda params, indices: T(np.asarray(params)[tuple(np.asarray(indices).T)])
+
+    def reduce_sum(x, axis=None, keepdims=False):
+        r = np.sum(np.asarray(x), axis=axis, keepdims=keepdims)
+        return T(r) if np.ndim(r) else r
+    tf.reduce_sum = reduce_sum
+
+    def argsort(values, axis=-1, direction="ASCENDING", stable=False):
+        v = np.asarray(values)
+        return T(np.argsort(-v if direction == "DESCENDING" else v, axis=axis, kind="stable").astype(np.int32))
+    tf.argsort = argsort
+
+    def tensor_scatter_nd_update(tensor, indices, updates):
+        out = np.array(np.asarray(tensor), copy=True)
+        out[tuple(np.asarray(indices).T)] = np.asarray(updates)
+        return T(out)
+    tf.tensor_scatter_nd_update = tensor_scatter_nd_update
+
+    def scatter_nd(indices, updates, shape):
+        out = np.zeros([int(s) for s in shape], dtype=np.asarray(updates).dtype)
+        np.add.at(out, tuple(np.asarray(indices).T), np.asarray(updates))
+        return T(out)
+    tf.scatter_nd = scatter_nd
+
+    def meshgrid(*xs, indexing="xy"):
+        return [T(a) for a in np.meshgrid(*[np.asarray(x) for x in xs], indexing=indexing)]
+    tf.meshgrid = meshgrid
 
     def gather(params, indices, axis=0):
         return T(_o.gather(np.asarray(params), np.asarray(indices)))
@@ -86,6 +118,10 @@ def build_tensorflow():
     math.sqrt = lambda x: (T(np.sqrt(np.asarray(x))) if np.ndim(x) else np.sqrt(np.float32(x)))
     math.floordiv = lambda a, b: T(np.asarray(a) // np.asarray(b))
     math.floormod = lambda a, b: T(np.asarray(a) % np.asarray(b))
+    math.segment_sum = lambda d, i: T(_o.unsorted_segment_sum(np.asarray(d), np.asarray(i), int(np.max(np.asarray(i))) + 1))
+    math.cumsum = lambda x, axis=0: T(np.cumsum(np.asarray(x), axis=axis))
+    math.minimum = lambda a, b: T(np.minimum(np.asarray(a), np.asarray(b)))
+    math.ceil = lambda x: T(np.ceil(np.asarray(x)))
     math.reduce_min = lambda x, axis=None: _red(np.min, x, axis)
     math.reduce_max = lambda x, axis=None: _red(np.max, x, axis)
     math.__getattr__ = lambda name: _unsupported("tf.math." + name)
