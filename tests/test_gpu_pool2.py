@@ -62,7 +62,7 @@ def test_topk_pool_matches_oracle(k, ratio):
         tfg.nn.topk_pool(dev(src), dev(score), k=1, ratio=0.5)
 
 
-@pytest.mark.parametrize("d,graphs,n", [(6, 9, 200), (64, 40, 5000), (128, 3, 9000)])
+@pytest.mark.parametrize("d,graphs,n", [(6, 9, 200), (64, 40, 5000), (64, 8, 4000), (128, 3, 9000)])
 def test_set2set_matches_oracle(d, graphs, n):
     rs = np.random.RandomState(d)
     gi = np.sort(rs.randint(0, graphs, n)).astype(np.int32)
@@ -156,3 +156,20 @@ def test_sag_pool_matches_oracle(k, ratio):
     assert tuple(pooled.shape) == (graphs, 8)
     np.testing.assert_array_equal(host(pooled), host(tfg.nn.max_pool(lx, lgi)))
     np.testing.assert_array_equal(host(tfg.layers.MeanPool()([lx, lgi, graphs])), host(tfg.nn.mean_pool(lx, lgi, graphs)))
+
+
+def test_pools_over_few_large_graphs_use_edge_sized_tasks():
+    """Average segment length >= 128: the work plan shrinks its tasks from 32 rows to ~512 entries (ops.build_plan);
+    per-graph sums stay sequential, so the results are still bit-exact."""
+    rs = np.random.RandomState(77)
+    n, graphs, d = 12000, 20, 24
+    gi = np.sort(rs.randint(0, graphs, n)).astype(np.int32)
+    gi[-1] = graphs - 1
+    x = rs.randn(n, d).astype(np.float32)
+    from tf_geometric_b200 import _structure
+    seg = _structure.csr_for_segment_ids(dev(gi), graphs)
+    if torch.cuda.is_available():
+        assert seg.plan is not None and seg.plan.n_hubs == 0 and seg.plan.n_tasks >= graphs
+    for name in ("mean_pool", "sum_pool", "max_pool", "min_pool"):
+        got = host(getattr(tfg.nn, name)(dev(x), dev(gi), graphs))
+        np.testing.assert_array_equal(got, getattr(o, name)(x, gi, graphs), err_msg=name)

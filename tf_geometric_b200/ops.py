@@ -156,14 +156,22 @@ def csr_build(row, col, n_rows, n_cols=None):
     return csr
 
 
+DENSE_ROW_DEGREE = 128   # average row length from which 32-row tasks starve the machine (few, long rows: pooling)
+TASK_EDGE_TARGET = 512   # ... and the edges one task should then hold
+
+
 def build_plan(csr):
-    """Work plan for graphs with hub rows (> HUB_THRESHOLD edges); None when there are none (the kernels then use their
-    implicit 32-row tasks, which is also the fastest path)."""
+    """Work plan: hub rows (> HUB_THRESHOLD edges) are cut into slices, and when the rows are few and long on average
+    (graph pooling, set2set: one row per graph) the tasks shrink from 32 rows to about TASK_EDGE_TARGET edges so that
+    there are enough warps to fill the GPU.  None when neither applies (the kernels then use their implicit 32-row
+    tasks, which is also the fastest path for ordinary graphs)."""
     if csr.nnz == 0 or csr.n_rows == 0:
         return None
+    avg = csr.nnz / float(csr.n_rows)
+    rows_per_task = ROWS_PER_TASK if avg < DENSE_ROW_DEGREE else max(1, min(ROWS_PER_TASK, int(TASK_EDGE_TARGET // avg)))
     dev = csr.rowptr.device
     cap_t, cap_h = ctypes.c_int64(), ctypes.c_int64()
-    _ffi.call("tfgk_plan_capacity", csr.nnz, csr.n_rows, HUB_THRESHOLD, HUB_CHUNK, ROWS_PER_TASK, ctypes.byref(cap_t),
+    _ffi.call("tfgk_plan_capacity", csr.nnz, csr.n_rows, HUB_THRESHOLD, HUB_CHUNK, rows_per_task, ctypes.byref(cap_t),
               ctypes.byref(cap_h))
     need = ctypes.c_size_t()
     _ffi.call("tfgk_plan_workspace_bytes", csr.n_rows, ctypes.byref(need))
@@ -172,12 +180,12 @@ def build_plan(csr):
     arrays.update({k: torch.empty((cap_t.value,), dtype=torch.int64, device=dev) for k in ("task_e0", "task_e1")})
     arrays.update({k: torch.empty((cap_h.value,), dtype=torch.int32, device=dev) for k in ("hub_row", "hub_slot0", "hub_nslots")})
     counts = (ctypes.c_int32 * 3)()
-    _ffi.call("tfgk_plan_build", _p(csr.rowptr), csr.n_rows, HUB_THRESHOLD, HUB_CHUNK, ROWS_PER_TASK,
+    _ffi.call("tfgk_plan_build", _p(csr.rowptr), csr.n_rows, HUB_THRESHOLD, HUB_CHUNK, rows_per_task,
               _p(arrays["task_row"]), _p(arrays["task_nrows"]), _p(arrays["task_e0"]), _p(arrays["task_e1"]),
               _p(arrays["task_slot"]), _p(arrays["hub_row"]), _p(arrays["hub_slot0"]), _p(arrays["hub_nslots"]),
               cap_t.value, cap_h.value, counts, _p(ws), need.value, _stream(csr.rowptr))
     n_tasks, n_hubs, n_slots = int(counts[0]), int(counts[1]), int(counts[2])
-    if n_hubs == 0:
+    if n_hubs == 0 and rows_per_task == ROWS_PER_TASK:
         return None
     arrays = {k: v[:(n_tasks if k.startswith("task") else n_hubs)].clone() for k, v in arrays.items()}
     return Plan(arrays, n_tasks, n_hubs, n_slots)
