@@ -173,3 +173,53 @@ def test_pools_over_few_large_graphs_use_edge_sized_tasks():
     for name in ("mean_pool", "sum_pool", "max_pool", "min_pool"):
         got = host(getattr(tfg.nn, name)(dev(x), dev(gi), graphs))
         np.testing.assert_array_equal(got, getattr(o, name)(x, gi, graphs), err_msg=name)
+
+
+def test_sort_pool_drop_edge_layer_and_map_reduce_layer():
+    rs = np.random.RandomState(55)
+    n, graphs = 2000, 30
+    ei = random_graph(n, 15000, seed=56, symmetric=True)
+    w = rs.rand(ei.shape[1]).astype(np.float32)
+    x = rs.randn(n, 6).astype(np.float32)
+    gi = np.sort(rs.randint(0, graphs, n)).astype(np.int32)
+    gi[-1] = graphs - 1
+    xd, eid, wd, gid = dev(x), dev(ei, torch.int32), dev(w), dev(gi)
+    # SortPool: rank by the last feature column
+    keep = o.topk_pool(gi, x[:, -1], k=10)
+    wx, wei, ww, wgi, _ = o.sample_new_graph_by_node_index(x, ei, w, keep, gi)
+    px, pei, pw, pgi = tfg.layers.SortPool(k=10)([xd, eid, wd, gid])
+    np.testing.assert_array_equal(host(px), wx)
+    np.testing.assert_array_equal(host(pei), wei)
+    np.testing.assert_array_equal(host(pw), ww)
+    np.testing.assert_array_equal(host(pgi), wgi)
+    keep = o.topk_pool(gi, x[:, 2], ratio=0.3)
+    px, pei, _, _ = tfg.nn.sort_pool(xd, eid, wd, gid, ratio=0.3, sort_index=2)
+    np.testing.assert_array_equal(host(px), x[keep])
+    np.testing.assert_array_equal(host(pei), o.sample_new_graph_by_node_index(x, ei, w, keep)[1])
+
+    # DropEdge layer
+    layer = tfg.layers.DropEdge(rate=0.4, force_undirected=True)
+    out = layer([eid, wd], training=True, seed=8)
+    want = o.drop_edge([ei, w], 0.4, True, True, seed=8)
+    np.testing.assert_array_equal(host(out[0]), want[0])
+    np.testing.assert_array_equal(host(out[1]), want[1])
+    same = layer([eid, wd], training=False)
+    assert same[0] is eid and same[1] is wd
+    with pytest.raises(ValueError):
+        tfg.layers.DropEdge(rate=1.2)
+
+    # MapReduceGNN: a user-defined mapper with a stock reducer
+    class Doubler(tfg.layers.MapReduceGNN):
+        def map(self, repeated_x, neighbor_x, edge_weight=None):
+            return neighbor_x * 2.0 * edge_weight.unsqueeze(1)
+
+        def reduce(self, neighbor_msg, node_index, num_nodes=None):
+            return tfg.nn.mean_reducer(neighbor_msg, node_index, num_nodes)
+
+        def update(self, x, reduced_neighbor_msg):
+            return x + reduced_neighbor_msg
+
+    got = Doubler()([xd, eid, wd])
+    want = o.aggregate_neighbors(x, ei, w, lambda rx, nx, edge_weight=None: (nx * np.float32(2.0) * edge_weight[:, None]).astype(np.float32),
+                                 o.mean_reducer, o.sum_updater, num_nodes=n)
+    assert_close(host(got), want, rtol=1e-6, atol_scale=1e-6, what="MapReduceGNN")

@@ -142,4 +142,5 @@ def test_pooling_family_on_the_fake_backend(fake):
     test_gpu_pool2.test_pools_over_few_large_graphs_use_edge_sized_tasks()
     test_gpu_pool2.test_sag_pool_matches_oracle(3, None)
     test_gpu_pool2.test_sag_pool_matches_oracle(None, 0.4)
+    test_gpu_pool2.test_sort_pool_drop_edge_layer_and_map_reduce_layer()
     golden_cases.replay("ref_exec_pool2.npz", np.load(test_gpu_train.GOLDEN + "/ref_exec_pool2.npz"), golden_cases.ProductApi())

@@ -5,4 +5,6 @@ from .conv.gat import GAT
 from .conv.graph_sage import MeanGraphSage, SumGraphSage, GCNGraphSage, MeanPoolGraphSage, MaxPoolGraphSage
 from .conv.appnp import APPNP
 from .conv.propagation import SGC, SSGC, TAGCN, GIN, LEConv, ChebyNet
-from .pool.pool import MeanPool, SumPool, MaxPool, MinPool, Set2Set, SAGPool
+from .pool.pool import MeanPool, SumPool, MaxPool, MinPool, Set2Set, SAGPool, SortPool
+from .sampling import DropEdge
+from .kernel import MapReduceGNN

@@ -1,2 +1,2 @@
 # coding=utf-8
-from .pool import MeanPool, SumPool, MaxPool, MinPool, Set2Set, SAGPool
+from .pool import MeanPool, SumPool, MaxPool, MinPool, Set2Set, SAGPool, SortPool

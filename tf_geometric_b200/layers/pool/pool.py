@@ -6,6 +6,7 @@ import torch
 from ...nn.pool.common_pool import mean_pool, sum_pool, max_pool, min_pool
 from ...nn.pool.set2set import set2set
 from ...nn.pool.sag_pool import sag_pool
+from ...nn.pool.sort_pool import sort_pool
 from .._base import Layer
 
 
@@ -91,3 +92,18 @@ class SAGPool(torch.nn.Module):
         x, edge_index, edge_weight, node_graph_index = inputs
         return sag_pool(x, edge_index, edge_weight, node_graph_index, self.score_gnn, k=self.k, ratio=self.ratio,
                         score_activation=self.score_activation, training=training, cache=cache)
+
+
+class SortPool(torch.nn.Module):
+    """inputs: [x, edge_index, edge_weight, node_graph_index] -> the pooled graph (layers/pool/sort_pool.py:7-40)."""
+
+    def __init__(self, k=None, ratio=None, sort_index=-1):
+        super().__init__()
+        self.k = k
+        self.ratio = ratio
+        self.sort_index = sort_index
+
+    def forward(self, inputs, training=None, mask=None):
+        x, edge_index, edge_weight, node_graph_index = inputs
+        return sort_pool(x, edge_index, edge_weight, node_graph_index, k=self.k, ratio=self.ratio,
+                         sort_index=self.sort_index, training=training)

@@ -15,5 +15,6 @@ from .pool.common_pool import mean_pool, sum_pool, max_pool, min_pool
 from .pool.set2set import set2set
 from .pool.topk_pool import topk_pool
 from .pool.sag_pool import sag_pool
+from .pool.sort_pool import sort_pool
 from ..ops import relu
 from .sampling.drop_edge import drop_edge
