@@ -4,6 +4,7 @@
 // pass (and its transpose for the scatter-shaped gradients), deterministic, no atomics.
 #include "common.cuh"
 #include "rng.cuh"
+#include <stdlib.h>
 
 namespace tfgk {
 namespace {
@@ -51,9 +52,11 @@ struct HeadsParams {
     int64_t ldo;
 };
 
+template <bool DROP = true>
 __device__ __forceinline__ float head_weight(const HeadsParams &p, int64_t e, int h) {
     const int64_t pos = p.emap ? (int64_t)p.emap[e] : e;
     const float w = p.w[pos * p.H + h];
+    if (!DROP) return w;                             // compiled without the generator: fewer registers, more warps
     const float k = keep_scale(p.rate, p.scale, p.seed, p.stream, (uint64_t)(pos * p.H + h));
     return k == 0.0f ? 0.0f : (p.rate > 0.0f ? __fmul_rn(w, k) : w);
 }
@@ -94,7 +97,8 @@ __global__ void __launch_bounds__(kTrainThreads) spmm_heads_kernel(const HeadsPa
 }
 
 // H*dh == 128, split layout, 16-byte aligned rows: every lane owns one float4 of the output row and the head it
-// belongs to; four edges in flight per iteration
+// belongs to; U edges in flight per iteration
+template <int U, bool DROP>
 __global__ void __launch_bounds__(kTrainThreads) spmm_heads128_kernel(const HeadsParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t r = (int64_t)blockIdx.x * kTrainWarps + warp;
@@ -103,16 +107,16 @@ __global__ void __launch_bounds__(kTrainThreads) spmm_heads128_kernel(const Head
     const int h = (lane * 4) / p.dh;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int64_t e = e0;
-    for (; e + 4 <= e1; e += 4) {
-        float4 v[4];
-        float w[4];
+    for (; e + U <= e1; e += U) {
+        float4 v[U];
+        float w[U];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < U; ++i) {
             v[i] = *reinterpret_cast<const float4 *>(p.src + (int64_t)p.col[e + i] * p.lds + lane * 4);
-            w[i] = head_weight(p, e + i, h);
+            w[i] = head_weight<DROP>(p, e + i, h);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < U; ++i) {
             acc.x = __fadd_rn(acc.x, __fmul_rn(v[i].x, w[i]));
             acc.y = __fadd_rn(acc.y, __fmul_rn(v[i].y, w[i]));
             acc.z = __fadd_rn(acc.z, __fmul_rn(v[i].z, w[i]));
@@ -121,7 +125,7 @@ __global__ void __launch_bounds__(kTrainThreads) spmm_heads128_kernel(const Head
     }
     for (; e < e1; ++e) {
         const float4 v = *reinterpret_cast<const float4 *>(p.src + (int64_t)p.col[e] * p.lds + lane * 4);
-        const float w = head_weight(p, e, h);
+        const float w = head_weight<DROP>(p, e, h);
         acc.x = __fadd_rn(acc.x, __fmul_rn(v.x, w));
         acc.y = __fadd_rn(acc.y, __fmul_rn(v.y, w));
         acc.z = __fadd_rn(acc.z, __fmul_rn(v.z, w));
@@ -197,7 +201,8 @@ __global__ void __launch_bounds__(kTrainThreads) gat_softmax_bwd_kernel(const Ga
 
 // split layout with H*dv == 128 (dv a multiple of 4 dividing 128): lane owns one float4; the dot products of all heads
 // are reduced at once inside groups of dv/4 lanes
-__global__ void __launch_bounds__(kTrainThreads) gat_softmax_bwd128_kernel(const GatBwdParams p) {
+template <int U, int MINB, bool DROP>
+__global__ void __launch_bounds__(kTrainThreads, MINB) gat_softmax_bwd128_kernel(const GatBwdParams p) {
     extern __shared__ float smem[];   // [warps][H]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t r = (int64_t)blockIdx.x * kTrainWarps + warp;
@@ -218,18 +223,18 @@ __global__ void __launch_bounds__(kTrainThreads) gat_softmax_bwd128_kernel(const
         for (int off = group >> 1; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
         if (leader) {
             const int64_t idx = (int64_t)e * H + h;
-            d *= keep_scale(p.rate, p.scale, p.seed, p.stream, (uint64_t)((start + e) * H + h));
+            if (DROP) d *= keep_scale(p.rate, p.scale, p.seed, p.stream, (uint64_t)((start + e) * H + h));
             ds[idx] = d;
             dacc += att[idx] * d;
         }
     };
     int e = 0;
-    for (; e + 4 <= deg; e += 4) {                  // four gathered value rows in flight
-        float4 v[4];
+    for (; e + U <= deg; e += U) {                  // U gathered value rows in flight
+        float4 v[U];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4 *>(p.V + (int64_t)col[e + i] * p.ldv + lane * 4);
+        for (int i = 0; i < U; ++i) v[i] = *reinterpret_cast<const float4 *>(p.V + (int64_t)col[e + i] * p.ldv + lane * 4);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) finish(g.x * v[i].x + g.y * v[i].y + g.z * v[i].z + g.w * v[i].w, e + i);
+        for (int i = 0; i < U; ++i) finish(g.x * v[i].x + g.y * v[i].y + g.z * v[i].z + g.w * v[i].w, e + i);
     }
     for (; e < deg; ++e) {
         const float4 v = *reinterpret_cast<const float4 *>(p.V + (int64_t)col[e] * p.ldv + lane * 4);
@@ -282,9 +287,17 @@ int tfgk_spmm_heads_f32(const int64_t *rowptr, const int32_t *col, const int32_t
     const unsigned blocks = (unsigned)ceil_div64(n_dst, kTrainWarps);
     const bool fast = mode == TFGK_HEADS_SPLIT && (int64_t)H * dh == 128 && dh % 4 == 0 && aligned16(src) && aligned16(out) &&
                       lds % 4 == 0 && ldo % 4 == 0 && (!bias || aligned16(bias));
-    if (fast)
-        spmm_heads128_kernel<<<blocks, kTrainThreads, 0, as_stream(stream)>>>(p);
-    else
+    if (fast) {
+        const char *cfg = getenv("TFGK_SPMM_HEADS_CFG");       // rows in flight per warp: "8" or the default 4
+        const bool wide = cfg && cfg[0] == '8';
+        if (drop_rate > 0.0f) {
+            if (wide) spmm_heads128_kernel<8, true><<<blocks, kTrainThreads, 0, as_stream(stream)>>>(p);
+            else spmm_heads128_kernel<4, true><<<blocks, kTrainThreads, 0, as_stream(stream)>>>(p);
+        } else {
+            if (wide) spmm_heads128_kernel<8, false><<<blocks, kTrainThreads, 0, as_stream(stream)>>>(p);
+            else spmm_heads128_kernel<4, false><<<blocks, kTrainThreads, 0, as_stream(stream)>>>(p);
+        }
+    } else
         spmm_heads_kernel<<<blocks, kTrainThreads, 0, as_stream(stream)>>>(p);
     TFGK_LAUNCH_CHECK();
     return TFGK_OK;
@@ -309,9 +322,22 @@ int tfgk_gat_softmax_bwd_f32(const int64_t *rowptr, const int32_t *col, const fl
     TFGK_CHECK_ARG(smem <= 48 * 1024, "gat_softmax_bwd: too many heads (%d)", H);
     const bool fast = p.split && (int64_t)H * dv == 128 && dv % 4 == 0 && pow2(dv >> 2) && aligned16(G) && aligned16(V) &&
                       ldg % 4 == 0 && ldv % 4 == 0;
-    if (fast)
-        gat_softmax_bwd128_kernel<<<blocks, kTrainThreads, smem, as_stream(stream)>>>(p);
-    else
+    if (fast) {
+        const char *cfg = getenv("TFGK_GAT_BWD_CFG");          // "UxB": rows in flight x resident CTAs per SM; default 4x4
+        const int sel = (cfg && cfg[0] == '8' && cfg[2] == '3') ? 1 : (cfg && cfg[0] == '4' && cfg[2] == '5') ? 2
+                        : (cfg && cfg[0] == '8' && cfg[2] == '4') ? 3 : 0;
+        cudaStream_t st = as_stream(stream);
+#define TFGK_LAUNCH_BWD(UU, BB)                                                                         \
+    do {                                                                                                \
+        if (drop_rate > 0.0f) gat_softmax_bwd128_kernel<UU, BB, true><<<blocks, kTrainThreads, smem, st>>>(p);  \
+        else gat_softmax_bwd128_kernel<UU, BB, false><<<blocks, kTrainThreads, smem, st>>>(p);          \
+    } while (0)
+        if (sel == 1) TFGK_LAUNCH_BWD(8, 3);
+        else if (sel == 2) TFGK_LAUNCH_BWD(4, 5);
+        else if (sel == 3) TFGK_LAUNCH_BWD(8, 4);
+        else TFGK_LAUNCH_BWD(4, 4);
+#undef TFGK_LAUNCH_BWD
+    } else
         gat_softmax_bwd_kernel<<<blocks, kTrainThreads, smem, as_stream(stream)>>>(p);
     TFGK_LAUNCH_CHECK();
     return TFGK_OK;
