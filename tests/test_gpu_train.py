@@ -342,3 +342,154 @@ def test_random_neighbor_sampler_matches_oracle(k, ratio, padding):
         assert wi.max() < 120
     with pytest.raises(Exception):
         sampler.sample(k=3, ratio=0.5)
+
+
+# ---- every other convolution trains through the same autograd Functions ---------------------------------------------------
+
+def _t64(a, grad=True):
+    return torch.tensor(np.asarray(a, np.float64), requires_grad=grad)
+
+
+def _spmm64(index, value, h, n):
+    return port.spmm(torch.from_numpy(index[0].astype(np.int64)), torch.from_numpy(index[1].astype(np.int64)),
+                     torch.tensor(np.asarray(value, np.float64)), h, n)
+
+
+@pytest.mark.parametrize("name", ["sgc", "ssgc", "tagcn", "gin", "le_conv", "chebynet", "gcn_graph_sage",
+                                  "mean_pool_graph_sage"])
+def test_conv_training_gradients_match_autodiff(name):
+    """Loss gradients of the remaining convolutions against float64 torch autograd over the reference's op sequence."""
+    rs = np.random.RandomState(sum(map(ord, name)))
+    n, f, u = 320, 9, 6
+    ei = random_graph(n, 2400, seed=len(name), symmetric=True, isolated=1)
+    w = (rs.rand(ei.shape[1]) + 0.2).astype(np.float32)
+    half = ei.shape[1] // 2
+    w[half:] = w[:half]                                             # symmetric weights (chebynet's Laplacian)
+    x = rs.randn(n, f).astype(np.float32)
+    eid, wd = dev(ei, torch.int32), dev(w)
+    relu = tfg.nn.relu
+    P = {}                                                          # name -> numpy parameter
+
+    def run(mine, ref, grad_x=False):
+        gout = None
+        tp = {k: dev(v).requires_grad_(True) for k, v in P.items()}
+        xd = dev(x).requires_grad_(grad_x)
+        y = mine(xd, tp)
+        gout = rs.randn(*y.shape).astype(np.float32)
+        (y * dev(gout)).sum().backward()
+        t64 = {k: _t64(v) for k, v in P.items()}
+        x64 = _t64(x, grad_x)
+        y_ref = ref(x64, t64)
+        (y_ref * torch.tensor(gout.astype(np.float64))).sum().backward()
+        assert_close(host(y), y_ref.detach().numpy(), what=name + " forward (training path)")
+        for k in P:
+            assert tp[k].grad is not None, k
+            assert_close(host(tp[k].grad), t64[k].grad.numpy(), rtol=1e-3, atol_scale=2e-4, what=name + " d " + k)
+        if grad_x:
+            assert_close(host(xd.grad), x64.grad.numpy(), rtol=1e-3, atol_scale=2e-4, what=name + " d x")
+
+    def normed(renorm=True, improved=False, weights=w):
+        m = o.gcn_norm_adj(o.SparseMatrix(ei, weights, [n, n]), renorm=renorm, improved=improved)
+        return m.index, m.value
+
+    if name == "sgc":
+        P.update(k=glorot(rs, f, u), b=rs.randn(u).astype(np.float32))
+        ai, av = normed()
+        run(lambda xd, p: tfg.nn.sgc(xd, eid, wd, 2, p["k"], p["b"], relu),
+            lambda x64, p: torch.relu(_spmm64(ai, av, _spmm64(ai, av, x64 @ p["k"], n), n) + p["b"]))
+    elif name == "ssgc":
+        P.update(k0=glorot(rs, f, 8), b0=rs.randn(8).astype(np.float32), k1=glorot(rs, 8, u), b1=rs.randn(u).astype(np.float32))
+        ai, av = normed()
+
+        def ref(x64, p):
+            h = torch.relu(x64 @ p["k0"] + p["b0"]) @ p["k1"] + p["b1"]
+            out = h * 0.2
+            for _ in range(3):
+                h = _spmm64(ai, av, h, n)
+                out = out + (1 - 0.2) * h / 3
+            return out
+        run(lambda xd, p: tfg.nn.ssgc(xd, eid, wd, [p["k0"], p["k1"]], [p["b0"], p["b1"]], k=3, alpha=0.2), ref)
+    elif name == "tagcn":
+        P.update(k=glorot(rs, 3 * f, u), b=rs.randn(u).astype(np.float32))
+        ai, av = normed(renorm=False)
+
+        def ref(x64, p):
+            a1 = _spmm64(ai, av, x64, n)
+            return torch.relu(torch.cat([x64, a1, _spmm64(ai, av, a1, n)], dim=1) @ p["k"] + p["b"])
+        run(lambda xd, p: tfg.nn.tagcn(xd, eid, wd, 2, p["k"], p["b"], relu), ref, grad_x=True)
+    elif name == "gin":
+        from tf_geometric_b200 import autograd
+        P.update(m=glorot(rs, f, u), eps=np.array([0.3], np.float32))
+        ones = np.ones(ei.shape[1], np.float32)
+        run(lambda xd, p: tfg.nn.gin(xd, eid, lambda h, training=None: autograd.dense(h, p["m"], None, relu), eps=p["eps"]),
+            lambda x64, p: torch.relu((x64 * (1.0 + p["eps"]) + _spmm64(ei, ones, x64, n)) @ p["m"]), grad_x=True)
+    elif name == "le_conv":
+        for k_ in ("ws", "wa", "wn"):
+            P[k_] = glorot(rs, f, u)
+        for k_ in ("bs", "ba", "bn"):
+            P[k_] = rs.randn(u).astype(np.float32)
+        run(lambda xd, p: tfg.nn.le_conv(xd, eid, wd, p["ws"], p["bs"], p["wa"], p["ba"], p["wn"], p["bn"], relu),
+            lambda x64, p: torch.relu(_spmm64(ei, w, (x64 @ p["wa"] + p["ba"]) - (x64 @ p["wn"] + p["bn"]), n)
+                                      + x64 @ p["ws"] + p["bs"]), grad_x=True)
+    elif name == "chebynet":
+        P.update(k0=glorot(rs, f, u), k1=glorot(rs, f, u), k2=glorot(rs, f, u), b=rs.randn(u).astype(np.float32))
+        li, lv = o.chebynet_norm_edge(ei, n, w, "sym")
+
+        def ref(x64, p):
+            t0 = x64
+            out = t0 @ p["k0"]
+            t1 = _spmm64(li, lv, t0, n)
+            out = out + t1 @ p["k1"]
+            t2 = _spmm64(li, lv, t1, n) * 2.0 - t0
+            return torch.relu(out + t2 @ p["k2"] + p["b"])
+        run(lambda xd, p: tfg.nn.chebynet(xd, eid, wd, 3, [p["k0"], p["k1"], p["k2"]], p["b"], relu), ref)
+    elif name == "gcn_graph_sage":
+        P.update(k=glorot(rs, f, u), b=rs.randn(u).astype(np.float32))
+        ai, av = normed(renorm=False, weights=np.ones_like(w))     # quirks: weights -> ones, cache=None -> renorm=False
+        run(lambda xd, p: tfg.nn.gcn_graph_sage(xd, eid, wd, p["k"], p["b"], relu),
+            lambda x64, p: torch.relu(_spmm64(ai, av, x64, n) @ p["k"] + p["b"]), grad_x=True)
+    else:
+        P.update(ws=glorot(rs, f, u), wm=glorot(rs, f, 8), wn=glorot(rs, 8, u), bm=rs.randn(8).astype(np.float32),
+                 b=rs.randn(2 * u).astype(np.float32))
+        cnt = np.maximum(np.bincount(ei[0], minlength=n), 1).astype(np.float64)
+
+        def ref(x64, p):
+            h_node = torch.relu(x64 @ p["wm"] + p["bm"])
+            red = _spmm64(ei, np.ones(ei.shape[1]), h_node, n) / torch.tensor(cnt).unsqueeze(1)
+            return torch.relu(torch.cat([x64 @ p["ws"], red @ p["wn"]], dim=1) + p["b"])
+        run(lambda xd, p: tfg.nn.mean_pool_graph_sage(xd, eid, wd, p["ws"], p["wm"], p["wn"], p["bm"], p["b"], relu), ref)
+
+
+def test_every_trainable_layer_gets_gradients():
+    """trainable=True layers: one forward+backward each, every registered weight receives a finite, non-zero gradient."""
+    rs = np.random.RandomState(2)
+    n, f = 200, 10
+    ei = random_graph(n, 1500, seed=3, symmetric=True)
+    xd, eid, wd = dev(rs.randn(n, f).astype(np.float32)), dev(ei, torch.int32), dev((rs.rand(ei.shape[1]) + .2).astype(np.float32))
+    L = tfg.layers
+    cases = [
+        (L.GCN(8, activation=tfg.nn.relu, seed=1, trainable=True), [xd, eid, wd]),
+        (L.GAT(8, num_heads=2, activation=tfg.nn.relu, seed=1, trainable=True), [xd, eid]),
+        (L.MeanGraphSage(8, seed=1, trainable=True), [xd, eid, wd]),
+        (L.SumGraphSage(8, concat=False, seed=1, trainable=True), [xd, eid, wd]),
+        (L.GCNGraphSage(8, seed=1, trainable=True), [xd, eid, wd]),
+        (L.MeanPoolGraphSage(8, seed=1, trainable=True), [xd, eid, wd]),
+        (L.APPNP([12, 5], k=3, seed=1, trainable=True), [xd, eid, wd]),
+        (L.SGC(6, k=2, seed=1, trainable=True), [xd, eid, wd]),
+        (L.SSGC([12, 5], k=3, seed=1, trainable=True), [xd, eid, wd]),
+        (L.TAGCN(6, k=2, seed=1, trainable=True), [xd, eid, wd]),
+        (L.LEConv(6, activation=tfg.nn.relu, seed=1, trainable=True), [xd, eid, wd]),
+        (L.ChebyNet(6, k=3, seed=1, trainable=True), [xd, eid, wd]),
+    ]
+    for layer, inputs in cases:
+        out = layer(inputs, training=True)
+        assert out.requires_grad, type(layer).__name__
+        (out * out).sum().backward()
+        params = dict(layer.named_parameters())
+        assert params, type(layer).__name__
+        for pname, p in params.items():
+            assert p.grad is not None and torch.isfinite(p.grad).all(), "{}.{}".format(type(layer).__name__, pname)
+            if "bias" not in pname:
+                assert float(p.grad.abs().sum()) > 0, "{}.{}".format(type(layer).__name__, pname)
+    with pytest.raises(NotImplementedError):
+        L.MaxPoolGraphSage(8, seed=1, trainable=True)([xd, eid, wd])

@@ -144,3 +144,9 @@ def test_pooling_family_on_the_fake_backend(fake):
     test_gpu_pool2.test_sag_pool_matches_oracle(None, 0.4)
     test_gpu_pool2.test_sort_pool_drop_edge_layer_and_map_reduce_layer()
     golden_cases.replay("ref_exec_pool2.npz", np.load(test_gpu_train.GOLDEN + "/ref_exec_pool2.npz"), golden_cases.ProductApi())
+
+
+def test_remaining_convs_train_on_the_fake_backend(fake):
+    for name in ("sgc", "ssgc", "tagcn", "gin", "le_conv", "chebynet", "gcn_graph_sage", "mean_pool_graph_sage"):
+        test_gpu_train.test_conv_training_gradients_match_autodiff(name)
+    test_gpu_train.test_every_trainable_layer_gets_gradients()

@@ -200,5 +200,17 @@ def dropout(x, rate, training, seed=None):
     return Dropout.apply(x, float(rate), _rng.resolve(seed))
 
 
+def dense(x, weight, bias=None, activation=None):
+    """Differentiable act(x @ W + b): relu is fused into the GEMM epilogue, any other callable runs on the result."""
+    code, leftover = ops.activation_code(activation)
+    y = Dense.apply(x, weight, bias, code)
+    return leftover(y) if leftover is not None else y
+
+
+def propagate(adj, h, bias=None, act_code=ops.ACT_NONE):
+    """Differentiable act(A @ h + b) for a SparseMatrix A (gradient w.r.t. h and b)."""
+    return SparseMatmul.apply(h, bias, adj, act_code)
+
+
 def needs_grad(*tensors):
     return torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in tensors)

@@ -38,9 +38,13 @@ def _project_pair(x, agg, self_kernel, neighbor_kernel, bias, activation, concat
 
 def _plain_sage_autograd(reduce, x, edge_index, edge_weight, ws, wn, bias, activation, concat, normalize):
     """Training path (any input requires grad): the same kernels wrapped in autograd Functions (autograd.py)."""
-    num_nodes = x.shape[0]
+    agg = autograd.NeighborAggregate.apply(x, edge_index, edge_weight, reduce, x.shape[0])
+    return _project_pair_autograd(x, agg, ws, wn, bias, activation, concat, normalize)
+
+
+def _project_pair_autograd(x, agg, ws, wn, bias, activation, concat, normalize):
+    """Differentiable twin of _project_pair."""
     act_code, leftover = ops.activation_code(activation)
-    agg = autograd.NeighborAggregate.apply(x, edge_index, edge_weight, reduce, num_nodes)
     if concat:
         u = ws.shape[1]
         left = autograd.Dense.apply(x, ws, None if bias is None else bias[:u], act_code)
@@ -100,6 +104,12 @@ def gcn_graph_sage(x, edge_index, edge_weight, kernel, bias=None, activation=Non
         edge_weight = torch.ones([edge_index.shape[1]], dtype=torch.float32, device=dev)
     # reference :142 passes `cache` positionally into gcn_norm_edge(edge_index, num_nodes, edge_weight, renorm=...)
     normed = SparseMatrix(*_norm_edge_as_matrix(edge_index, num_nodes, edge_weight, renorm=bool(cache)))
+    if autograd.needs_grad(x, kernel, bias):
+        h = autograd.dense(autograd.propagate(normed, x), ops.as_device(kernel, torch.float32, device=dev),
+                           None if bias is None else ops.as_device(bias, torch.float32, device=dev), activation)
+        if normalize:
+            h = h * torch.rsqrt(torch.clamp((h * h).sum(dim=-1, keepdim=True), min=1e-12))
+        return h
     reduced = normed.matmul(x)
     act_code, leftover = ops.activation_code(activation)
     h = ops.gemm(reduced, ops.as_device(kernel, torch.float32, device=dev),
@@ -125,6 +135,14 @@ def _pool_sage(reduce, x, edge_index, edge_weight, self_kernel, neighbor_mlp_ker
     dev = edge_index.device
     x = ops.as_device(x, torch.float32, device=dev)
     num_nodes = x.shape[0]
+    if autograd.needs_grad(x, self_kernel, neighbor_mlp_kernel, neighbor_kernel, neighbor_mlp_bias, bias):
+        if reduce != "mean":
+            raise NotImplementedError("max_pool_graph_sage has no backward kernel (the max reduce keeps no argmax)")
+        f32 = lambda t: None if t is None else ops.as_device(t, torch.float32, device=dev)   # noqa: E731
+        h_node = autograd.dense(x, f32(neighbor_mlp_kernel), f32(neighbor_mlp_bias), activation)
+        reduced = autograd.NeighborAggregate.apply(h_node, edge_index, None, "mean", num_nodes)
+        return _project_pair_autograd(x, reduced, f32(self_kernel), f32(neighbor_kernel), f32(bias), activation, concat,
+                                      normalize)
     csr, _ = _structure.csr_for_edge_index(edge_index, num_nodes)
     act_code, leftover = ops.activation_code(activation)
     # per-node neighbour MLP (weights are all ones, so x[col] * w == x[col])

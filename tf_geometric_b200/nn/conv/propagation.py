@@ -20,12 +20,16 @@ def sgc(x, edge_index, edge_weight, k, kernel, bias=None, activation=None, renor
     x = _f32(x, dev)
     n = x.shape[0]
     normed = gcn_norm_adj(SparseMatrix(edge_index, edge_weight, [n, n]), renorm=renorm, improved=improved, cache=cache)
-    h = ops.gemm(x, _f32(kernel, dev))
     act_code, leftover = ops.activation_code(activation)
     b = _f32(bias, dev)
+    with_grad = autograd.needs_grad(x, kernel, bias)       # training: the same kernels behind autograd Functions
+    h = autograd.dense(x, _f32(kernel, dev)) if with_grad else ops.gemm(x, _f32(kernel, dev))
     for i in range(k):
         last = i == k - 1
-        h = normed.matmul(h, bias=b if last else None, act=act_code if last else ops.ACT_NONE)
+        if with_grad:
+            h = autograd.propagate(normed, h, b if last else None, act_code if last else ops.ACT_NONE)
+        else:
+            h = normed.matmul(h, bias=b if last else None, act=act_code if last else ops.ACT_NONE)
     if k == 0:
         if b is not None:
             h = h + b
@@ -45,18 +49,23 @@ def ssgc(x, edge_index, edge_weight, kernels=None, biases=None, k=10, alpha=0.1,
     n = h.shape[0]
     normed = gcn_norm_adj(SparseMatrix(edge_index, edge_weight, [n, n]), cache=cache)
     normed = normed.dropout(edge_drop_rate, training=training)                          # ssgc.py:60-61
+    with_grad = autograd.needs_grad(h, *[t for t in list(kernels or []) + list(biases or []) if t is not None])
     if kernels is not None:
         num_dense = len(kernels)
         for i, (kern, b) in enumerate(zip(kernels, biases)):
-            act_code, leftover = ops.activation_code(dense_activation if i < num_dense - 1 else None)
-            h = ops.gemm(h, _f32(kern, dev), bias=_f32(b, dev), act=act_code)
-            if leftover is not None:
-                h = leftover(h)
+            act = dense_activation if i < num_dense - 1 else None
+            if with_grad:
+                h = autograd.dense(h, _f32(kern, dev), _f32(b, dev), act)
+            else:
+                act_code, leftover = ops.activation_code(act)
+                h = ops.gemm(h, _f32(kern, dev), bias=_f32(b, dev), act=act_code)
+                if leftover is not None:
+                    h = leftover(h)
             h = autograd.dropout(h, dense_drop_rate if i < num_dense - 1 else last_dense_drop_rate, training)  # :84-88
     output = h * alpha                                    # elementwise glue in the reference's rounding order (:91-94)
     for _ in range(k):
-        h = normed.matmul(h)
-        output += (1 - alpha) * h / k
+        h = autograd.propagate(normed, h) if with_grad else normed.matmul(h)
+        output = output + (1 - alpha) * h / k
     if activation is not None:
         output = activation(output)
     return output
@@ -70,6 +79,11 @@ def tagcn(x, edge_index, edge_weight, k, kernel, bias=None, activation=None, ren
     x = _f32(x, dev)
     n, f = x.shape
     normed = gcn_norm_adj(SparseMatrix(edge_index, edge_weight, [n, n]), renorm=renorm, improved=improved, cache=cache)
+    if autograd.needs_grad(x, kernel, bias):
+        terms = [x]
+        for _ in range(k):
+            terms.append(autograd.propagate(normed, terms[-1]))
+        return autograd.dense(torch.cat(terms, dim=1), _f32(kernel, dev), _f32(bias, dev), activation)
     hops = torch.empty((n, f * (k + 1)), dtype=torch.float32, device=dev)
     hops[:, :f].copy_(x)
     for i in range(k):
@@ -89,9 +103,12 @@ def gin(x, edge_index, mlp_model, eps=0.0, training=None):
     edge_index = ops.as_device(edge_index, torch.int32)
     dev = edge_index.device
     x = _f32(x, dev)
-    csr, _ = _structure.csr_for_edge_index(edge_index, x.shape[0])
-    eps_value = float(eps.detach().item()) if torch.is_tensor(eps) else float(eps)
-    h = ops.spmm(csr, None, x, reduce="sum", alpha=1.0, addend=x, beta=1.0 + eps_value)
+    if autograd.needs_grad(x, eps):                        # trainable eps (layers/conv/gin.py train_eps) or upstream layers
+        h = gin_updater(x, autograd.NeighborAggregate.apply(x, edge_index, None, "sum", x.shape[0]), eps)
+    else:
+        csr, _ = _structure.csr_for_edge_index(edge_index, x.shape[0])
+        eps_value = float(eps.detach().item()) if torch.is_tensor(eps) else float(eps)
+        h = ops.spmm(csr, None, x, reduce="sum", alpha=1.0, addend=x, beta=1.0 + eps_value)
     try:
         return mlp_model(h, training=training)
     except TypeError:
@@ -106,6 +123,13 @@ def le_conv(x, edge_index, edge_weight, self_kernel, self_bias, aggr_self_kernel
     dev = edge_index.device
     x = _f32(x, dev)
     n = x.shape[0]
+    if autograd.needs_grad(x, self_kernel, self_bias, aggr_self_kernel, aggr_self_bias, aggr_neighbor_kernel,
+                           aggr_neighbor_bias):
+        self_h = autograd.dense(x, _f32(self_kernel, dev), _f32(self_bias, dev))
+        diff = autograd.dense(x, _f32(aggr_self_kernel, dev), _f32(aggr_self_bias, dev)) \
+            - autograd.dense(x, _f32(aggr_neighbor_kernel, dev), _f32(aggr_neighbor_bias, dev))
+        h = autograd.NeighborAggregate.apply(diff, edge_index, _f32(edge_weight, dev), "sum", n) + self_h
+        return activation(h) if activation is not None else h
     csr, _ = _structure.csr_for_edge_index(edge_index, n)
     w_csr = None
     if edge_weight is not None:
@@ -199,6 +223,19 @@ def chebynet(x, edge_index, edge_weight, k, kernels, bias=None, activation=None,
                                            use_dynamic_lambda_max=use_dynamic_lambda_max, cache=cache)
     adj = SparseMatrix(n_index, n_weight, [n, n]) if cache is None else cache.setdefault(
         "tfgk_chebynet_adj_{}".format(normalization_type), SparseMatrix(n_index, n_weight, [n, n]))
+    if autograd.needs_grad(x, bias, *kernels):
+        t0 = x
+        out = autograd.dense(t0, _f32(kernels[0], dev))
+        if k > 1:
+            t1 = autograd.propagate(adj, x)
+            out = out + autograd.dense(t1, _f32(kernels[1], dev))
+        for i in range(2, k):
+            t2 = autograd.propagate(adj, t1) * 2.0 - t0
+            out = out + autograd.dense(t2, _f32(kernels[i], dev))
+            t0, t1 = t1, t2
+        if bias is not None:
+            out = out + _f32(bias, dev)
+        return activation(out) if activation is not None else out
     t0 = x
     out = ops.gemm(t0, _f32(kernels[0], dev))
     if k > 1:
