@@ -223,3 +223,59 @@ def test_sort_pool_drop_edge_layer_and_map_reduce_layer():
     want = o.aggregate_neighbors(x, ei, w, lambda rx, nx, edge_weight=None: (nx * np.float32(2.0) * edge_weight[:, None]).astype(np.float32),
                                  o.mean_reducer, o.sum_updater, num_nodes=n)
     assert_close(host(got), want, rtol=1e-6, atol_scale=1e-6, what="MapReduceGNN")
+
+
+def _torch_lstm(k, r, b):
+    """The LSTM cell of oracle.numpy_lstm on torch tensors of any dtype/device (differentiable)."""
+    units = r.shape[0]
+
+    def lstm(inputs, initial_state=None, training=None):
+        h, c = initial_state
+        seq = []
+        for t in range(inputs.shape[1]):
+            z = inputs[:, t] @ k + h @ r + b
+            i, f, g, o_ = (z[:, j * units:(j + 1) * units] for j in range(4))
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+            h = torch.sigmoid(o_) * torch.tanh(c)
+            seq.append(h)
+        return torch.stack(seq, dim=1), h, c
+    return lstm
+
+
+@pytest.mark.parametrize("d,graphs,n", [(6, 7, 150), (64, 5, 3000)])
+def test_set2set_gradients_match_autodiff(d, graphs, n):
+    from oracle import torch_cpu_port as port
+    rs = np.random.RandomState(d + 1)
+    gi = np.sort(rs.randint(0, graphs, n)).astype(np.int32)
+    gi[-1] = graphs - 1
+    x = (rs.randn(n, d) * 0.5).astype(np.float32)
+    k, r, b = glorot(rs, 2 * d, 4 * d), glorot(rs, d, 4 * d), (rs.randn(4 * d) * 0.1).astype(np.float32)
+    gout = rs.randn(graphs, 2 * d).astype(np.float32)
+
+    tp = [dev(a).requires_grad_(True) for a in (x, k, r, b)]
+    y = tfg.nn.set2set(tp[0], dev(gi), _torch_lstm(*tp[1:]), 2)
+    (y * dev(gout)).sum().backward()
+
+    t64 = [torch.tensor(a.astype(np.float64), requires_grad=True) for a in (x, k, r, b)]
+    ids = torch.from_numpy(gi.astype(np.int64))
+    lstm64 = _torch_lstm(*t64[1:])
+    h = torch.zeros((graphs, 2 * d), dtype=torch.float64)
+    state = [torch.zeros((1, d), dtype=torch.float64), torch.zeros((1, d), dtype=torch.float64)]
+    for _ in range(2):                                                   # set2set.py:28-40 on float64 torch ops
+        q, sh, sc = lstm64(h.unsqueeze(0), initial_state=state)
+        state = [sh, sc]
+        q = q.squeeze(0)
+        score = (t64[0] * q.index_select(0, ids)).sum(-1)
+        a = port.segment_softmax(score, ids, graphs)
+        att_h = torch.zeros((graphs, d), dtype=torch.float64).index_add_(0, ids, t64[0] * a.unsqueeze(1))
+        h = torch.cat([q, att_h], dim=-1)
+    (h * torch.tensor(gout.astype(np.float64))).sum().backward()
+
+    assert_close(host(y), h.detach().numpy(), what="set2set forward (training path)")
+    for name, mine, ref in zip(("x", "lstm kernel", "lstm recurrent kernel", "lstm bias"), tp, t64):
+        assert mine.grad is not None, name
+        assert_close(host(mine.grad), ref.grad.numpy(), rtol=1e-3, atol_scale=2e-4, what="set2set d " + name)
+    layer = tfg.layers.Set2Set(num_iterations=2, trainable=True)
+    out = layer([dev(x), dev(gi)])
+    out.sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in layer.parameters())

@@ -143,6 +143,7 @@ def test_pooling_family_on_the_fake_backend(fake):
     test_gpu_pool2.test_sag_pool_matches_oracle(3, None)
     test_gpu_pool2.test_sag_pool_matches_oracle(None, 0.4)
     test_gpu_pool2.test_sort_pool_drop_edge_layer_and_map_reduce_layer()
+    test_gpu_pool2.test_set2set_gradients_match_autodiff(6, 7, 150)
     golden_cases.replay("ref_exec_pool2.npz", np.load(test_gpu_train.GOLDEN + "/ref_exec_pool2.npz"), golden_cases.ProductApi())
 
 

@@ -138,29 +138,31 @@ class GatAttention(torch.autograd.Function):
     The mask is regenerated from (seed, edge, head) in every kernel, never stored."""
 
     @staticmethod
-    def forward(ctx, Q, K, V, bias, csr, edge_index_used, num_heads, split, act_code, drop_rate, seed):
+    def forward(ctx, Q, K, V, bias, csr, edge_index_used, num_heads, split, act_code, drop_rate, seed, scale=None):
         Qd, Kd, Vd = Q.detach(), K.detach(), V.detach()
         b = None if bias is None else bias.detach()
         H = int(num_heads)
+        if scale is None:                                    # gat.py:78; set2set.py:37 passes 1 (raw dot products)
+            scale = float(np.sqrt(np.float32(Q.shape[1] // H)))
         if drop_rate > 0.0:
-            _, att = ops.gat_fused(csr, Qd, Kd, Vd, H, split_value_heads=split, return_attention=True)
+            _, att = ops.gat_fused(csr, Qd, Kd, Vd, H, split_value_heads=split, return_attention=True, scale=scale)
             y = ops.spmm_heads(csr, att, Vd, H, mode=ops.HEADS_SPLIT if split else ops.HEADS_REDUCE,
                                drop_rate=drop_rate, seed=seed, alpha=1.0 if split else 1.0 / H, bias=b, act=act_code)
         else:
             y, att = ops.gat_fused(csr, Qd, Kd, Vd, H, split_value_heads=split, bias=b, act=act_code,
-                                   return_attention=True)
+                                   return_attention=True, scale=scale)
         ctx.save_for_backward(Qd, Kd, Vd, att, y if act_code == ops.ACT_RELU else None)
-        ctx.meta = (csr, edge_index_used, H, bool(split), act_code, float(drop_rate), seed, bias is not None)
+        ctx.meta = (csr, edge_index_used, H, bool(split), act_code, float(drop_rate), seed, bias is not None, float(scale))
         return y
 
     @staticmethod
     def backward(ctx, grad_y):
         Q, K, V, att, y = ctx.saved_tensors
-        csr, edge_index_used, H, split, act_code, drop_rate, seed, has_bias = ctx.meta
+        csr, edge_index_used, H, split, act_code, drop_rate, seed, has_bias, scale = ctx.meta
         g = grad_y.contiguous()
         if act_code == ops.ACT_RELU:
             g = g * (y > 0).to(g.dtype)
-        inv_scale = 1.0 / float(np.sqrt(np.float32(Q.shape[1] // H)))
+        inv_scale = 1.0 / scale
         ds = ops.gat_softmax_bwd(csr, att, g, V, H, split_value_heads=split, drop_rate=drop_rate, seed=seed)
         grad_q = grad_k = grad_v = grad_b = None
         if ctx.needs_input_grad[0]:
@@ -175,7 +177,7 @@ class GatAttention(torch.autograd.Function):
         if has_bias and ctx.needs_input_grad[3]:
             ones = torch.ones((g.shape[0], 1), dtype=torch.float32, device=g.device)
             grad_b = ops.gemm(ones, g, trans_a=True).reshape(-1)
-        return grad_q, grad_k, grad_v, grad_b, None, None, None, None, None, None, None
+        return grad_q, grad_k, grad_v, grad_b, None, None, None, None, None, None, None, None
 
 
 class Dropout(torch.autograd.Function):

@@ -63,18 +63,15 @@ class Set2Set(Layer):
         self.lstm = None
 
     def build(self, input_shapes, device=None):
-        if self._trainable:
-            raise NotImplementedError("Set2Set is forward-only here: the attention read-out has no backward kernel yet")
         num_features = input_shapes[0][-1]
         self.__dict__.pop("lstm", None)
         self.lstm = _KerasStyleLSTM(2 * num_features, num_features, device=device)
         for p in self.lstm.parameters():
-            p.requires_grad_(False)
+            p.requires_grad_(self._trainable)
 
     def call(self, inputs, cache=None, training=None, mask=None):
         x, node_graph_index = inputs
-        with torch.no_grad():
-            return set2set(x, node_graph_index, self.lstm, self.num_iterations, training=training)
+        return set2set(x, node_graph_index, self.lstm, self.num_iterations, training=training)
 
 
 class SAGPool(torch.nn.Module):

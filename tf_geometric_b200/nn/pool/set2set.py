@@ -7,7 +7,7 @@ and the nodes of a graph as that row's "neighbours": a single tfgk_gat_fused_f32
 node_graph_index (scale 1, one head) instead of two gathers, a 5-pass softmax and a scatter."""
 import torch
 
-from ... import ops, _structure
+from ... import ops, _structure, autograd
 
 
 def _graph_rows(node_graph_index, num_graphs, num_nodes):
@@ -37,6 +37,12 @@ def set2set(x, node_graph_index, lstm, num_iterations, training=None):
     num_nodes, units = x.shape
     num_graphs = int(node_graph_index.max().item()) + 1
     rows = _graph_rows(node_graph_index, num_graphs, num_nodes)
+    with_grad = autograd.needs_grad(x, *[p for p in getattr(lstm, "parameters", lambda: [])()])
+    if with_grad:        # (graph id, node id) pairs: the "edge list" the transposed structure of the backward is built from
+        pairs = _structure._lookup(node_graph_index, ("graph_pairs",))
+        if pairs is None:
+            pairs = _structure._store(node_graph_index, ("graph_pairs",), torch.stack(
+                [node_graph_index, torch.arange(num_nodes, dtype=torch.int32, device=dev)]))
 
     h = torch.zeros((num_graphs, units * 2), dtype=torch.float32, device=dev)
     state = [torch.zeros((1, units), dtype=torch.float32, device=dev), torch.zeros((1, units), dtype=torch.float32, device=dev)]
@@ -44,6 +50,9 @@ def set2set(x, node_graph_index, lstm, num_iterations, training=None):
         q, state_h, state_c = lstm(h.unsqueeze(0), initial_state=state, training=training)      # set2set.py:30-33
         state = [state_h, state_c]
         q = q.squeeze(0).contiguous()
-        att_h = ops.gat_fused(rows, q, x, x, 1, scale=1.0)                                       # set2set.py:35-39
+        if with_grad:
+            att_h = autograd.GatAttention.apply(q, x, x, None, rows, pairs, 1, True, ops.ACT_NONE, 0.0, 0, 1.0)
+        else:
+            att_h = ops.gat_fused(rows, q, x, x, 1, scale=1.0)                                   # set2set.py:35-39
         h = torch.cat([q, att_h], dim=-1)
     return h
