@@ -1131,3 +1131,24 @@ def numpy_lstm(kernel, recurrent_kernel, bias):
             seq.append(h)
         return np.stack(seq, axis=1).astype(F32), h, c
     return lstm
+
+
+def sort_pool(x, edge_index, edge_weight, node_graph_index, k=None, ratio=None, sort_index=-1):
+    """nn/pool/sort_pool.py:7-37."""
+    x = _as_f32(x)
+    topk_node_index = topk_pool(node_graph_index, x[:, sort_index], k=k, ratio=ratio)
+    px, pei, pw, pgi, _ = sample_new_graph_by_node_index(x, edge_index, edge_weight, topk_node_index, node_graph_index)
+    return px, pei, pw, pgi
+
+
+def batch_graphs(parts):
+    """BatchGraph.from_graphs (data/graph.py:463-560) for parts = [(x, edge_index, edge_weight, y), ...]:
+    returns (x, edge_index, edge_weight, y, node_graph_index, edge_graph_index)."""
+    xs, eis, ws, ys, ngi, egi, before = [], [], [], [], [], [], 0
+    for i, (x, ei, w, y) in enumerate(parts):
+        xs.append(np.asarray(x)); ws.append(np.asarray(w)); ys.append(np.asarray(y))
+        eis.append(np.asarray(ei, I32) + before)
+        ngi.append(np.full(len(x), i, I32)); egi.append(np.full(np.asarray(ei).shape[1], i, I32))
+        before += len(x)
+    return (np.concatenate(xs), np.concatenate(eis, axis=1).astype(I32), np.concatenate(ws), np.concatenate(ys),
+            np.concatenate(ngi), np.concatenate(egi))

@@ -53,6 +53,15 @@ class OracleApi(object):
     def lstm(self, kernel, recurrent_kernel, bias):
         return self.o.numpy_lstm(kernel, recurrent_kernel, bias)
 
+    def subgraph(self, x, ei, w, gi, y, keep):
+        return self.o.sample_new_graph_by_node_index(x, ei, w, keep, gi, y)
+
+    def sag_pool_scored(self, x, ei, w, gi, score, **kw):
+        return self.o.sag_pool(x, ei, w, gi, lambda inputs: score, score_activation=np.tanh, **kw)
+
+    def batch(self, parts):
+        return self.o.batch_graphs(parts)
+
 
 class ProductApi(object):
     exact_float = False
@@ -66,7 +75,7 @@ class ProductApi(object):
                      "mean_reducer", "max_reducer", "sum_updater", "identity_updater", "segment_softmax", "segment_count",
                      "gcn", "gat", "mean_graph_sage", "sum_graph_sage", "gcn_graph_sage", "mean_pool_graph_sage",
                      "max_pool_graph_sage", "appnp", "sgc", "ssgc", "tagcn", "gin", "le_conv", "mean_pool", "sum_pool",
-                     "max_pool", "min_pool", "chebynet", "chebynet_norm_edge", "topk_pool", "set2set"):
+                     "max_pool", "min_pool", "chebynet", "chebynet_norm_edge", "topk_pool", "set2set", "sort_pool"):
             setattr(self, name, getattr(tfg.nn, name))
         for name in ("convert_edge_to_directed", "merge_duplicated_edge", "add_self_loop_edge", "remove_self_loop_edge",
                      "adj_norm_edge"):
@@ -90,6 +99,17 @@ class ProductApi(object):
 
     def neighbor_sample(self, ei, w, **kw):
         return self.tfg.utils.RandomNeighborSampler(ei, w).sample(seed=1, **kw)
+
+    def subgraph(self, x, ei, w, gi, y, keep):
+        g = self.tfg.BatchGraph(x, ei, gi, None, y=y, edge_weight=w).sample_new_graph_by_node_index(keep)
+        return g.x, g.edge_index, g.edge_weight, g.node_graph_index, g.y
+
+    def sag_pool_scored(self, x, ei, w, gi, score, **kw):
+        return self.tfg.nn.sag_pool(x, ei, w, gi, lambda inputs, training=None: score, score_activation=self.torch.tanh, **kw)
+
+    def batch(self, parts):
+        bg = self.tfg.BatchGraph.from_graphs([self.tfg.Graph(x, ei, y=y, edge_weight=w) for x, ei, w, y in parts])
+        return bg.x, bg.edge_index, bg.edge_weight, bg.y, bg.node_graph_index, bg.edge_graph_index
 
     def lstm(self, kernel, recurrent_kernel, bias):
         """The same LSTM cell as oracle.numpy_lstm, on torch tensors (it is the caller-supplied ARGUMENT of set2set)."""
@@ -293,3 +313,28 @@ def _replay_pool2(d, api):
     tol = dict(rtol=1e-6, atol_scale=1e-6) if api.exact_float else dict(rtol=1e-4, atol_scale=1e-4)
     _close(O(api.set2set(A(d["x"]), A(d["gi_sorted"]), lstm, 3)), d["set2set_it3"], "set2set 3 iterations", **tol)
     _close(O(api.set2set(A(d["x"]), gi, lstm, 2)), d["set2set_unsorted_it2"], "set2set unsorted graph ids", **tol)
+
+
+def _replay_graph(d, api):
+    """Induced subgraphs, batching, sag_pool and sort_pool as the reference's own data/graph.py and nn/pool code produced
+    them (integer outputs and gathered rows: exact; gated features: 1e-6)."""
+    A, O = api.arr, api.out
+    x, ei, w, gi, y, keep = (A(d[k]) for k in ("x", "ei", "w", "gi", "y", "keep"))
+    sx, sei, sw, sgi, sy = api.subgraph(x, ei, w, gi, y, keep)
+    for got, key in ((sx, "sub_x"), (sei, "sub_ei"), (sw, "sub_w"), (sgi, "sub_gi"), (sy, "sub_y")):
+        _eq(O(got), d[key], "sample_new_graph_by_node_index " + key)
+    _eq(d["subnp_ei"], d["sub_ei"], "numpy and tensor containers agree in the reference")
+    score = A(d["score"])
+    for tag, kw in (("k4", {"k": 4}), ("r50", {"ratio": 0.5})):
+        px, pei, pw, pgi = api.sag_pool_scored(x, ei, w, gi, score, **kw)
+        _eq(O(pei), d["sag_%s_ei" % tag], "sag_pool edge_index " + tag)
+        _eq(O(pgi), d["sag_%s_gi" % tag], "sag_pool node_graph_index " + tag)
+        _eq(O(pw), d["sag_%s_w" % tag], "sag_pool edge_weight " + tag)
+        _close(O(px), d["sag_%s_x" % tag], "sag_pool x " + tag, rtol=1e-6, atol_scale=1e-6)
+        px, pei, pw, pgi = api.sort_pool(x, ei, w, gi, sort_index=1, **kw)
+        for got, key in ((px, "x"), (pei, "ei"), (pw, "w"), (pgi, "gi")):
+            _eq(O(got), d["sort_%s_%s" % (tag, key)], "sort_pool " + key + " " + tag)
+    parts = [(A(d["part%d_x" % i]), A(d["part%d_ei" % i]), A(d["part%d_w" % i]), A(d["part%d_y" % i])) for i in range(3)]
+    bx, bei, bw, by, bgi, begi = api.batch(parts)
+    for got, key in ((bx, "batch_x"), (bei, "batch_ei"), (bw, "batch_w"), (by, "batch_y"), (bgi, "batch_gi"), (begi, "batch_egi")):
+        _eq(O(got), d[key], "BatchGraph.from_graphs " + key)

@@ -283,6 +283,47 @@ def main():
     out["set2set_unsorted_it2"] = s2s_m.set2set(T(x), T(gi), shim_lstm, 2)
     save("pool2", **out)
 
+    # ---- Graph / BatchGraph: induced subgraphs, batching, and the pooling functions built on them --------------------------
+    import types as _types
+    data_pkg = _types.ModuleType("tf_geometric.data")
+    data_pkg.__path__ = [os.path.join(REFERENCE, "tf_geometric", "data")]
+    sys.modules["tf_geometric.data"] = data_pkg
+    graph_m = importlib.import_module("tf_geometric.data.graph")
+    sag_m = importlib.import_module("tf_geometric.nn.pool.sag_pool")
+    sort_m = importlib.import_module("tf_geometric.nn.pool.sort_pool")
+    n, g = 90, 7
+    ei = graph(n, 700, 31, False)
+    w = rs.rand(ei.shape[1]).astype(np.float32)
+    x = rs.randn(n, 5).astype(np.float32)
+    y = rs.randint(0, 4, n).astype(np.int32)
+    gi = np.sort(rs.randint(0, g, n)).astype(np.int32)
+    gi[-1] = g - 1
+    keep = rs.permutation(n)[:35].astype(np.int32)
+    out = {"n": n, "ei": ei, "w": w, "x": x, "y": y, "gi": gi, "keep": keep}
+    sub = graph_m.BatchGraph(T(x), T(ei), T(gi), None, y=T(y), edge_weight=T(w)).sample_new_graph_by_node_index(T(keep))
+    out.update(sub_x=sub.x, sub_ei=sub.edge_index, sub_w=sub.edge_weight, sub_gi=sub.node_graph_index, sub_y=sub.y)
+    sub_np = graph_m.Graph(x, ei, y=y, edge_weight=w).sample_new_graph_by_node_index(keep)        # numpy container path
+    out.update(subnp_x=sub_np.x, subnp_ei=sub_np.edge_index, subnp_w=sub_np.edge_weight)
+    score = rs.randn(n, 1).astype(np.float32)
+    out["score"] = score
+    for tag, kw in (("k4", {"k": 4}), ("r50", {"ratio": 0.5})):
+        px, pei, pw, pgi = sag_m.sag_pool(T(x), T(ei), T(w), T(gi), lambda inputs, training=None: T(score),
+                                          score_activation=lambda v: T(np.tanh(np.asarray(v))), **kw)
+        out.update({"sag_%s_x" % tag: px, "sag_%s_ei" % tag: pei, "sag_%s_w" % tag: pw, "sag_%s_gi" % tag: pgi})
+        px, pei, pw, pgi = sort_m.sort_pool(T(x), T(ei), T(w), T(gi), sort_index=1, **kw)
+        out.update({"sort_%s_x" % tag: px, "sort_%s_ei" % tag: pei, "sort_%s_w" % tag: pw, "sort_%s_gi" % tag: pgi})
+    parts = []
+    for i, size in enumerate((4, 1, 6)):
+        pe = graph(size, 3 * size, 40 + i, False) % size if size > 1 else np.zeros((2, 0), np.int32)
+        parts.append((rs.randn(size, 3).astype(np.float32), pe.astype(np.int32), rs.rand(pe.shape[1]).astype(np.float32),
+                      (np.arange(size) + 10 * i).astype(np.int32)))
+    bg = graph_m.BatchGraph.from_graphs([graph_m.Graph(T(px_), T(pe_), y=T(py_), edge_weight=T(pw_)) for px_, pe_, pw_, py_ in parts])
+    for i, (px_, pe_, pw_, py_) in enumerate(parts):
+        out.update({"part%d_x" % i: px_, "part%d_ei" % i: pe_, "part%d_w" % i: pw_, "part%d_y" % i: py_})
+    out.update(batch_x=bg.x, batch_ei=bg.edge_index, batch_w=bg.edge_weight, batch_y=bg.y, batch_gi=bg.node_graph_index,
+               batch_egi=bg.edge_graph_index)
+    save("graph", **out)
+
 
 if __name__ == "__main__":
     main()

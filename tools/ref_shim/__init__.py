@@ -65,6 +65,8 @@ def build_tensorflow():
     tf.reduce_max = lambda x, axis=None: _red(np.max, x, axis)
     tf.reduce_any = lambda x, axis=None: bool(np.any(np.asarray(x)))
     tf.reduce_min = lambda x, axis=None: _red(np.min, x, axis)
+    tf.TensorSpec = lambda shape=None, dtype=None, name=None: (shape, dtype)
+    tf.cond = lambda pred, true_fn, false_fn: true_fn() if bool(pred) else false_fn()
     tf.squeeze = lambda x, axis=None: T(np.squeeze(np.asarray(x), axis=axis))
     tf.minimum = lambda a, b: T(np.minimum(np.asarray(a), np.asarray(b)))
     tf.greater_equal = lambda a, b: T(np.greater_equal(np.asarray(a), np.asarray(b)))
@@ -138,6 +140,11 @@ def build_tensorflow():
     class SparseTensor(object):
         pass
     sparse.SparseTensor = SparseTensor
+    tf.SparseTensor = SparseTensor
+
+    class Variable(object):
+        pass
+    tf.Variable = Variable
     sparse.__getattr__ = lambda name: _unsupported("tf.sparse." + name)
     tf.sparse = sparse
     tf.__getattr__ = lambda name: _unsupported("tf." + name)
