@@ -1,7 +1,13 @@
 # coding=utf-8
-"""tfg.layers.MapReduceGNN (reference layers/kernel/map_reduce.py:6-46): subclass and override map / reduce / update;
-the call runs aggregate_neighbors with them.  Stock reducers (tfg.nn.sum_reducer / mean_reducer / max_reducer) returned from
-`reduce` still land on the segment kernel; arbitrary `map` callables take the gather route."""
+"""tfg.layers.MapReduceGNN (reference layers/kernel/map_reduce.py:6-46): a layer defined by three overridable hooks.
+
+    class Mine(tfg.layers.MapReduceGNN):
+        def map(self, repeated_x, neighbor_x, edge_weight=None): ...      # per-edge message
+        def reduce(self, neighbor_msg, node_index, num_nodes=None): ...   # per-node reduction, e.g. tfg.nn.mean_reducer(...)
+        def update(self, x, reduced_neighbor_msg): ...                    # combine with the node's own features
+
+Calling the layer on [x, edge_index, edge_weight] runs aggregate_neighbors with the hooks.  User-defined `map` code takes
+the gather route; a stock reducer called from `reduce` still lands on the segment kernel."""
 import torch
 
 from ..nn.kernel.map_reduce import aggregate_neighbors
@@ -10,29 +16,24 @@ from ..nn.kernel.map_reduce import aggregate_neighbors
 class MapReduceGNN(torch.nn.Module):
 
     def map(self, repeated_x, neighbor_x, edge_weight=None):
-        pass
+        raise NotImplementedError("override map()")
 
     def reduce(self, neighbor_msg, node_index, num_nodes=None):
-        pass
+        raise NotImplementedError("override reduce()")
 
     def update(self, x, reduced_neighbor_msg):
-        pass
+        raise NotImplementedError("override update()")
 
+    # the reference also hands the hooks out as plain callables
     def get_mapper(self):
-        def mapper(repeated_x, neighbor_x, edge_weight=None):
-            return self.map(repeated_x, neighbor_x, edge_weight)
-        return mapper
+        return self.map
 
     def get_reducer(self):
-        def reducer(neighbor_msg, node_index, num_nodes=None):
-            return self.reduce(neighbor_msg, node_index, num_nodes)
-        return reducer
+        return self.reduce
 
     def get_updater(self):
-        def updater(x, reduced_neighbor_msg):
-            return self.update(x, reduced_neighbor_msg)
-        return updater
+        return self.update
 
     def forward(self, inputs, training=None, mask=None):
         x, edge_index, edge_weight = inputs
-        return aggregate_neighbors(x, edge_index, edge_weight, self.get_mapper(), self.get_reducer(), self.get_updater())
+        return aggregate_neighbors(x, edge_index, edge_weight, mapper=self.map, reducer=self.reduce, updater=self.update)

@@ -5,8 +5,7 @@ import torch
 
 from ...nn.pool.common_pool import mean_pool, sum_pool, max_pool, min_pool
 from ...nn.pool.set2set import set2set
-from ...nn.pool.sag_pool import sag_pool
-from ...nn.pool.sort_pool import sort_pool
+from ...nn.pool.score_pool import sag_pool, sort_pool
 from .._base import Layer
 
 

@@ -1,1 +1,2 @@
 # coding=utf-8
+from . import gcn, gat, graph_sage, appnp, propagation

@@ -1,1 +1,2 @@
 # coding=utf-8
+from . import map_reduce, segment

@@ -1,2 +1,2 @@
 # coding=utf-8
-from .drop_edge import drop_edge
+from . import drop_edge
