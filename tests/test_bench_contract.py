@@ -43,3 +43,13 @@ def test_reference_arm_under_torchrun_only_rank0_speaks():
                           "--steps", "1", "--warmup", "1"], cwd=ROOT, capture_output=True, text=True, timeout=900, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     _check_line(out.stdout, 2)
+
+
+def test_gpu_arm_refuses_to_run_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a GPU is present")
+    out = subprocess.run([sys.executable, "bench.py", "--steps", "1", "--warmup", "1"], cwd=ROOT, capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode != 0 and out.stdout.strip() == "" and "no CPU fallback" in out.stderr
