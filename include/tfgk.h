@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TFGK_ABI_VERSION 4
+#define TFGK_ABI_VERSION 5
 
 enum tfgk_status {
     TFGK_OK = 0,
@@ -174,6 +174,46 @@ int tfgk_gemm_workspace_bytes(int32_t M, int32_t N, int32_t K, size_t *out_bytes
 int tfgk_gemm_f32(const float *A, int64_t lda, int transA, const float *B, int64_t ldb, int transB,
                   const float *bias, int act, float beta, int32_t M, int32_t N, int32_t K,
                   float *C, int64_t ldc, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Several projections of the same input in ONE launch (round 2): for every column block b < n_blocks
+ *   C_b[M, ncols_b] = act_b( A[M, K] @ B_b[K, ncols_b] + bias_b ),   ncols_b <= 128, n_blocks <= 4,
+ * e.g. the three projections of gat.py:52,61,70 (Q | K | V) or gcn.py:272 next to them; A is read from HBM once.
+ * Same 3xTF32 tcgen05 arithmetic as tfgk_gemm_f32's tensor-core path (bit-identical results).
+ * A may live in n_parts <= 8 row blocks of part_rows rows each (a multiple of 128 when n_parts > 1), part i at
+ * A_parts[i]: with the other ranks' buffers mapped through tfgk_peer_open this is the fused all-gather -> GEMM of the
+ * partitioned path (rows are pulled over NVLink tile by tile while earlier tiles are multiplied); the walk starts at
+ * part first_part so that concurrent ranks read from different peers.  max_ctas > 0 bounds the grid (to share the GPU
+ * with a kernel on another stream).  Returns TFGK_ERR_UNSUPPORTED when the shape does not qualify (K > 512, unaligned A,
+ * W too large for shared memory): the caller then uses tfgk_gemm_f32 per block. */
+typedef struct tfgk_proj_block {
+    const float *B; int64_t ldb;       /* [K, ncols] row-major weights */
+    int32_t ncols;
+    const float *bias;                 /* [ncols] or NULL */
+    int act;                           /* tfgk_act */
+    float *C; int64_t ldc;             /* [M, ncols] output (may be a column slice of a wider buffer) */
+} tfgk_proj_block;
+int tfgk_gemm_proj_f32(const float *const *A_parts, int32_t n_parts, int64_t part_rows, int64_t lda,
+                       int32_t M, int32_t K, const tfgk_proj_block *blocks, int32_t n_blocks,
+                       int32_t first_part, int32_t max_ctas, void *stream);
+
+/* ---- K5: peer memory for the partitioned path ---------------------------------------------------
+ * The ONE exception to "the library never allocates": buffers that other ranks on the same node read over NVLink
+ * must come from cudaMalloc so that they can be exported with CUDA IPC (PyTorch's caching allocator sub-allocates).
+ *   tfgk_peer_alloc / _free    device buffer on the current device (zero-initialised)
+ *   tfgk_peer_export           64-byte IPC handle of a buffer from tfgk_peer_alloc (sent to the other ranks by the host)
+ *   tfgk_peer_open / _close    map another process's buffer into this process (peer access enabled lazily)
+ *   tfgk_peer_barrier          device-side barrier over NVLink on `stream`: thread j stores `value` into slot `rank` of
+ *                              rank j's flag array (flags[j], uint32[world], from tfgk_peer_open) after a system-scope
+ *                              fence, then waits until slot j of the local array reaches `value` (values grow by one per
+ *                              barrier).  Traps instead of hanging if a peer does not arrive within timeout_ms.
+ * The reference has no counterpart (its multi-GPU demos replicate the graph, demo/demo_distributed_gcn.py:37-57). */
+#define TFGK_PEER_HANDLE_BYTES 64
+int tfgk_peer_alloc(size_t bytes, void **ptr);
+int tfgk_peer_free(void *ptr);
+int tfgk_peer_export(void *ptr, void *handle_out);
+int tfgk_peer_open(const void *handle, void **ptr);
+int tfgk_peer_close(void *ptr);
+int tfgk_peer_barrier(uint32_t *const *flags, int32_t rank, int32_t world, uint32_t value, int32_t timeout_ms, void *stream);
 
 /* tf.nn.l2_normalize(x, axis=-1) (graph_sage.py:57-58): out = x * rsqrt(max(sum(x^2), 1e-12)). */
 int tfgk_l2_normalize_f32(const float *x, int64_t ldx, int32_t N, int32_t D, float *out, int64_t ldo, void *stream);

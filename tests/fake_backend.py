@@ -123,6 +123,17 @@ def install(monkeypatch):
             return out
         return res
 
+    def gemm_proj(a, blocks, a_parts=None, part_rows=0, first_part=0, max_ctas=0, num_rows=None):
+        assert a_parts is None, "peer-mapped inputs need a GPU"
+        outs = []
+        for w, bias, act, out in blocks:
+            res = gemm(a if num_rows is None else a[:num_rows], w, bias=bias, act=act)
+            if out is not None:
+                out.copy_(res)
+                res = out
+            outs.append(res)
+        return outs
+
     def l2_normalize(x, out=None):
         return _t(o.l2_normalize(_np(x)))
 
@@ -198,5 +209,5 @@ def install(monkeypatch):
     for name, fn in dict(self_loops=self_loops, self_loop_weights=self_loop_weights, segment_count=segment_count,
                          csr_build=csr_build, permute=permute, csr_rowsum=csr_rowsum, deg_inv=deg_inv,
                          scale_edges=scale_edges, spmm=spmm, segment_softmax_csr=segment_softmax_csr,
-                         gat_fused=gat_fused, gemm=gemm, l2_normalize=l2_normalize).items():
+                         gat_fused=gat_fused, gemm=gemm, gemm_proj=gemm_proj, l2_normalize=l2_normalize).items():
         monkeypatch.setattr(ops, name, fn)

@@ -58,6 +58,20 @@ def _worker(rank, world, port, n, seed, renorm, queue):
         if renorm:      # the overlapped step uses the default normalisation
             assert np.array_equal(both[0].numpy(), gcn_local.numpy())
         assert np.array_equal(both[1].numpy(), gat_local.numpy())
+        # the same through tfg.layers with [x_local, partitioned_graph] inputs, alone and with one shared publication
+        import tf_geometric_b200 as tfg
+        gcn_l = tfg.layers.GCN(u, activation=ops.relu, renorm=renorm, seed=2)
+        gat_l = tfg.layers.GAT(u, num_heads=heads, activation=ops.relu, seed=3)
+        xl = torch.from_numpy(x_local)
+        alone = gcn_l([xl, pg]), gat_l([xl, pg])
+        shared = pg.share(xl, [gcn_l, gat_l])
+        assert len(shared.projected) == 2
+        together = gcn_l([shared, pg]), gat_l([shared, pg])
+        want = (tdist.gcn_partitioned(pg, x_local, gcn_l.kernel, gcn_l.bias, ops.relu, renorm=renorm),
+                tdist.gat_partitioned(pg, x_local, gat_l.query_kernel, gat_l.query_bias, ops.relu, gat_l.key_kernel,
+                                      gat_l.key_bias, ops.relu, gat_l.kernel, gat_l.bias, ops.relu, num_heads=heads))
+        for got in (alone, together):
+            assert np.array_equal(got[0].numpy(), want[0].numpy()) and np.array_equal(got[1].numpy(), want[1].numpy())
         queue.put((rank, p.lo, p.hi, gcn_local.numpy(), gat_local.numpy()))
         dist.barrier()
     finally:

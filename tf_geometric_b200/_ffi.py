@@ -12,7 +12,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "lib
 _lock = threading.Lock()
 _lib = None
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 OK = 0
 ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED, ERR_INDEX_OUT_OF_RANGE = 1, 2, 3, 4, 5
@@ -58,6 +58,13 @@ SIGNATURES = {
     "tfgk_gemm_workspace_bytes": [_i32, _i32, _i32, ctypes.POINTER(_size)],
     "tfgk_gemm_f32": [_ptr, _i64, _int, _ptr, _i64, _int, _ptr, _int, _f32, _i32, _i32, _i32, _ptr, _i64, _ptr, _size,
                       _ptr],
+    "tfgk_gemm_proj_f32": [_ptr, _i32, _i64, _i64, _i32, _i32, _ptr, _i32, _i32, _i32, _ptr],
+    "tfgk_peer_alloc": [_size, ctypes.POINTER(_ptr)],
+    "tfgk_peer_free": [_ptr],
+    "tfgk_peer_export": [_ptr, _ptr],
+    "tfgk_peer_open": [_ptr, ctypes.POINTER(_ptr)],
+    "tfgk_peer_close": [_ptr],
+    "tfgk_peer_barrier": [_ptr, _i32, _i32, _u32, _i32, _ptr],
     "tfgk_l2_normalize_f32": [_ptr, _i64, _i32, _i32, _ptr, _i64, _ptr],
     "tfgk_dropout_f32": [_ptr, _i64, _f32, _u64, _u32, _ptr, _ptr],
     "tfgk_spmm_heads_f32": [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _i32, _int, _f32, _u64, _u32, _f32, _ptr,
@@ -81,6 +88,14 @@ class PlanStruct(ctypes.Structure):
     _fields_ = [("n_tasks", _i32), ("n_hubs", _i32), ("n_slots", _i32), ("chunk", _i32),
                 ("task_row", _ptr), ("task_nrows", _ptr), ("task_e0", _ptr), ("task_e1", _ptr), ("task_slot", _ptr),
                 ("hub_row", _ptr), ("hub_slot0", _ptr), ("hub_nslots", _ptr), ("scratch", _ptr), ("scratch_bytes", _size)]
+
+
+class ProjBlock(ctypes.Structure):
+    """struct tfgk_proj_block of include/tfgk.h."""
+    _fields_ = [("B", _ptr), ("ldb", _i64), ("ncols", _i32), ("bias", _ptr), ("act", _int), ("C", _ptr), ("ldc", _i64)]
+
+
+PEER_HANDLE_BYTES = 64
 
 
 class TfgkError(RuntimeError):

@@ -1,0 +1,338 @@
+// K4 (round 2): the dense projections of the hot path as ONE launch over several column blocks, optionally with the A
+// operand gathered tile by tile from other GPUs' memory (fused all-gather -> GEMM over NVLink peer mappings, K5).
+//
+//   C_b[M, n_b] = act_b(A[M, K] @ W_b[K, n_b] + bias_b)     for b in 0..nb-1  (n_b <= 128, nb <= 4)
+//
+// replaces x@W at nn/conv/gcn.py:272 and the three projections x@Wq, x@Wk, x@W of nn/conv/gat.py:52,61,70, which the
+// round-1 path ran as three launches that each re-read x.  Differences from gemm_tc.cu (same 3xTF32 arithmetic, same bits):
+//   * column blocks: CTA b handles block b % nb for the row tiles of its group b / nb; the nb CTAs of a group walk the
+//     same tiles in the same order, so x is read from HBM once and from L2 nb-1 times (A traffic is 4(MK), not 4 nb MK);
+//   * W_b (hi | lo) resident in shared memory for K rounded up to 8 (not 32), the MMA issuer skips the UMMA_K steps
+//     beyond K and the producers skip the 16-byte chunks beyond it: K = 100 costs 13 k-steps instead of 16;
+//   * epilogue through shared memory: tcgen05.ld 32 columns per round trip -> +bias -> act -> per-warp staging tile ->
+//     full 128-byte row segments per store instruction (the round-1 epilogue wrote 16 bytes per row per instruction);
+//   * A may be split into `n_parts` row blocks living at different base pointers (the other ranks' copies of x, mapped
+//     through CUDA IPC): the producers' cp.async then read straight over NVLink, tile by tile, while the tensor core
+//     works on the previous tiles - no halo buffer for x, no separate exchange step.  Tiles are walked starting at part
+//     `first_part` so that every rank pulls from a different peer at any moment.
+#include "common.cuh"
+#include "tfgk_tc.cuh"
+
+namespace tfgk {
+namespace proj {
+
+using namespace tc;
+
+constexpr int kMaxBlocks = 4;
+constexpr int kMaxParts = 8;
+constexpr int kProducerWarps = 4, kEpilogueWarps = 4;
+constexpr int kThreadsProj = (kProducerWarps + kEpilogueWarps + 1) * 32;      // 288
+constexpr int kUN = 128;                 // accumulator columns per buffer
+constexpr int kTmemColsProj = 256;       // 2 accumulator buffers
+constexpr int kStageRowBytes = 144;      // 32 floats + 16 B pad: conflict-free for row-wise STS.128 and segment-wise LDS.128
+constexpr int kStageBytes = 32 * kStageRowBytes;
+
+struct Params {
+    const float *A[kMaxParts];
+    int64_t lda, part_rows;
+    int n_parts, first_tile;
+    int M, K, nb, tiles_m, n_groups;
+    const float *B[kMaxBlocks]; int64_t ldb[kMaxBlocks];
+    const float *bias[kMaxBlocks]; int act[kMaxBlocks]; int ncols[kMaxBlocks];
+    float *C[kMaxBlocks]; int64_t ldc[kMaxBlocks];
+};
+
+struct Plan {
+    uint32_t kpad8, b_bytes, a_stage_bytes, stages, total;
+    __host__ __device__ explicit Plan(int K) {
+        kpad8 = (uint32_t)((K + 7) / 8) * 8;
+        b_bytes = (uint32_t)kUN * kpad8 * 4u;
+        a_stage_bytes = 2u * BM * BK * 4u;
+        const uint32_t fixed = 2u * b_bytes + kEpilogueWarps * kStageBytes + 128u + kUN * 4u;
+        const uint32_t budget = 227u * 1024u;
+        stages = 0;
+        for (uint32_t st = 4; st >= 2; --st)
+            if (fixed + st * a_stage_bytes <= budget) { stages = st; break; }
+        total = fixed + stages * a_stage_bytes;
+    }
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(kThreadsProj, 1) gemm_proj_kernel(const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const Plan L(p.K);
+    uint8_t *b_hi_ptr = smem, *b_lo_ptr = smem + L.b_bytes;
+    uint8_t *a_ring = smem + 2 * L.b_bytes;
+    uint8_t *stage_base = a_ring + STAGES * L.a_stage_bytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(stage_base + kEpilogueWarps * kStageBytes);
+    uint64_t *empty = full + STAGES, *acc_full = empty + STAGES, *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    float *s_bias = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(full) + 128);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int cb = (int)blockIdx.x % p.nb, group = (int)blockIdx.x / p.nb;
+    const int ncols = p.ncols[cb];
+    const int un = ((ncols + 15) / 16) * 16;
+    const float *__restrict__ Bm = p.B[cb];
+    const int64_t ldb = p.ldb[cb];
+
+    for (int i = t; i < kUN; i += kThreadsProj) s_bias[i] = (p.bias[cb] != nullptr && i < ncols) ? __ldg(p.bias[cb] + i) : 0.0f;
+    if (t == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], kProducerWarps); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpilogueWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemColsProj) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {   // W_b: transpose + RNA split into the K-major core-matrix layout, once per CTA
+        const int kchunks = (int)L.kpad8 / 4;
+        const int total = un * kchunks;
+        const uint32_t bh = smem_u32(b_hi_ptr), bl = smem_u32(b_lo_ptr);
+        for (int c = t; c < total; c += kThreadsProj) {
+            const int n8 = c & 7, kc = (c >> 3) % kchunks, ng = (c >> 3) / kchunks;
+            const int n = ng * 8 + n8, k = kc * 4;
+            float w[4] = {0.f, 0.f, 0.f, 0.f}, h[4], l[4];
+            if (n < ncols) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (k + i < p.K) w[i] = __ldg(Bm + (int64_t)(k + i) * ldb + n);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_tf32(w[i], h[i], l[i]);
+            st_shared_v4(bh + c * 16, h[0], h[1], h[2], h[3]);
+            st_shared_v4(bl + c * 16, l[0], l[1], l[2], l[3]);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nkb = (int)(L.kpad8 + BK - 1) / BK;
+    const int last_steps = ((int)L.kpad8 - (nkb - 1) * BK) / UMMA_K;
+    const int my_tiles = group < p.tiles_m ? (p.tiles_m - 1 - group) / p.n_groups + 1 : 0;
+    const int total_kb = my_tiles * nkb;
+    // logical tile i of this group -> physical row tile (rotated so that ranks start on different parts)
+    auto tile_of = [&](int it) {
+        int tl = group + it * p.n_groups + p.first_tile;
+        return tl >= p.tiles_m ? tl - p.tiles_m : tl;
+    };
+
+    if (warp < kProducerWarps) {
+        // ===================== producers: cp.async A (possibly from a peer GPU) -> UMMA layout, lo = a - trunc(a) =====================
+        const uint32_t a_ring_addr = smem_u32(a_ring);
+        constexpr int kChunks = (BM * BK / 4) / (kProducerWarps * 32);      // 8 per thread per k-block
+        const int r8 = t & 7, kc = (t >> 3) & 7, rg0 = t >> 6;              // chunk c = t + 128 i: rows (rg0 + 2 i) * 8 + r8
+        auto issue_load = [&](int G) {
+            if (G < total_kb) {
+                const int stage = G % STAGES;
+                mbar_wait(&empty[stage], (uint32_t)(((G / STAGES) & 1) ^ 1));
+                const int tile = tile_of(G / nkb), kb = G % nkb;
+                const int k = kb * BK + kc * 4;
+                if (k < (int)L.kpad8) {
+                    const int64_t m0 = (int64_t)tile * BM;
+                    const int part = p.n_parts > 1 ? (int)(m0 / p.part_rows) : 0;
+                    const float *base = p.A[part] + (m0 - (int64_t)part * p.part_rows) * p.lda + k;
+                    const uint32_t kbytes = k < p.K ? (uint32_t)min(4, p.K - k) * 4u : 0u;
+                    const uint32_t dst0 = a_ring_addr + stage * L.a_stage_bytes + (uint32_t)t * 16u;
+#pragma unroll
+                    for (int i = 0; i < kChunks; ++i) {
+                        const int rl = (rg0 + 2 * i) * 8 + r8;
+                        const bool ok = m0 + rl < p.M;
+                        cp_async16_zfill(dst0 + (uint32_t)i * 2048u, ok ? base + (int64_t)rl * p.lda : p.A[0], ok ? kbytes : 0u);
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+#pragma unroll
+        for (int G = 0; G < STAGES - 1; ++G) issue_load(G);
+        for (int G = 0; G < total_kb; ++G) {
+            issue_load(G + STAGES - 1);
+            asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+            const int stage = G % STAGES, kb = G % nkb;
+            if (kb * BK + kc * 4 < (int)L.kpad8) {
+                uint8_t *sraw = a_ring + stage * L.a_stage_bytes + t * 16;
+#pragma unroll
+                for (int i = 0; i < kChunks; ++i) {
+                    const float4 v = *reinterpret_cast<const float4 *>(sraw + i * 2048);
+                    float4 l;
+                    l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                    l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                    l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                    l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                    *reinterpret_cast<float4 *>(sraw + BM * BK * 4 + i * 2048) = l;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[stage]);
+        }
+    } else if (warp == kProducerWarps + kEpilogueWarps) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(un);
+            const uint32_t sbo_b = (L.kpad8 / 4) * 128u;
+            for (int G = 0; G < total_kb; ++G) {
+                const int stage = G % STAGES, it = G / nkb, kb = G % nkb, buf = it & 1;
+                if (kb == 0) mbar_wait(&acc_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
+                mbar_wait(&full[stage], (uint32_t)((G / STAGES) & 1));
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kUN);
+                const uint32_t a_raw = smem_u32(a_ring + stage * L.a_stage_bytes), a_lo = a_raw + BM * BK * 4;
+                const uint32_t b_hi = smem_u32(b_hi_ptr) + (uint32_t)kb * (BK / 4) * 128u, b_lo = b_hi + L.b_bytes;
+                const int steps = kb == nkb - 1 ? last_steps : BK / UMMA_K;
+                for (int j = 0; j < steps; ++j) {
+                    const uint32_t off = (uint32_t)j * 2u * 128u;
+                    const uint64_t dah = make_desc_sbo(a_raw + off, 1024u), dal = make_desc_sbo(a_lo + off, 1024u);
+                    const uint64_t dbh = make_desc_sbo(b_hi + off, sbo_b), dbl = make_desc_sbo(b_lo + off, sbo_b);
+                    umma_tf32(d_tmem, dal, dbh, idesc, (kb | j) != 0);
+                    umma_tf32(d_tmem, dah, dbl, idesc, 1u);
+                    umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+                }
+                umma_commit(&empty[stage]);
+                if (kb == nkb - 1) umma_commit(&acc_full[buf]);
+            }
+        }
+    } else {
+        // ===================== epilogue: TMEM -> registers -> staging tile -> 128-byte row segments =====================
+        const int q = warp & 3;                               // TMEM lane quarter of this warp (warps 4..7 -> 0..3)
+        uint8_t *stg = stage_base + q * kStageBytes;
+        const uint32_t stg_addr = smem_u32(stg);
+        float *__restrict__ Cb = p.C[cb];
+        const int64_t ldc = p.ldc[cb];
+        const int act = p.act[cb];
+        const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cb) & 15) == 0);
+        const int seg_row = lane >> 3, seg_chunk = lane & 7;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int buf = it & 1;
+            const int tile = tile_of(it);
+            mbar_wait(&acc_full[buf], (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            const int64_t row0 = (int64_t)tile * BM + q * 32;
+            for (int c0 = 0; c0 < un; c0 += 32) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kUN + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                    "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c0 + 32 >= un) {                          // accumulator drained: the MMA issuer may reuse this buffer
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float v0 = apply_act(__uint_as_float(r[j]) + s_bias[c0 + j], act);
+                    const float v1 = apply_act(__uint_as_float(r[j + 1]) + s_bias[c0 + j + 1], act);
+                    const float v2 = apply_act(__uint_as_float(r[j + 2]) + s_bias[c0 + j + 2], act);
+                    const float v3 = apply_act(__uint_as_float(r[j + 3]) + s_bias[c0 + j + 3], act);
+                    st_shared_v4(stg_addr + (uint32_t)lane * kStageRowBytes + (uint32_t)j * 4u, v0, v1, v2, v3);
+                }
+                __syncwarp();
+                const int col = c0 + seg_chunk * 4;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int rl = j * 4 + seg_row;
+                    const int64_t row = row0 + rl;
+                    const float4 v = *reinterpret_cast<const float4 *>(stg + rl * kStageRowBytes + seg_chunk * 16);
+                    if (row < p.M) {
+                        float *dst = Cb + row * ldc + col;
+                        if (vec_ok && col + 4 <= ncols) {
+                            *reinterpret_cast<float4 *>(dst) = v;
+                        } else {
+                            if (col < ncols) dst[0] = v.x;
+                            if (col + 1 < ncols) dst[1] = v.y;
+                            if (col + 2 < ncols) dst[2] = v.z;
+                            if (col + 3 < ncols) dst[3] = v.w;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemColsProj) : "memory");
+    }
+}
+
+template <int STAGES>
+static int launch(const Params &p, int grid, uint32_t smem_bytes, cudaStream_t st) {
+    static int configured[16] = {0};       // cudaFuncSetAttribute once per device, not per call
+    int dev = 0;
+    TFGK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16 || configured[dev] < (int)smem_bytes) {
+        TFGK_CUDA(cudaFuncSetAttribute(gemm_proj_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        if (dev >= 0 && dev < 16) configured[dev] = (int)smem_bytes;
+    }
+    gemm_proj_kernel<STAGES><<<grid, kThreadsProj, smem_bytes, st>>>(p);
+    TFGK_LAUNCH_CHECK();
+    return TFGK_OK;
+}
+
+}  // namespace proj
+}  // namespace tfgk
+
+using namespace tfgk;
+
+extern "C" int tfgk_gemm_proj_f32(const float *const *A_parts, int32_t n_parts, int64_t part_rows, int64_t lda,
+                                  int32_t M, int32_t K, const tfgk_proj_block *blocks, int32_t n_blocks,
+                                  int32_t first_part, int32_t max_ctas, void *stream) {
+    TFGK_CHECK_ARG(A_parts != nullptr && blocks != nullptr, "gemm_proj: null argument");
+    TFGK_CHECK_ARG(n_parts >= 1 && n_parts <= proj::kMaxParts, "gemm_proj: n_parts=%d not in [1, %d]", n_parts, proj::kMaxParts);
+    TFGK_CHECK_ARG(n_blocks >= 1 && n_blocks <= proj::kMaxBlocks, "gemm_proj: n_blocks=%d not in [1, %d]", n_blocks, proj::kMaxBlocks);
+    TFGK_CHECK_ARG(M >= 0 && K >= 1, "gemm_proj: bad size (M=%d, K=%d)", M, K);
+    TFGK_CHECK_ARG(first_part >= 0 && first_part < n_parts, "gemm_proj: first_part=%d out of range", first_part);
+    if (M == 0) return TFGK_OK;
+    if (n_parts > 1)
+        TFGK_CHECK_ARG(part_rows > 0 && part_rows % tc::BM == 0 && (int64_t)n_parts * part_rows >= M,
+                       "gemm_proj: part_rows=%lld must be a positive multiple of %d covering M=%d", (long long)part_rows, tc::BM, M);
+    if (K > 512 || (lda % 4) != 0 || lda < K) return TFGK_ERR_UNSUPPORTED;        // same accuracy bound as gemm_tc.cu
+    proj::Params p;
+    for (int i = 0; i < proj::kMaxParts; ++i) {
+        p.A[i] = A_parts[i < n_parts ? i : 0];
+        if (!aligned16(p.A[i]) || p.A[i] == nullptr) return i < n_parts && A_parts[i] == nullptr
+            ? set_error(TFGK_ERR_INVALID_ARGUMENT, "gemm_proj: A part %d is null", i) : TFGK_ERR_UNSUPPORTED;
+    }
+    p.lda = lda; p.part_rows = n_parts > 1 ? part_rows : (int64_t)1 << 40; p.n_parts = n_parts;
+    p.M = M; p.K = K; p.nb = n_blocks;
+    p.tiles_m = (int)ceil_div64(M, tc::BM);
+    p.first_tile = n_parts > 1 ? (int)((int64_t)first_part * part_rows / tc::BM) : 0;
+    if (p.first_tile >= p.tiles_m) p.first_tile = 0;
+    for (int b = 0; b < proj::kMaxBlocks; ++b) {
+        const tfgk_proj_block &blk = blocks[b < n_blocks ? b : 0];
+        if (b < n_blocks) {
+            TFGK_CHECK_ARG(blk.B != nullptr && blk.C != nullptr, "gemm_proj: block %d has a null operand", b);
+            TFGK_CHECK_ARG(blk.ncols >= 1 && blk.ldb >= blk.ncols && blk.ldc >= blk.ncols, "gemm_proj: block %d has bad sizes", b);
+            TFGK_CHECK_ARG(blk.act == TFGK_ACT_NONE || blk.act == TFGK_ACT_RELU, "gemm_proj: unknown activation %d", blk.act);
+            if (blk.ncols > proj::kUN) return TFGK_ERR_UNSUPPORTED;
+        }
+        p.B[b] = blk.B; p.ldb[b] = blk.ldb; p.bias[b] = blk.bias; p.act[b] = blk.act; p.ncols[b] = blk.ncols;
+        p.C[b] = blk.C; p.ldc[b] = blk.ldc;
+    }
+    const proj::Plan L(K);
+    if (L.stages == 0) return TFGK_ERR_UNSUPPORTED;
+    int dev = 0, sms = 0;
+    TFGK_CUDA(cudaGetDevice(&dev));
+    TFGK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
+    int n_groups = sms / n_blocks;
+    if (n_groups < 1) n_groups = 1;
+    if (n_groups > p.tiles_m) n_groups = p.tiles_m;
+    p.n_groups = n_groups;
+    const int grid = n_groups * n_blocks;
+    cudaStream_t st = as_stream(stream);
+    if (L.stages >= 4) return proj::launch<4>(p, grid, L.total, st);
+    if (L.stages == 3) return proj::launch<3>(p, grid, L.total, st);
+    return proj::launch<2>(p, grid, L.total, st);
+}

@@ -11,22 +11,40 @@ tf.distribute.MirroredStrategy, demo/demo_distributed_gcn.py:37-57); this is the
   * softmax / mean / max are per destination, so nothing is reduced across ranks; the GCN normalisation exchanges only
     the [N] vector of deg^-1/2.
 Per-row edge order is the caller's order, so every output row is bit-identical to the single-GPU result.
+
+Round 2 - how the source rows reach a rank (the exchange step):
+  * "p2p" (default on GPUs of one node): NO collective on the data path.  Every rank publishes its rows of x in a
+    peer-mapped buffer (peer.RowExchange: one device-to-device copy + a device-side flag barrier over NVLink) and the
+    dense projections of ALL rows are computed by one tcgen05 launch whose A tiles are pulled straight from the owning
+    rank's memory (tfgk_gemm_proj_f32 with a_parts): a fused all-gather -> GEMM.  Because x is narrower than what is
+    aggregated (F = 100 against 128 + 256 projected columns in the bench) this moves 3.8x fewer bytes over NVLink than
+    shipping projected rows, and the projections replicated on every rank are cheap tensor-core work hidden under the
+    transfer.  Rows are identical to the ones the owner would compute (row-local arithmetic, same kernel).
+  * "collective": the round-1 path - project the local rows, all-gather the projected rows (NCCL on GPUs, gloo in the
+    CPU tests); also the fallback when peer mappings cannot be set up.
+tfg.layers.GCN / GAT accept [x_local, partitioned_graph] (or the result of partitioned_graph.share(...)).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
 from . import ops
 from .ops import CSR  # noqa: F401
 
+ROW_ALIGN = 128       # partition blocks are multiples of the GEMM row tile, so a tile never straddles two owners
+
 
 class RowPartition(object):
     """Block partition of node ids: rank r owns [lo(r), hi(r))."""
 
-    def __init__(self, num_nodes, world_size, rank):
+    def __init__(self, num_nodes, world_size, rank, align=1):
         self.num_nodes = int(num_nodes)
         self.world_size = int(world_size)
         self.rank = int(rank)
         self.block = (self.num_nodes + self.world_size - 1) // self.world_size
+        if align > 1 and self.world_size > 1:
+            self.block = (self.block + align - 1) // align * align
         self.lo = min(self.rank * self.block, self.num_nodes)
         self.hi = min(self.lo + self.block, self.num_nodes)
         self.n_local = self.hi - self.lo
@@ -40,27 +58,34 @@ class PartitionedGraph(object):
     """The slice of a graph one rank works on: edges whose destination it owns, destinations renumbered locally,
     sources kept as GLOBAL ids (they index the all-gathered buffer)."""
 
-    def __init__(self, partition, local_edge_index, local_edge_weight=None, group=None):
+    def __init__(self, partition, local_edge_index, local_edge_weight=None, group=None, exchange=None):
         self.part = partition
         self.edge_index = local_edge_index          # int32 [2, E_local]: row in [0, n_local), col in [0, N)
         self.edge_weight = local_edge_weight
         self.group = group
         self.cache = {}
+        # "p2p" | "collective"; default: p2p on CUDA with more than one rank (TFGK_DIST_EXCHANGE overrides)
+        self.exchange = exchange or os.environ.get("TFGK_DIST_EXCHANGE") or (
+            "p2p" if local_edge_index.is_cuda and partition.world_size > 1 else "collective")
+        self._row_exchanges = {}
+        self.nvlink_bytes = 0                       # bytes pulled from / received from peers so far (accounting)
 
     @classmethod
-    def from_global(cls, edge_index, edge_weight, num_nodes, rank=None, world_size=None, group=None):
+    def from_global(cls, edge_index, edge_weight, num_nodes, rank=None, world_size=None, group=None, exchange=None):
         """Select this rank's in-edges from a full edge list (order preserved)."""
         rank = dist.get_rank(group) if rank is None else rank
         world_size = dist.get_world_size(group) if world_size is None else world_size
-        part = RowPartition(num_nodes, world_size, rank)
         edge_index = ops.as_device(edge_index, torch.int32)
+        exchange = exchange or os.environ.get("TFGK_DIST_EXCHANGE") or (
+            "p2p" if edge_index.is_cuda and world_size > 1 else "collective")
+        part = RowPartition(num_nodes, world_size, rank, align=ROW_ALIGN if exchange == "p2p" else 1)
         row = edge_index[0]
         mask = (row >= part.lo) & (row < part.hi)
         local = torch.stack([row[mask] - part.lo, edge_index[1][mask]]).contiguous()
         w = None
         if edge_weight is not None:
             w = ops.as_device(edge_weight, torch.float32, device=edge_index.device)[mask].contiguous()
-        return cls(part, local, w, group)
+        return cls(part, local, w, group, exchange)
 
     # ---- structure ------------------------------------------------------------------------------------------------
     def _with_self_loops(self, weight, fill):
@@ -114,6 +139,86 @@ class PartitionedGraph(object):
         return index, value
 
     # ---- the exchange step -----------------------------------------------------------------------------------------
+    def _row_exchange(self, width, device):
+        """peer.RowExchange for rows of `width` floats, created on first use; None when peer mappings are unavailable
+        on any rank (all ranks then agree on the collective path)."""
+        if width in self._row_exchanges:
+            return self._row_exchanges[width]
+        from . import peer, _ffi
+        ex, ok = None, 1
+        try:
+            ex = peer.RowExchange(self.part.block, width, device, self.group)
+        except (_ffi.TfgkError, RuntimeError) as err:
+            ok = 0
+            self._peer_error = str(err)
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            if ex is not None:
+                ex.close()
+            ex = None
+            self.exchange = "collective"
+        self._row_exchanges[width] = ex
+        return ex
+
+    def new_step(self):
+        """Forget which tensor was published last: the next layer call publishes its input again even if it is the same
+        tensor object (bench.py calls this so that every timed step pays for the full exchange protocol)."""
+        for ex in self._row_exchanges.values():
+            if ex is not None:
+                ex._published = None
+
+    def project_all_rows(self, x_local, groups):
+        """Dense projections of EVERY node's features, which each aggregation kernel then gathers from.
+        groups: list of column groups, each a list of (weight [F, n], bias or None, act code); the projections of one
+        group are laid side by side in one [padded_nodes, sum n] buffer (e.g. K | V).  Returns the list of buffers.
+        p2p: one fused all-gather -> GEMM launch per four 128-column blocks, A tiles pulled from the owning ranks;
+        collective: local projection + all-gather of the projected rows."""
+        p = self.part
+        dev = x_local.device
+        widths = [sum(int(w.shape[1]) for w, _, _ in g) for g in groups]
+        fused_ok = x_local.shape[1] % 4 == 0 and x_local.shape[1] <= 512 and x_local.is_cuda      # tfgk_gemm_proj_f32 limits
+        if p.world_size == 1 or self.exchange != "p2p" or not fused_ok \
+                or self._row_exchange(x_local.shape[1], dev) is None:
+            send = torch.empty((p.block, sum(widths)), dtype=torch.float32, device=dev)
+            if p.n_local < p.block:
+                send[p.n_local:].zero_()
+            _project_into(x_local, groups, send, p.n_local)
+            full = self.all_gather_rows(send)
+            if p.world_size > 1:
+                self.nvlink_bytes += (p.world_size - 1) * p.block * sum(widths) * 4
+            outs, c0 = [], 0
+            for wd in widths:
+                outs.append(full[:, c0:c0 + wd])
+                c0 += wd
+            return outs
+        ex = self._row_exchange(x_local.shape[1], dev)
+        slot = ex.publish(x_local)
+        outs = [torch.empty((p.padded_nodes, wd), dtype=torch.float32, device=dev) for wd in widths]
+        pieces = _pieces(groups, outs)
+        first = (p.rank + 1) % p.world_size
+        for i in range(0, len(pieces), 4):
+            ops.gemm_proj(ex.local_slot(slot), pieces[i:i + 4], a_parts=ex.slot_ptrs(slot), part_rows=p.block,
+                          first_part=first, num_rows=p.num_nodes)
+            self.nvlink_bytes += (p.num_nodes - p.n_local) * x_local.shape[1] * 4
+        return outs
+
+    def share(self, x_local, layers):
+        """Publish x_local once and compute, in ONE fused launch sequence, the all-row projections of every layer in
+        `layers` (tfg.layers.GCN / GAT ...).  Pass the result instead of x_local: layer([shared, partitioned_graph])."""
+        x_local = ops.as_device(x_local, torch.float32, device=self.edge_index.device)
+        shared = SharedRows(x_local, self)
+        groups, owners = [], []
+        for layer in layers:
+            layer._maybe_build([x_local])
+            for key, group in layer.partitioned_projections():
+                owners.append(key)
+                groups.append(group)
+        if groups:
+            for key, buf in zip(owners, self.project_all_rows(x_local, groups)):
+                shared.projected[key] = buf
+        return shared
+
     def all_gather_rows(self, local_rows, out=None, async_op=False):
         """[n_local, D] on every rank -> [R*B, D] indexed by global node id (rows >= N are padding).
         async_op=True returns (buffer, work): the collective runs on the communicator's stream and `work.wait()` makes the
@@ -126,20 +231,68 @@ class PartitionedGraph(object):
             out[:p.n_local].copy_(local_rows)
             return (out, None) if async_op else out
         send = local_rows
-        if p.n_local != p.block or not local_rows.is_contiguous():
+        if local_rows.shape[0] != p.block or not local_rows.is_contiguous():      # callers may pass block-padded rows
             send = torch.zeros((p.block, d), dtype=local_rows.dtype, device=local_rows.device)
-            send[:p.n_local].copy_(local_rows)
+            send[:local_rows.shape[0]].copy_(local_rows)
         work = dist.all_gather_into_tensor(out, send, group=self.group, async_op=async_op)
         return (out, work) if async_op else out
+
+
+def _pieces(groups, outs):
+    """(weight, bias, act, out view) per block of at most 128 columns, in buffer order."""
+    pieces = []
+    for group, out in zip(groups, outs):
+        c0 = 0
+        for w, b, act in group:
+            for k0 in range(0, w.shape[1], 128):
+                k1 = min(k0 + 128, w.shape[1])
+                pieces.append((w[:, k0:k1], None if b is None else b[k0:k1], act, out[:, c0 + k0:c0 + k1]))
+            c0 += w.shape[1]
+    return pieces
+
+
+def _project_into(x_local, groups, out, n_rows):
+    outs, c0 = [], 0
+    for g in groups:
+        wd = sum(int(w.shape[1]) for w, _, _ in g)
+        outs.append(out[:n_rows, c0:c0 + wd])
+        c0 += wd
+    pieces = _pieces(groups, outs)
+    for i in range(0, len(pieces), 4):
+        ops.gemm_proj(x_local, pieces[i:i + 4])
+
+
+class SharedRows(object):
+    """x_local plus the all-row projections computed for it by PartitionedGraph.share (keyed by weight identity)."""
+
+    def __init__(self, x_local, pg):
+        self.x, self.pg, self.projected = x_local, pg, {}
+        self.shape, self.device, self.is_cuda = x_local.shape, x_local.device, x_local.is_cuda
+
+    def __len__(self):
+        return self.shape[0]
+
+    def find(self, *weights):
+        return self.projected.get(tuple(id(w) for w in weights))
+
+
+def _unwrap(x_local, dev):
+    if isinstance(x_local, SharedRows):
+        return x_local.x, x_local
+    return ops.as_device(x_local, torch.float32, device=dev), None
 
 
 def gcn_partitioned(pg, x_local, kernel, bias=None, activation=None, renorm=True, improved=False):
     """tfg.nn.gcn on a PartitionedGraph: returns this rank's rows of act(norm(A) (x W) + b)."""
     dev = pg.edge_index.device
-    x_local = ops.as_device(x_local, torch.float32, device=dev)
+    x_local, shared = _unwrap(x_local, dev)
     csr, value_csr = pg.gcn_normed(renorm=renorm, improved=improved)
-    h_local = x_local if kernel is None else ops.gemm(x_local, ops.as_device(kernel, torch.float32, device=dev))
-    h_full = pg.all_gather_rows(h_local)
+    h_full = shared.find(kernel) if shared is not None and kernel is not None else None
+    if h_full is None:
+        if kernel is None:
+            h_full = pg.all_gather_rows(x_local)
+        else:
+            h_full = pg.project_all_rows(x_local, [[(ops.as_device(kernel, torch.float32, device=dev), None, ops.ACT_NONE)]])[0]
     act_code, leftover = ops.activation_code(activation)
     out = ops.spmm(csr, value_csr, h_full, reduce="sum",
                    bias=None if bias is None else ops.as_device(bias, torch.float32, device=dev), act=act_code)
@@ -151,22 +304,22 @@ def gat_partitioned(pg, x_local, query_kernel, query_bias, query_activation, key
     """tfg.nn.gat (split_value_heads=True) on a PartitionedGraph: Q stays local, K and V travel in ONE all-gather of a
     [n_local, A + U] buffer that both projections write into directly."""
     dev = pg.edge_index.device
-    x_local = ops.as_device(x_local, torch.float32, device=dev)
-    wq, wk, wv = (ops.as_device(t, torch.float32, device=dev) for t in (query_kernel, key_kernel, kernel))
+    x_local, shared = _unwrap(x_local, dev)
+    f32 = lambda t: None if t is None else ops.as_device(t, torch.float32, device=dev)   # noqa: E731
     q_act, q_left = ops.activation_code(query_activation)
     k_act, k_left = ops.activation_code(key_activation)
     if q_left is not None or k_left is not None:
         raise NotImplementedError("partitioned GAT supports relu / None for the query and key activations")
-    a, u = wq.shape[1], wv.shape[1]
-    n_local = x_local.shape[0]
-    Q = ops.gemm(x_local, wq, bias=ops.as_device(query_bias, torch.float32, device=dev), act=q_act)
-    kv_local = torch.empty((n_local, a + u), dtype=torch.float32, device=dev)
-    ops.gemm(x_local, wk, bias=ops.as_device(key_bias, torch.float32, device=dev), act=k_act, out=kv_local[:, :a])
-    ops.gemm(x_local, wv, out=kv_local[:, a:])
-    kv_full = pg.all_gather_rows(kv_local)
+    kv_full = shared.find(key_kernel, kernel) if shared is not None else None
+    wq, wk, wv = f32(query_kernel), f32(key_kernel), f32(kernel)
+    a = wk.shape[1]
+    if kv_full is None:
+        kv_full = pg.project_all_rows(x_local, [[(wk, f32(key_bias), k_act), (wv, None, ops.ACT_NONE)]])[0]
+    Q = torch.empty((x_local.shape[0], wq.shape[1]), dtype=torch.float32, device=dev)
+    _project_into(x_local, [[(wq, f32(query_bias), q_act)]], Q, x_local.shape[0])
     act_code, leftover = ops.activation_code(activation)
     out = ops.gat_fused(pg.csr(self_loops=True), Q, kv_full[:, :a], kv_full[:, a:], num_heads,
-                        bias=None if bias is None else ops.as_device(bias, torch.float32, device=dev), act=act_code)
+                        bias=None if bias is None else f32(bias), act=act_code)
     return leftover(out) if leftover is not None else out
 
 
@@ -207,13 +360,45 @@ def gcn_gat_overlapped(pg, x_local, gcn_kernel, gcn_bias, gcn_activation,
 
 # ---- bench.py --gpus N ------------------------------------------------------------------------------------------------
 
+def _sampled_row_check(pg, edge_index_global, n, x_hosts, gcn, gat, out_gcn, out_gat, heads, samples=48):
+    """Independent float64 restatement (plain torch on the device, no kernel of this library) of GCN and GAT for a few
+    of this rank's rows, from the GLOBAL edge list and the features of every rank: guards the path that is timed."""
+    p = pg.part
+    dev = out_gcn.device
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(7 + p.rank)
+    rows = (torch.randint(0, max(p.n_local, 1), (samples,), generator=gen) + p.lo).to(dev)
+    row_g, col_g = edge_index_global[0].long(), edge_index_global[1].long()
+    deg = torch.bincount(row_g, minlength=n).double() + 1.0                   # renormalised: A + I
+    x_all = torch.cat([h.to(dev) for h in x_hosts]).double()
+    w_gcn = gcn.kernel.double()
+    wq, wk, wv = gat.query_kernel.double(), gat.key_kernel.double(), gat.kernel.double()
+    worst = 0.0
+    for r in rows.tolist():
+        nb = torch.cat([col_g[row_g == r], torch.tensor([r], device=dev)])
+        # GCN: relu(sum_j d_r^-1/2 d_j^-1/2 (x_j W) + b)
+        coef = (deg[r] ** -0.5) * (deg[nb] ** -0.5)
+        want = torch.relu((coef[:, None] * (x_all[nb] @ w_gcn)).sum(0) + gcn.bias.double())
+        got = out_gcn[r - p.lo].double()
+        worst = max(worst, float(((got - want).abs() / (want.abs() + 1e-4 * want.abs().max() + 1e-12)).max()))
+        # GAT: per head softmax over the neighbours (self loop included) of <q_r, k_j> / sqrt(d)
+        q = torch.relu(x_all[r] @ wq + gat.query_bias.double()).view(heads, -1)
+        k = torch.relu(x_all[nb] @ wk + gat.key_bias.double()).view(len(nb), heads, -1)
+        v = (x_all[nb] @ wv).view(len(nb), heads, -1)
+        att = torch.softmax((k * q[None]).sum(-1) / (q.shape[1] ** 0.5), dim=0)
+        want = torch.relu((att[:, :, None] * v).sum(0).reshape(-1) + gat.bias.double())
+        got = out_gat[r - p.lo].double()
+        worst = max(worst, float(((got - want).abs() / (want.abs() + 1e-4 * want.abs().max() + 1e-12)).max()))
+    return worst
+
+
 def bench_partitioned(args, rank, world, device, metric, config):
-    """Strong scaling of the bench workload: the same synthetic graph, destination-partitioned over `world` ranks.
-    Timed on the device with CUDA events between barriers; the reported time is the max over ranks."""
-    import json
-    import os
+    """Strong scaling of the bench workload: the same synthetic graph, destination-partitioned over `world` ranks, driven
+    through tfg.layers.GCN / GAT with [x_local, partitioned_graph] inputs.  Timed on the device with CUDA events between
+    barriers; the reported time is the max over ranks."""
     import numpy as np
     import bench as B
+    import tf_geometric_b200 as tfg
     from . import _ffi
 
     n = int(B.PRODUCTS_NODES * args.scale)
@@ -221,31 +406,53 @@ def bench_partitioned(args, rank, world, device, metric, config):
     edge_index = B.make_graph_device(n, pairs, 0, device)      # same seed on every rank -> identical global graph
     E = edge_index.shape[1]
     pg = PartitionedGraph.from_global(edge_index, None, n, rank, world)
-    del edge_index
-    torch.cuda.empty_cache()
     p = pg.part
-    gen = torch.Generator(device="cpu")
-    gen.manual_seed(100 + rank)
-    x_host = torch.randn((p.n_local, B.FEATURES), generator=gen, dtype=torch.float32).pin_memory()
+
+    def features(r):
+        part = RowPartition(n, world, r, align=ROW_ALIGN if pg.exchange == "p2p" else 1)
+        gen = torch.Generator(device="cpu")
+        gen.manual_seed(100 + r)
+        return torch.randn((part.n_local, B.FEATURES), generator=gen, dtype=torch.float32)
+
+    x_host = features(rank).pin_memory()
     x = x_host.to(device)
-    wk = B.glorot((B.FEATURES, B.UNITS), 2).to(device)
-    wq_, wk_, wv_ = (B.glorot((B.FEATURES, B.UNITS), s).to(device) for s in (3, 4, 5))
-    zero = torch.zeros((B.UNITS,), dtype=torch.float32, device=device)
-    relu = ops.relu
+    gcn = tfg.layers.GCN(B.UNITS, activation=tfg.nn.relu, seed=2)
+    gat = tfg.layers.GAT(B.UNITS, num_heads=B.HEADS, activation=tfg.nn.relu, seed=3)
 
     def step(xd):
-        if os.environ.get("TFGK_DIST_OVERLAP", "1") == "0":
-            a = gcn_partitioned(pg, xd, wk, zero, relu)
-            b = gat_partitioned(pg, xd, wq_, zero, relu, wk_, zero, relu, wv_, zero, relu, num_heads=B.HEADS)
-            return a, b
-        return gcn_gat_overlapped(pg, xd, wk, zero, relu, wq_, zero, wk_, zero, wv_, zero, relu, B.HEADS)
+        pg.new_step()                                          # every step publishes and pulls its input again
+        shared = pg.share(xd, [gcn, gat])                      # one fused all-gather -> projection launch for both layers
+        return gcn([shared, pg]), gat([shared, pg])
+
+    a, b = step(x)                                             # builds weights, CSRs, normalisation, peer mappings
+    torch.cuda.synchronize()
+    # parity of the path that is timed, before timing: (1) sampled rows against a float64 restatement,
+    # (2) all rows bit-identical to the collective (NCCL all-gather) path
+    err = _sampled_row_check(pg, edge_index, n, [features(r) for r in range(world)], gcn, gat, a, b, B.HEADS)
+    del edge_index
+    mode = pg.exchange
+    identical = None
+    if mode == "p2p":
+        pg.exchange = "collective"
+        a2, b2 = step(x)
+        pg.exchange = "p2p"
+        identical = bool(torch.equal(a, a2) and torch.equal(b, b2))
+        del a2, b2
+    check = torch.tensor([err, 0.0 if identical in (None, True) else 1.0], dtype=torch.float64, device=device)
+    dist.all_reduce(check, op=dist.ReduceOp.MAX)
+    if float(check[0]) > 1e-4 or float(check[1]) != 0.0:
+        raise SystemExit("partitioned path failed its parity check: sampled-row error {:.3e}, p2p == collective: {}".format(
+            float(check[0]), float(check[1]) == 0.0))
+    del a, b
+    torch.cuda.empty_cache()
 
     for _ in range(max(args.warmup, 3)):
         step(x)
-    trace = _ffi.CallTrace(timed=("tfgk_gat_fused_f32", "tfgk_spmm_f32"))
+    trace = _ffi.CallTrace(timed=("tfgk_gat_fused_f32", "tfgk_spmm_f32", "tfgk_gemm_proj_f32"))
     _ffi.set_trace(trace)
     sampler = B.ClockSampler(device.index)
     sampler.start()
+    nv0 = pg.nvlink_bytes
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
@@ -259,6 +466,7 @@ def bench_partitioned(args, rank, world, device, metric, config):
     torch.cuda.synchronize()
     clocks = sampler.stop()
     _ffi.set_trace(None)
+    nvlink_per_step = (pg.nvlink_bytes - nv0) / args.steps
     t = torch.tensor([ev[0].elapsed_time(ev[1]) / args.steps], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item())
@@ -272,13 +480,16 @@ def bench_partitioned(args, rank, world, device, metric, config):
                    h2d_bytes_per_step=n * B.FEATURES * 4, d2h_bytes_per_step=2 * n * B.UNITS * 4)
 
     gat_ms = float(np.mean(trace.elapsed_ms("tfgk_gat_fused_f32")))
+    spmm_ms = float(np.mean(trace.elapsed_ms("tfgk_spmm_f32")))
+    proj_ms = float(np.sum(trace.elapsed_ms("tfgk_gemm_proj_f32"))) / args.steps
     e_local = pg.csr(self_loops=True).nnz
     gat_bytes = e_local * (8 * B.UNITS + 4) + p.n_local * (8 * B.UNITS + 8)
     peak, peak_src = B.measured_peak_gbs()
-    launching = ("tfgk_gat_fused_f32", "tfgk_spmm_f32", "tfgk_gemm_f32")
+    launching = ("tfgk_gat_fused_f32", "tfgk_spmm_f32", "tfgk_gemm_f32", "tfgk_gemm_proj_f32", "tfgk_peer_barrier")
     launches = sum(trace.counts.get(k, 0) for k in launching)
     if rank == 0:
-        halo = (world - 1) * p.block * (B.UNITS + 2 * B.UNITS) * 4
+        hbm_step = gat_bytes + e_local * (4 * B.UNITS + 8) + p.n_local * (4 * B.UNITS + 8) \
+            + n * B.FEATURES * 4 + n * 3 * B.UNITS * 4
         line = {"metric": metric, "value": 2.0 * E / (ms_step * 1e-3), "unit": "edges/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
@@ -288,6 +499,14 @@ def bench_partitioned(args, rank, world, device, metric, config):
                              "frac": gat_bytes / (gat_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                              "algorithmic_bytes": gat_bytes, "kernel_ms": gat_ms},
                 "cpu_baseline": None,
-                "exchange": {"collective": "all_gather_into_tensor (NCCL), async: K|V exchange overlaps the GCN aggregation", "halo_bytes_in_per_rank_per_step": halo}}
+                "breakdown_ms": {"gat_fused": gat_ms, "gcn_spmm": spmm_ms, "projections_incl_exchange": proj_ms},
+                "parity": {"sampled_rows_max_rel_err_vs_float64": float(check[0]),
+                           "all_rows_bit_identical_to_collective_path": identical},
+                "exchange": {"mode": mode,
+                             "what": ("x rows pulled over NVLink peer mappings inside the projection GEMM (fused all-gather -> "
+                                      "GEMM, no collective)") if mode == "p2p" else
+                                     "all_gather_into_tensor of the projected rows (NCCL)",
+                             "nvlink_bytes_in_per_rank_per_step": nvlink_per_step,
+                             "hbm_algorithmic_bytes_per_rank_per_step": hbm_step}}
         B.emit(line)
     dist.destroy_process_group()

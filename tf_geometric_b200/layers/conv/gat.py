@@ -44,8 +44,22 @@ class GAT(Layer):
         if self.use_bias:
             self.bias = self.add_weight("bias", [self.units], "zeros", device=device)
 
+    def partitioned_projections(self):
+        """All-row projections this layer needs on a partitioned graph: K | V side by side (Q only for local rows)."""
+        k_act, _ = ops.activation_code(self.key_activation)
+        return [((id(self.key_kernel), id(self.kernel)),
+                 [(self.key_kernel, self.key_bias, k_act), (self.kernel, None, ops.ACT_NONE)])]
+
     def call(self, inputs, training=None, mask=None, cache=None):
-        """inputs = [x, edge_index] (a third entry, edge_weight, is accepted and ignored like in the reference)."""
+        """inputs = [x, edge_index] (a third entry, edge_weight, is accepted and ignored like in the reference); on
+        several GPUs [x_local, partitioned_graph] (tf_geometric_b200.dist.PartitionedGraph)."""
+        if hasattr(inputs[1], "part") and hasattr(inputs[1], "project_all_rows"):
+            from ... import dist as tdist
+            if not self.split_value_heads:
+                raise NotImplementedError("partitioned GAT concatenates the heads (split_value_heads=True)")
+            return tdist.gat_partitioned(inputs[1], inputs[0], self.query_kernel, self.query_bias, self.query_activation,
+                                         self.key_kernel, self.key_bias, self.key_activation, self.kernel, self.bias,
+                                         self.activation, num_heads=self.num_heads)
         return gat(inputs[0], inputs[1], self.query_kernel, self.query_bias, self.query_activation, self.key_kernel,
                    self.key_bias, self.key_activation, self.kernel, self.bias, self.activation, num_heads=self.num_heads,
                    split_value_heads=self.split_value_heads, edge_drop_rate=self.edge_drop_rate, training=bool(training),

@@ -60,8 +60,22 @@ class GCN(Layer):
                       "'GCN.build_cache_for_graph(graph, override)' instead", DeprecationWarning)
         return self.build_cache_for_graph(graph, override=override)
 
+    def partitioned_projections(self):
+        """All-row projections this layer needs on a partitioned graph: [(key, [(weight, bias, act code)])]."""
+        return [((id(self.kernel),), [(self.kernel, None, ops.ACT_NONE)])] if self.use_kernel else []
+
+    def _call_partitioned(self, x_local, pg):
+        from ... import dist as tdist
+        if not (self.norm == "both" and self.add_self_loop and self.sym):
+            raise NotImplementedError("partitioned GCN implements the default normalisation (norm='both', self loops, sym)")
+        return tdist.gcn_partitioned(pg, x_local, self.kernel, self.bias, self.activation, renorm=self.renorm,
+                                     improved=self.improved)
+
     def call(self, inputs, cache=None, split=True, training=None, mask=None):
-        """inputs: [x, sparse_adj], [x, edge_index] or [x, edge_index, edge_weight]."""
+        """inputs: [x, sparse_adj], [x, edge_index] or [x, edge_index, edge_weight]; on several GPUs
+        [x_local, partitioned_graph] (tf_geometric_b200.dist.PartitionedGraph; x_local may be the result of its share())."""
+        if hasattr(inputs[1], "part") and hasattr(inputs[1], "project_all_rows"):
+            return self._call_partitioned(inputs[0], inputs[1])
         if isinstance(inputs[1], SparseMatrix):
             x, sparse_adj = inputs
         elif len(inputs) == 3:

@@ -10,6 +10,17 @@ import torch
 from ... import ops, _structure, _rng, autograd
 
 
+def project(x, blocks):
+    """Dense projections of the same x: column blocks of at most 128 outputs, at most four per launch."""
+    pieces = []
+    for w, b, act, out in blocks:
+        for c0 in range(0, w.shape[1], 128):
+            c1 = min(c0 + 128, w.shape[1])
+            pieces.append((w[:, c0:c1], None if b is None else b[c0:c1], act, out[:, c0:c1]))
+    for i in range(0, len(pieces), 4):
+        ops.gemm_proj(x, pieces[i:i + 4])
+
+
 def gat(x, edge_index,
         query_kernel, query_bias, query_activation,
         key_kernel, key_bias, key_activation,
@@ -43,21 +54,22 @@ def gat(x, edge_index,
 
     q_act, q_left = ops.activation_code(query_activation)
     k_act, k_left = ops.activation_code(key_activation)
-    Q = ops.gemm(x, ops.as_device(query_kernel, torch.float32, device=dev),
-                 bias=ops.as_device(query_bias, torch.float32, device=dev), act=q_act)
-    if q_left is not None:
-        Q = q_left(Q)
-    # K and V are projected into ONE [N, A + U] buffer: the fused kernel then fetches a neighbour's key and value
-    # from the same DRAM burst (and the multi-GPU path ships them in a single all-gather)
+    # Q, K and V come out of ONE launch that reads x once (tfgk_gemm_proj_f32).  K and V land in ONE [N, A + U]
+    # buffer: the fused kernel then fetches a neighbour's key and value from the same DRAM burst
+    wq = ops.as_device(query_kernel, torch.float32, device=dev)
     wk = ops.as_device(key_kernel, torch.float32, device=dev)
     wv = ops.as_device(kernel, torch.float32, device=dev)
     a_units = wk.shape[1]
+    Q = torch.empty((num_nodes, wq.shape[1]), dtype=torch.float32, device=dev)
     kv = torch.empty((num_nodes, a_units + wv.shape[1]), dtype=torch.float32, device=dev)
     K, V = kv[:, :a_units], kv[:, a_units:]
-    ops.gemm(x, wk, bias=ops.as_device(key_bias, torch.float32, device=dev), act=k_act, out=K)
+    project(x, [(wq, ops.as_device(query_bias, torch.float32, device=dev), q_act, Q),
+                (wk, ops.as_device(key_bias, torch.float32, device=dev), k_act, K),
+                (wv, None, ops.ACT_NONE, V)])
+    if q_left is not None:
+        Q = q_left(Q)
     if k_left is not None:
         K.copy_(k_left(K))
-    ops.gemm(x, wv, out=V)
 
     act_code, leftover = ops.activation_code(activation)
     bias = None if bias is None else ops.as_device(bias, torch.float32, device=dev)

@@ -511,6 +511,47 @@ def gemm(a, b, bias=None, act=ACT_NONE, trans_a=False, trans_b=False, beta=0.0, 
     return out
 
 
+def gemm_proj(a, blocks, a_parts=None, part_rows=0, first_part=0, max_ctas=0, num_rows=None):
+    """Several projections of the same rows in ONE launch (tfgk_gemm_proj_f32): `blocks` is a list of
+    (weight [K, n<=128], bias or None, act code, out [M, n] view); returns the list of outputs.
+    With `a_parts` (device pointers of the row blocks of A, `part_rows` rows each, e.g. the other ranks' copies of x
+    mapped through peer memory) the rows are pulled from where they live; `a` then only supplies lda / K / the stream.
+    Shapes the tensor-core kernel does not take fall back to one tfgk_gemm_f32 per block (single-part input only)."""
+    if not (a.is_cuda and a.dtype == torch.float32 and a.dim() == 2):
+        raise TypeError("a must be a 2-D float32 CUDA tensor")
+    lda = _row_major_2d(a, "a")
+    M = int(a.shape[0] if num_rows is None else num_rows)
+    K = a.shape[1]
+    structs = (_ffi.ProjBlock * len(blocks))()
+    outs = []
+    for i, (w, bias, act, out) in enumerate(blocks):
+        if not (w.is_cuda and w.dtype == torch.float32 and w.dim() == 2 and w.shape[0] == K):
+            raise TypeError("gemm_proj: weight {} must be a float32 CUDA tensor [{}, n]".format(i, K))
+        if out is None:
+            out = torch.empty((M, w.shape[1]), dtype=torch.float32, device=a.device)
+        if bias is not None:
+            _check(bias, torch.float32, "bias")
+        structs[i] = _ffi.ProjBlock(w.data_ptr(), _row_major_2d(w, "weight"), w.shape[1],
+                                    None if bias is None else bias.data_ptr(), int(act), out.data_ptr(),
+                                    _row_major_2d(out, "out"))
+        outs.append(out)
+    if a_parts is None:
+        parts = (ctypes.c_void_p * 1)(a.data_ptr())
+        n_parts = 1
+    else:
+        parts = (ctypes.c_void_p * len(a_parts))(*[int(q) for q in a_parts])
+        n_parts = len(a_parts)
+    try:
+        _ffi.call("tfgk_gemm_proj_f32", parts, n_parts, int(part_rows), lda, M, K, structs, len(blocks), int(first_part),
+                  int(max_ctas), _stream(a))
+    except _ffi.TfgkError as err:
+        if err.code != _ffi.ERR_UNSUPPORTED or n_parts != 1:
+            raise
+        for (w, bias, act, _), out in zip(blocks, outs):
+            gemm(a[:M], w, bias=bias, act=act, out=out)
+    return outs
+
+
 def l2_normalize(x, out=None):
     if out is None:
         out = torch.empty_like(x)

@@ -39,6 +39,26 @@ p = pg.part
 x_loc = x_d[p.lo:p.hi].contiguous()
 loc_gcn = tdist.gcn_partitioned(pg, x_loc, k, b, tfg.nn.relu)
 loc_gat = tdist.gat_partitioned(pg, x_loc, wq, bq, tfg.nn.relu, wk, bk, tfg.nn.relu, wv, b, tfg.nn.relu, num_heads=heads)
+# the same through the public layers (what bench.py --gpus N times): one shared publication, fused projections
+gcn_l = tfg.layers.GCN(u, activation=tfg.nn.relu, seed=2)
+gat_l = tfg.layers.GAT(u, num_heads=heads, activation=tfg.nn.relu, seed=3)
+ref_gcn = gcn_l([x_d, ei_d])
+ref_gat = gat_l([x_d, ei_d])
+for step in range(3):                      # three publications: both slots and their reuse
+    pg.new_step()
+    shared = pg.share(x_loc, [gcn_l, gat_l])
+    lay_gcn, lay_gat = gcn_l([shared, pg]), gat_l([shared, pg])
+    torch.cuda.synchronize()
+    ok_layers = torch.equal(lay_gcn, ref_gcn[p.lo:p.hi]) and torch.equal(lay_gat, ref_gat[p.lo:p.hi])
+    print("rank {} step {} exchange={} layers bit-identical to single GPU: {}".format(rank, step, pg.exchange, ok_layers), flush=True)
+    if not ok_layers:
+        print("rank {} max diff gcn {:.3e} gat {:.3e}".format(rank, float((lay_gcn - ref_gcn[p.lo:p.hi]).abs().max()),
+                                                             float((lay_gat - ref_gat[p.lo:p.hi]).abs().max())), flush=True)
+pg_c = tdist.PartitionedGraph.from_global(ei_d, None, n, rank, world, exchange="collective")
+x_c = x_d[pg_c.part.lo:pg_c.part.hi].contiguous()
+col_gcn = gcn_l([x_c, pg_c])
+ok_coll = torch.equal(col_gcn, ref_gcn[pg_c.part.lo:pg_c.part.hi])
+print("rank {} collective path bit-identical: {}".format(rank, ok_coll), flush=True)
 torch.cuda.synchronize()
 ok_gcn = torch.equal(loc_gcn, full_gcn[p.lo:p.hi])
 ok_gat = torch.equal(loc_gat, full_gat[p.lo:p.hi])
@@ -46,7 +66,7 @@ err_gcn = float((loc_gcn - full_gcn[p.lo:p.hi]).abs().max())
 err_gat = float((loc_gat - full_gat[p.lo:p.hi]).abs().max())
 print("rank {} rows [{}, {}): gcn bit-identical={} (max diff {:.2e}), gat bit-identical={} (max diff {:.2e})".format(
     rank, p.lo, p.hi, ok_gcn, err_gcn, ok_gat, err_gat), flush=True)
-flag = torch.tensor([int(err_gcn < 1e-5 and err_gat < 1e-5)], device=dev)
+flag = torch.tensor([int(err_gcn < 1e-5 and err_gat < 1e-5 and ok_layers and ok_coll)], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()
 sys.exit(0 if int(flag.item()) == 1 else 1)
