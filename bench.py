@@ -39,12 +39,31 @@ HEADS = 8
 METRIC = "edges/sec GCN+GAT fwd on 2.4M-node/123M-edge synthetic; %HBM roofline"
 
 
+# BASELINE.json `configs`: sizes, layer(s) per step, and which pass is timed
+CONFIGS = {
+    "headline": {"nodes": PRODUCTS_NODES, "pairs": PRODUCTS_UNDIRECTED, "features": 100, "kind": "gcn+gat",
+                 "what": "GCN(128,relu) fwd + GAT(128, 8 heads, relu) fwd, synthetic ogbn-products shape"},
+    "cfg1": {"nodes": 2708, "pairs": 5278, "features": 1433, "kind": "gcn2",
+             "what": "demo_gcn.py model (GCN 1433->16 relu -> GCN 16->7) fwd on a Cora-shaped synthetic graph, sparse bag-of-words x"},
+    "cfg2": {"nodes": 1000000, "pairs": 10000000, "features": 128, "kind": "gcn",
+             "what": "GCN(128,relu) fwd, synthetic 1M nodes / 20M edges / 128 features"},
+    "cfg3": {"nodes": 1000000, "pairs": 10000000, "features": 128, "kind": "gat",
+             "what": "GAT(128, 8 heads, relu) fwd, synthetic 1M nodes / 20M edges / 128 features"},
+    "cfg4": {"nodes": PRODUCTS_NODES, "pairs": PRODUCTS_UNDIRECTED, "features": 100, "kind": "sage_train",
+             "what": "MeanGraphSage(256, concat) forward + backward (gradients w.r.t. weights and inputs), ogbn-products shape"},
+    "cfg5": {"nodes": 111059956, "edges": 1615685872, "features": 128, "kind": "gcn_partitioned",
+             "what": "GCN(128,relu) fwd, synthetic ogbn-papers100M shape, destination-partitioned"},
+}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="headline", choices=sorted(CONFIGS),
+                    help="BASELINE.json workload: headline = the metric's own configuration (default); cfg1..cfg5 = configs[0..4]")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (testing only; 1.0 = BASELINE size)")
     ap.add_argument("--cpu-sample-div", type=int, default=0,
                     help="reference arm: graph scaled down by this factor (0 = auto: about two minutes of CPU work in total)")
@@ -152,34 +171,92 @@ def measured_peak_gbs():
 
 # ---- reference arm (CPU) ---------------------------------------------------------------------------------------------
 
-def cpu_reference(num_nodes, num_pairs, steps, warmup, seed=0):
-    """The reference's op sequence on the host cores for one step (GCN fwd + GAT fwd) on a bounded graph."""
+def _cpu_workload(kind, num_nodes, num_pairs, features, seed=0):
+    """Builds the reference's op sequence for one step of `kind` on a graph of the given size; returns (step_fn, E,
+    edge layer passes per step)."""
     from oracle import torch_cpu_port as port
     from oracle import tfg_oracle as o
-    torch.set_num_threads(os.cpu_count() or 1)
     ei = make_graph_device(num_nodes, num_pairs, seed, torch.device("cpu"))
     E = ei.shape[1]
     gen = torch.Generator(device="cpu"); gen.manual_seed(1)
-    x = torch.randn((num_nodes, FEATURES), generator=gen, dtype=torch.float32)
+    x = torch.randn((num_nodes, features), generator=gen, dtype=torch.float32)
     # warm cache, like demo_gcn.py:47: normalised adjacency precomputed (numpy oracle), self loops appended for GAT
     normed = o.gcn_norm_adj(o.SparseMatrix(ei.numpy(), None, [num_nodes, num_nodes]))
     n_row = torch.from_numpy(normed.index[0]).long(); n_col = torch.from_numpy(normed.index[1]).long()
     n_val = torch.from_numpy(normed.value)
-    wk = glorot((FEATURES, UNITS), 2); b = torch.zeros(UNITS)
-    wq_, wk_, wv_ = glorot((FEATURES, UNITS), 3), glorot((FEATURES, UNITS), 4), glorot((FEATURES, UNITS), 5)
+    b = torch.zeros(UNITS)
+    if kind == "gcn+gat":
+        wk = glorot((features, UNITS), 2)
+        wq_, wk_, wv_ = glorot((features, UNITS), 3), glorot((features, UNITS), 4), glorot((features, UNITS), 5)
 
-    def step():
-        port.gcn_forward(x, n_row, n_col, n_val, wk, b)
-        port.gat_forward(x, n_row, n_col, wq_, b, wk_, b, wv_, b, HEADS)   # same index: edges + appended self loops
+        def step():
+            port.gcn_forward(x, n_row, n_col, n_val, wk, b)
+            port.gat_forward(x, n_row, n_col, wq_, b, wk_, b, wv_, b, HEADS)   # same index: edges + appended self loops
+        return step, E, 2
+    if kind in ("gcn", "gcn_partitioned"):
+        wk = glorot((features, UNITS), 2)
+        return (lambda: port.gcn_forward(x, n_row, n_col, n_val, wk, b)), E, 1
+    if kind == "gat":
+        wq_, wk_, wv_ = glorot((features, UNITS), 3), glorot((features, UNITS), 4), glorot((features, UNITS), 5)
+        return (lambda: port.gat_forward(x, n_row, n_col, wq_, b, wk_, b, wv_, b, HEADS)), E, 1
+    if kind == "gcn2":
+        w1, w2 = glorot((features, 16), 2), glorot((16, 7), 3)
+        b1, b2 = torch.zeros(16), torch.zeros(7)
 
+        def step():
+            h = port.gcn_forward(x, n_row, n_col, n_val, w1, b1)
+            port.gcn_forward(h, n_row, n_col, n_val, w2, b2, relu=False)
+        return step, E, 2
+    if kind == "sage_train":
+        # nn/conv/graph_sage.py:9-60 under autodiff (demo_graph_sage.py:100-106): gather, segment mean, two projections, concat
+        row, col = ei[0].long(), ei[1].long()
+        ws, wn = glorot((features, UNITS), 2).requires_grad_(True), glorot((features, UNITS), 3).requires_grad_(True)
+        bb = torch.zeros(2 * UNITS).requires_grad_(True)
+        g = torch.randn((num_nodes, 2 * UNITS), generator=gen)
+        cnt = torch.bincount(row, minlength=num_nodes).clamp(min=1).float().unsqueeze(1)
+        xg = x.clone().requires_grad_(True)
+
+        def step():
+            for t in (ws, wn, bb, xg):
+                t.grad = None
+            msg = xg.index_select(0, col)
+            agg = torch.zeros_like(xg).index_add_(0, row, msg) / cnt
+            out = torch.relu(torch.cat([xg @ ws, agg @ wn], dim=1) + bb)
+            (out * g).sum().backward()
+        return step, E, 1
+    raise ValueError(kind)
+
+
+def cpu_reference(kind, num_nodes, num_pairs, features, steps, warmup, threads=None):
+    """The reference's op sequence on the host cores on a bounded graph.  The thread count is swept on a 4x smaller graph
+    first (index_add_ / scatter_reduce_ do not scale with threads; 128 threads were 4x slower than 1 in round 1)."""
+    ncpu = os.cpu_count() or 1
+    sweep = {}
+    if threads is None:
+        small, _, _ = _cpu_workload(kind, max(num_nodes // 4, 1000), max(num_pairs // 4, 1000), features)
+        for t in sorted({1, 4, 8, 16, 32, 64, ncpu}):
+            if t > ncpu:
+                continue
+            torch.set_num_threads(t)
+            small()
+            t0 = time.perf_counter()
+            small()
+            sweep[t] = time.perf_counter() - t0
+        threads = min(sweep, key=sweep.get)
+    torch.set_num_threads(threads)
+    step, E, passes = _cpu_workload(kind, num_nodes, num_pairs, features)
     for _ in range(warmup):
         step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
+    times = []
+    for _ in range(max(steps, 1)):
+        t0 = time.perf_counter()
         step()
-    dt = (time.perf_counter() - t0) / max(steps, 1)
-    return {"edges_per_s": 2.0 * E / dt, "ms_per_step": dt * 1e3, "edges": E, "nodes": num_nodes,
-            "cores": torch.get_num_threads()}
+        times.append(time.perf_counter() - t0)
+    dt = float(np.mean(times))
+    return {"edges_per_s": passes * E / dt, "ms_per_step": dt * 1e3, "edges": E, "nodes": num_nodes,
+            "cores": threads, "host_cores": ncpu, "passes": passes,
+            "thread_sweep_s_per_step_quarter_sample": {str(k): v for k, v in sweep.items()},
+            "spread": (max(times) - min(times)) / dt if len(times) > 1 else 0.0}
 
 
 def cpu_model_name():
@@ -192,57 +269,83 @@ def cpu_model_name():
     return "unknown"
 
 
+def config_sizes(args):
+    cfg = CONFIGS[args.config]
+    n = int(cfg["nodes"] * args.scale)
+    pairs = int(cfg.get("pairs", cfg.get("edges", 0) // 2) * args.scale)
+    return cfg, n, pairs
+
+
 def cpu_sample_div(args, passes):
-    """Bounded sample for the CPU arm: the op-for-op port sustains ~0.6 M edges/s on the box's host cores (measured), so
+    """Bounded sample for the CPU arm: the op-for-op port sustains ~1 M edges/s on the box's host cores (measured), so
     `passes` step executions of the full graph would take hours; scale the graph so the whole arm takes ~2 minutes."""
     if args.cpu_sample_div > 0:
         return args.cpu_sample_div
-    budget_edges = 0.6e6 * 120.0                       # edge-layer passes affordable in ~120 s
-    per_step_full = 4.0 * PRODUCTS_UNDIRECTED * args.scale
-    return max(25, int(np.ceil(per_step_full * passes / budget_edges)))
+    cfg, n, pairs = config_sizes(args)
+    layers = {"gcn+gat": 2, "gcn2": 2, "sage_train": 3}.get(cfg["kind"], 1)
+    budget_edges = 1.0e6 * 100.0                       # edge-layer passes affordable in ~100 s
+    per_step_full = 2.0 * pairs * layers
+    return max(1, int(np.ceil(per_step_full * passes / budget_edges)))
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    args.cpu_sample_div = cpu_sample_div(args, args.steps + args.warmup)
-    n = max(int(PRODUCTS_NODES * args.scale) // args.cpu_sample_div, 1000)
-    pairs = max(int(PRODUCTS_UNDIRECTED * args.scale) // args.cpu_sample_div, 1000)
-    res = cpu_reference(n, pairs, args.steps, args.warmup)
+    cfg, n, pairs = config_sizes(args)
+    args.cpu_sample_div = cpu_sample_div(args, args.steps + args.warmup + 2)
+    ns = max(n // args.cpu_sample_div, min(n, 1000))
+    ps = max(pairs // args.cpu_sample_div, min(pairs, 1000))
+    res = cpu_reference(cfg["kind"], ns, ps, cfg["features"], args.steps, args.warmup)
     sample = ("same generator and layer shapes at 1/{} scale: {} nodes, {} directed edges; op-for-op torch-CPU port of "
-              "the reference op sequence, {}").format(args.cpu_sample_div, res["nodes"], res["edges"], cpu_model_name())
-    line = {"metric": METRIC, "value": res["edges_per_s"], "unit": "edges/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": workload_config(args, 1),
+              "the reference op sequence, {} threads (best of a sweep) on {} host cores, {}").format(
+                  args.cpu_sample_div, res["nodes"], res["edges"], res["cores"], res["host_cores"], cpu_model_name())
+    config = workload_config(args, 1)
+    config["reference_sample"] = {"nodes": res["nodes"], "edges": res["edges"], "scale": "1/{}".format(args.cpu_sample_div),
+                                  "note": "the CPU arm times a bounded sample of the workload named above"}
+    line = {"metric": config_metric(args), "value": res["edges_per_s"], "unit": "edges/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": config,
             "cpu_baseline": {"value": res["edges_per_s"], "unit": "edges/s", "cores": res["cores"], "kind": "port",
-                             "sample": sample},
+                             "sample": sample, "thread_sweep": res["thread_sweep_s_per_step_quarter_sample"],
+                             "step_time_spread": res["spread"]},
             "e2e": {"value": res["edges_per_s"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
+def config_metric(args):
+    return METRIC if args.config == "headline" else "edges/sec " + CONFIGS[args.config]["what"]
+
+
 def workload_config(args, world):
-    n = int(PRODUCTS_NODES * args.scale)
-    e = 2 * int(PRODUCTS_UNDIRECTED * args.scale)
-    return {"workload": "GCN(128,relu) fwd + GAT(128, 8 heads, relu) fwd, synthetic ogbn-products shape "
-                        "({} nodes, {} directed edges, {} features), uniform random undirected pairs mirrored, "
-                        "warm graph.cache".format(n, e, FEATURES),
-            "nodes": n, "edges": e, "features": FEATURES, "units": UNITS, "heads": HEADS,
-            "edges_per_step": 2 * e, "parallelism": "single GPU" if world == 1 else "dst-partitioned x{}".format(world),
-            "l2_policy": "working set (>= 2 GB of gathered rows + CSR) exceeds the 126 MB L2; no explicit flush"}
+    cfg, n, pairs = config_sizes(args)
+    e = 2 * pairs
+    passes = {"gcn+gat": 2, "gcn2": 2}.get(cfg["kind"], 1)
+    out = {"workload": "{} ({} nodes, {} directed edges, {} features), uniform random undirected pairs mirrored, "
+                       "warm graph.cache".format(cfg["what"], n, e, cfg["features"]),
+           "name": args.config, "nodes": n, "edges": e, "features": cfg["features"], "units": UNITS, "heads": HEADS,
+           "edges_per_step": passes * e, "parallelism": "single GPU" if world == 1 else "dst-partitioned x{}".format(world),
+           "l2_policy": "working set (gathered rows + CSR, GBs) exceeds the 126 MB L2; no explicit flush"}
+    if cfg["kind"] == "gcn2":
+        out["l2_policy"] = "Cora-sized working set fits in L2: this config is latency/launch bound by construction"
+    return out
 
 
 # ---- our arm -----------------------------------------------------------------------------------------------------------
 
-def run_e2e(args, device, x_host, step_fn, n_out_rows, edges_per_layer, barrier=None):
+def run_e2e(args, device, x_host, step_fn, n_out_rows, edges_per_layer, barrier=None, passes=2):
     """Host-to-host throughput of the same step: every step copies its input features from pinned host memory and lands
-    both layer outputs in pinned host memory.  The three engines are pipelined the way a serving loop would do it:
+    every output of the step in pinned host memory.  The three engines are pipelined the way a serving loop would do it:
     H2D of step i+1 and D2H of step i's outputs run on their own streams while step i / i+1 compute; device and host
-    buffers are double buffered and every dependency is an event.  All copies are inside the timed region."""
+    buffers are double buffered and every dependency is an event.  All copies are inside the timed region.
+    (n_out_rows is kept for the callers' bookkeeping; host output buffers take the shapes the step returns.)"""
     s_in, s_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
     main = torch.cuda.current_stream(device)
-    outs = [[torch.empty((n_out_rows, UNITS), dtype=torch.float32).pin_memory() for _ in range(2)] for _ in range(2)]
     x_dev = [torch.empty(x_host.shape, dtype=torch.float32, device=device) for _ in range(2)]
+    probe = step_fn(x_dev[0].copy_(x_host))
+    outs = [[torch.empty(tuple(o.shape), dtype=torch.float32).pin_memory() for o in probe] for _ in range(2)]
+    d2h = sum(o.numel() * 4 for o in probe)
+    del probe
     ev_in = [torch.cuda.Event() for _ in range(2)]
     ev_free = [torch.cuda.Event() for _ in range(2)]       # x_dev[slot] no longer read by compute
     ev_out_done = [torch.cuda.Event() for _ in range(2)]   # host output slot drained (previous use)
@@ -254,18 +357,18 @@ def run_e2e(args, device, x_host, step_fn, n_out_rows, edges_per_layer, barrier=
             x_dev[slot].copy_(x_host, non_blocking=True)
             ev_in[slot].record(s_in)
         main.wait_event(ev_in[slot])
-        a, b = step_fn(x_dev[slot])                          # public layer API, GCN then GAT
+        results = step_fn(x_dev[slot])                       # public layer API
         ev_free[slot].record(main)
         ev_done = torch.cuda.Event()
         ev_done.record(main)
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_done)
             s_out.wait_event(ev_out_done[slot])
-            outs[slot][0].copy_(a, non_blocking=True)
-            outs[slot][1].copy_(b, non_blocking=True)
+            for host, res in zip(outs[slot], results):
+                host.copy_(res, non_blocking=True)
             ev_out_done[slot].record(s_out)
-        a.record_stream(s_out)
-        b.record_stream(s_out)
+        for res in results:
+            res.record_stream(s_out)
 
     for slot in range(2):
         ev_free[slot].record(main)
@@ -284,9 +387,84 @@ def run_e2e(args, device, x_host, step_fn, n_out_rows, edges_per_layer, barrier=
     t1.record(main)
     torch.cuda.synchronize(device)
     ms = t0.elapsed_time(t1) / args.steps
-    return {"value": 2.0 * edges_per_layer / (ms * 1e-3), "unit": "edges/s", "ms_per_step": ms,
-            "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 2 * n_out_rows * UNITS * 4,
+    return {"value": passes * edges_per_layer / (ms * 1e-3), "unit": "edges/s", "ms_per_step": ms,
+            "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": d2h,
             "pipelining": "H2D / compute / D2H on three streams, double buffered, all inside the timed region"}
+
+
+TIMED_CALLS = ("tfgk_gat_fused_f32", "tfgk_spmm_f32", "tfgk_gemm_f32", "tfgk_gemm_proj_f32")
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from committed `ncu --set full` captures (constants, NOT live
+# counters): profiles/r1_ncu_full_final_kernels.json; only valid for the full-size products-shape graph
+NCU_TRAFFIC = {"gat": 128184537000, "spmm_d128": 63515602000}
+
+
+def build_workload(args, tfg, device):
+    """Graph, features, layers and the step function of args.config on one GPU.  Returns a dict with: x_host, step,
+    E, passes, kernels = {family: (abi call, algorithmic bytes per step, description)}."""
+    cfg, n, pairs = config_sizes(args)
+    F = cfg["features"]
+    kind = cfg["kind"]
+    edge_index = make_graph_device(n, pairs, 0, device)
+    E = edge_index.shape[1]
+    gen = torch.Generator(device="cpu"); gen.manual_seed(1)
+    if kind == "gcn2":       # Cora-like bag of words: ~18 non-zeros per row, row-normalised (datasets/planetoid.py:88-92)
+        x_host = (torch.rand((n, F), generator=gen) < 18.0 / F).float()
+        x_host = (x_host / x_host.sum(1, keepdim=True).clamp(min=1.0)).pin_memory()
+    else:
+        x_host = torch.randn((n, F), generator=gen, dtype=torch.float32).pin_memory()
+    x = x_host.to(device)
+    graph = tfg.Graph(x, edge_index)
+    e_loop = E + n
+    spmm_bytes = lambda d, e, w: e * (4 * d + 4 + (4 if w else 0)) + n * (4 * d + 8)      # noqa: E731  DESIGN.md K1
+    gat_bytes = e_loop * (4 * UNITS + 4 * UNITS + 4) + n * (4 * UNITS + 4 * UNITS + 8)       # DESIGN.md K3
+    proj_bytes = lambda cols: n * F * 4 + n * cols * 4                                       # noqa: E731
+    kernels = {}
+    if kind in ("gcn+gat", "gcn", "gat"):
+        layers = []
+        if "gcn" in kind:
+            gcn = tfg.layers.GCN(UNITS, activation=tfg.nn.relu, seed=2)
+            gcn.build_cache_for_graph(graph)                   # normalised adjacency + CSR (one-off, untimed)
+            layers.append(lambda xd: gcn([xd, graph.edge_index, graph.edge_weight], cache=graph.cache))
+            kernels["gcn_spmm"] = ("tfgk_spmm_f32", spmm_bytes(UNITS, e_loop, True), "spmm_async_kernel<1,0,4,3> (tfgk_spmm_f32)",
+                                   NCU_TRAFFIC["spmm_d128"] if args.config == "headline" and args.scale == 1.0 else None)
+            kernels["gcn_projection"] = ("tfgk_gemm_f32", proj_bytes(UNITS), "gemm_tf32x3_ws_kernel (tfgk_gemm_f32)", None)
+        if "gat" in kind:
+            gat = tfg.layers.GAT(UNITS, num_heads=HEADS, activation=tfg.nn.relu, seed=3)
+            layers.append(lambda xd: gat([xd, graph.edge_index], cache=graph.cache))
+            kernels["gat_fused"] = ("tfgk_gat_fused_f32", gat_bytes, "gat_async_kernel<2,3> (tfgk_gat_fused_f32)",
+                                    NCU_TRAFFIC["gat"] if args.config == "headline" and args.scale == 1.0 else None)
+            kernels["gat_projections"] = ("tfgk_gemm_proj_f32", proj_bytes(3 * UNITS),
+                                          "gemm_proj_kernel, Q|K|V in one launch (tfgk_gemm_proj_f32)", None)
+        step = lambda xd: tuple(f(xd) for f in layers)     # noqa: E731
+        passes = len(layers)
+    elif kind == "gcn2":
+        l1 = tfg.layers.GCN(16, activation=tfg.nn.relu, seed=2)
+        l2 = tfg.layers.GCN(7, seed=3)
+        l1.build_cache_for_graph(graph)
+        step = lambda xd: (l2([l1([xd, graph.edge_index, graph.edge_weight], cache=graph.cache),     # noqa: E731
+                               graph.edge_index, graph.edge_weight], cache=graph.cache),)
+        kernels["gcn_spmm"] = ("tfgk_spmm_f32", spmm_bytes(16, e_loop, True) + spmm_bytes(7, e_loop, True),
+                               "spmm kernels, D=16 and D=7 (tfgk_spmm_f32)", None)
+        passes = 2
+    elif kind == "sage_train":
+        layer = tfg.layers.MeanGraphSage(2 * UNITS, activation=tfg.nn.relu, concat=True, seed=2, trainable=True)
+        g = torch.randn((n, 2 * UNITS), generator=torch.Generator(device="cpu").manual_seed(9)).to(device)
+
+        def step(xd):
+            xg = xd.detach().requires_grad_(True)
+            layer.zero_grad(set_to_none=True)
+            out = layer([xg, graph.edge_index])
+            loss = (out * g).sum()
+            loss.backward()
+            return (loss.detach().reshape(1), xg.grad)
+        # forward mean aggregation (unweighted) + backward aggregation on the transposed CSR (weights 1/deg)
+        kernels["sage_spmm"] = ("tfgk_spmm_f32", spmm_bytes(F, E, False) + spmm_bytes(F, E, True),
+                                "spmm kernels at D=100, forward + transposed backward (tfgk_spmm_f32)", None)
+        kernels["sage_dense"] = ("tfgk_gemm_f32", 0, "forward projections, dX and split-K dW GEMMs (tfgk_gemm_f32)", None)
+        passes = 1
+    else:
+        raise ValueError(kind)
+    return {"x_host": x_host, "x": x, "step": step, "E": E, "n": n, "passes": passes, "kernels": kernels, "graph": graph}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -295,43 +473,35 @@ def run_ours(args, rank, world, local_rank):
 
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
-    if world > 1:
+    cfg = CONFIGS[args.config]
+    if world > 1 or cfg["kind"] == "gcn_partitioned":
         os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep NCCL's version banner off stdout: one JSON line only
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=device)
-    if world > 1:
+        if world == 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", device_id=device, rank=rank, world_size=world)
+        if cfg["kind"] == "gcn_partitioned":
+            from tf_geometric_b200.dist import bench_papers
+            return bench_papers(args, rank, world, device, config_metric(args), workload_config(args, world))
+        if args.config != "headline":
+            raise SystemExit("--config {} is a single-GPU workload (BASELINE.json configs); use --gpus 1".format(args.config))
         from tf_geometric_b200.dist import bench_partitioned
         return bench_partitioned(args, rank, world, device, METRIC, workload_config(args, world))
 
-    n = int(PRODUCTS_NODES * args.scale)
-    pairs = int(PRODUCTS_UNDIRECTED * args.scale)
-    edge_index = make_graph_device(n, pairs, 0, device)
-    E = edge_index.shape[1]
-    gen = torch.Generator(device="cpu"); gen.manual_seed(1)
-    x_host = torch.randn((n, FEATURES), generator=gen, dtype=torch.float32).pin_memory()
-    x = x_host.to(device)
-    graph = tfg.Graph(x, edge_index)
-
-    gcn = tfg.layers.GCN(UNITS, activation=tfg.nn.relu, seed=2)
-    gat = tfg.layers.GAT(UNITS, num_heads=HEADS, activation=tfg.nn.relu, seed=3)
-    gcn.build_cache_for_graph(graph)                       # normalised adjacency + CSR (one-off, untimed)
     torch.cuda.synchronize()
     t_cache = time.perf_counter()
-    gat([graph.x, graph.edge_index], cache=graph.cache)    # builds the self-looped CSR + weights
-    gcn([graph.x, graph.edge_index, graph.edge_weight], cache=graph.cache)
+    wl = build_workload(args, tfg, device)
+    step, x, E, n = wl["step"], wl["x"], wl["E"], wl["n"]
+    step(x)                                                # builds the self-looped CSR + weights
     torch.cuda.synchronize()
     t_cache = time.perf_counter() - t_cache
-
-    def step(xd):
-        a = gcn([xd, graph.edge_index, graph.edge_weight], cache=graph.cache)
-        b = gat([xd, graph.edge_index], cache=graph.cache)
-        return a, b
 
     # ---- device-resident timing ("value") ----
     for _ in range(max(args.warmup, 3)):
         step(x)
     torch.cuda.synchronize()
-    trace = _ffi.CallTrace(timed=("tfgk_gat_fused_f32", "tfgk_spmm_f32", "tfgk_gemm_f32"))
+    trace = _ffi.CallTrace(timed=TIMED_CALLS)
     _ffi.set_trace(trace)
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -345,54 +515,56 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop()
     _ffi.set_trace(None)
     ms_step = ev[0].elapsed_time(ev[1]) / args.steps
-    value = 2.0 * E / (ms_step * 1e-3)
+    value = wl["passes"] * E / (ms_step * 1e-3)
 
-    gat_ms = float(np.mean(trace.elapsed_ms("tfgk_gat_fused_f32")))
-    spmm_ms = float(np.mean(trace.elapsed_ms("tfgk_spmm_f32")))
-    gemm_ms = float(np.sum(trace.elapsed_ms("tfgk_gemm_f32"))) / args.steps
-    launching = ("tfgk_gat_fused_f32", "tfgk_spmm_f32", "tfgk_gemm_f32")   # each is exactly one kernel launch here
-    launches = sum(trace.counts.get(k, 0) for k in launching)
-
-    # roofline of the dominant kernel (K3 fused GAT): algorithmic bytes per launch, DESIGN.md "K3"
-    e_loop = E + n
-    gat_bytes = e_loop * (4 * UNITS + 4 * UNITS + 4) + n * (4 * UNITS + 4 * UNITS + 8)
-    spmm_bytes = e_loop * (4 * UNITS + 4 + 4) + n * (4 * UNITS + 8)
+    call_ms = {name: float(np.sum(trace.elapsed_ms(name))) / args.steps for name in TIMED_CALLS}
+    call_n = {name: trace.counts.get(name, 0) / args.steps for name in TIMED_CALLS}
+    launches = sum(trace.counts.get(k, 0) for k in TIMED_CALLS)      # each call is one kernel launch on these paths
     peak, peak_src = measured_peak_gbs()
-    achieved = gat_bytes / (gat_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "gat_async_kernel<2,3> (tfgk_gat_fused_f32)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
-                # (profiles/r1_ncu_full_final_kernels.json); only valid for the default full-size workload
-                "traffic": 128184537000 if args.scale == 1.0 else None, "peak_source": peak_src,
-                "algorithmic_bytes": gat_bytes, "kernel_ms": gat_ms,
-                "secondary": {"kernel": "spmm_async_kernel<1,0,4,3> (tfgk_spmm_f32)", "traffic": 63515602000 if args.scale == 1.0 else None, "algorithmic_bytes": spmm_bytes,
-                              "kernel_ms": spmm_ms, "achieved": spmm_bytes / (spmm_ms * 1e-3) / 1e9,
-                              "frac": spmm_bytes / (spmm_ms * 1e-3) / 1e9 / peak},
-                "gemm_ms_per_step": gemm_ms}
+    fams = {}
+    for fam, (call, nbytes, desc, traffic) in wl["kernels"].items():
+        ms = call_ms[call]
+        fams[fam] = {"kernel": desc, "ms_per_step": ms, "launches_per_step": call_n[call], "algorithmic_bytes_per_step": nbytes,
+                     "achieved": (nbytes / (ms * 1e-3) / 1e9) if ms > 0 and nbytes else None,
+                     "frac": (nbytes / (ms * 1e-3) / 1e9 / peak) if ms > 0 and nbytes else None, "traffic": traffic}
+    if cfg["kind"] == "gcn+gat":          # both layers call tfgk_gemm_proj/gemm once each: attribute the calls
+        pass
+    dominant = max((f for f in fams if fams[f]["algorithmic_bytes_per_step"]), key=lambda f: fams[f]["ms_per_step"])
+    d = fams[dominant]
+    roofline = {"bound": "hbm", "kernel": d["kernel"], "achieved": d["achieved"], "peak": peak, "unit": "GB/s",
+                "frac": d["frac"], "traffic": d["traffic"],
+                "traffic_source": ("constant copied from the committed ncu --set full capture of round 1 "
+                                   "(profiles/r1_ncu_full_final_kernels.json), not measured in this run") if d["traffic"] else None,
+                "peak_source": peak_src, "algorithmic_bytes": d["algorithmic_bytes_per_step"] / max(d["launches_per_step"], 1),
+                "kernel_ms": d["ms_per_step"] / max(d["launches_per_step"], 1),
+                "launches_per_step": d["launches_per_step"],
+                "other_kernels": {f: v for f, v in fams.items() if f != dominant}}
 
     # ---- end to end: host buffers in, host buffers out, through the same public API ----
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, device, x_host, lambda xd: step(xd), n, E)
+        e2e = run_e2e(args, device, wl["x_host"], step, n, E, passes=wl["passes"])
 
     cpu_base = None
     if not args.no_cpu_baseline:
-        args.cpu_sample_div = cpu_sample_div(args, 2)
-        ns = max(n // args.cpu_sample_div, 1000)
-        ps = max(pairs // args.cpu_sample_div, 1000)
-        res = cpu_reference(ns, ps, steps=1, warmup=1)
+        _, _, pairs = config_sizes(args)
+        args.cpu_sample_div = cpu_sample_div(args, 4)
+        ns = max(n // args.cpu_sample_div, min(n, 1000))
+        ps = max(pairs // args.cpu_sample_div, min(pairs, 1000))
+        res = cpu_reference(cfg["kind"], ns, ps, cfg["features"], steps=1, warmup=1)
         cpu_base = {"value": res["edges_per_s"], "unit": "edges/s", "cores": res["cores"], "kind": "port",
                     "sample": "same generator and layer shapes at 1/{} scale ({} nodes, {} directed edges), 1 step after "
-                              "1 warm-up, op-for-op torch-CPU port of the reference op sequence, {}".format(
-                                  args.cpu_sample_div, res["nodes"], res["edges"], cpu_model_name())}
+                              "1 warm-up, op-for-op torch-CPU port of the reference op sequence, {} threads (best of a sweep) "
+                              "of {} host cores, {}".format(args.cpu_sample_div, res["nodes"], res["edges"], res["cores"],
+                                                            res["host_cores"], cpu_model_name()),
+                    "thread_sweep": res["thread_sweep_s_per_step_quarter_sample"]}
 
-    line = {"metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": 1, "steps": args.steps,
+    line = {"metric": config_metric(args), "value": value, "unit": "edges/s", "n_gpus": 1, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, 1),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "launches_per_step": launches / args.steps,
             "roofline": roofline, "cpu_baseline": cpu_base,
-            "breakdown_ms": {"gcn_spmm": spmm_ms, "gat_fused": gat_ms, "dense_projections": gemm_ms,
-                             "cache_build_s": t_cache}}
+            "breakdown_ms": dict({f: v["ms_per_step"] for f, v in fams.items()}, cache_build_s=t_cache)}
     emit(line)
 
 

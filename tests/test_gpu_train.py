@@ -493,3 +493,67 @@ def test_every_trainable_layer_gets_gradients():
                 assert float(p.grad.abs().sum()) > 0, "{}.{}".format(type(layer).__name__, pname)
     with pytest.raises(NotImplementedError):
         L.MaxPoolGraphSage(8, seed=1, trainable=True)([xd, eid, wd])
+
+
+def test_every_pool_layer_passes_gradients():
+    """Round-1 advisory: pooling / reducers cut the autograd graph silently.  Gradients of the four graph poolings, the stock
+    reducers, the fused aggregate_neighbors routes and of a GCN -> SAGPool -> MeanPool model against float64 autograd over
+    plain torch ops."""
+    rs = np.random.RandomState(3)
+    n, graphs, d = 400, 9, 6
+    gi = np.sort(rs.randint(0, graphs - 1, n)).astype(np.int32)          # the last graph stays empty
+    x = rs.randn(n, d).astype(np.float32)
+    x[5] = x[6]                                                          # a tie inside one graph for max / min
+    gi[5] = gi[6]
+    g = rs.randn(graphs, d).astype(np.float32)
+    gid = dev(gi, torch.int32)
+    seg = torch.from_numpy(gi.astype(np.int64))
+    for name in ("sum", "mean", "max", "min"):
+        xd = dev(x).requires_grad_(True)
+        out = getattr(tfg.nn, name + "_pool")(xd, gid, graphs)
+        (out * dev(g)).sum().backward()
+        x64 = torch.from_numpy(x).double().requires_grad_(True)
+        if name in ("sum", "mean"):
+            ref = torch.zeros((graphs, d), dtype=torch.float64).index_add_(0, seg, x64)
+            if name == "mean":
+                ref = ref / torch.bincount(seg, minlength=graphs).clamp(min=1).double().unsqueeze(1)
+        else:
+            ref = torch.zeros((graphs, d), dtype=torch.float64).scatter_reduce(
+                0, seg.unsqueeze(1).expand(-1, d), x64, reduce="amax" if name == "max" else "amin", include_self=False)
+        (ref * torch.from_numpy(g).double()).sum().backward()
+        assert xd.grad is not None, name + "_pool returned no gradient"
+        assert_close(host(xd.grad), x64.grad.numpy(), rtol=1e-5, atol_scale=1e-6, what=name + "_pool gradient")
+    # fused aggregate_neighbors routes with a differentiable input
+    ei = random_graph(n, 3000, seed=4)
+    w = (rs.rand(ei.shape[1]) + 0.1).astype(np.float32)
+    gg = rs.randn(n, d).astype(np.float32)
+    row, col = torch.from_numpy(ei[0].astype(np.int64)), torch.from_numpy(ei[1].astype(np.int64))
+    for reducer, red in ((tfg.nn.sum_reducer, "sum"), (tfg.nn.mean_reducer, "mean"), (tfg.nn.max_reducer, "max")):
+        xd = dev(x).requires_grad_(True)
+        out = tfg.nn.aggregate_neighbors(xd, dev(ei, torch.int32), dev(w), tfg.nn.gcn_mapper, reducer, tfg.nn.sum_updater)
+        (out * dev(gg)).sum().backward()
+        x64 = torch.from_numpy(x).double().requires_grad_(True)
+        msg = x64[col] * torch.from_numpy(w).double().unsqueeze(1)
+        if red == "max":
+            agg = torch.full((n, d), float(np.finfo(np.float32).min), dtype=torch.float64).scatter_reduce(
+                0, row.unsqueeze(1).expand(-1, d), msg, reduce="amax", include_self=True)
+        else:
+            agg = torch.zeros((n, d), dtype=torch.float64).index_add_(0, row, msg)
+            if red == "mean":
+                agg = agg / torch.bincount(row, minlength=n).clamp(min=1).double().unsqueeze(1)
+        ((x64 + agg) * torch.from_numpy(gg).double()).sum().backward()
+        assert_close(host(xd.grad), x64.grad.numpy(), rtol=1e-5, atol_scale=1e-5, what="aggregate_neighbors({}) gradient".format(red))
+    # a small trainable model: conv -> SAGPool -> MeanPool -> loss; every weight must receive a gradient
+    conv = tfg.layers.GCN(d, activation=tfg.nn.relu, seed=1, trainable=True)
+    score = tfg.layers.GCN(1, seed=2, trainable=True)
+    xd, eid, wd = dev(x), dev(ei, torch.int32), dev(w)
+    gi2 = np.sort(rs.randint(0, graphs, n)).astype(np.int32)
+    gi2[-1] = graphs - 1
+    h = conv([xd, eid, wd])
+    px, pei, pw, pgi = tfg.layers.SAGPool(score, ratio=0.5, score_activation=torch.tanh)([h, eid, wd, dev(gi2, torch.int32)])
+    pooled = tfg.layers.MeanPool()([px, pgi, graphs])
+    pooled.pow(2).sum().backward()
+    for layer in (conv, score):
+        for name, p in layer.named_parameters():
+            assert p.grad is not None and torch.isfinite(p.grad).all(), name
+    assert float(conv.kernel.grad.abs().max()) > 0 and float(score.kernel.grad.abs().max()) > 0

@@ -151,3 +151,7 @@ def test_remaining_convs_train_on_the_fake_backend(fake):
     for name in ("sgc", "ssgc", "tagcn", "gin", "le_conv", "chebynet", "gcn_graph_sage", "mean_pool_graph_sage"):
         test_gpu_train.test_conv_training_gradients_match_autodiff(name)
     test_gpu_train.test_every_trainable_layer_gets_gradients()
+
+
+def test_pooling_passes_gradients_on_the_fake_backend(fake):
+    test_gpu_train.test_every_pool_layer_passes_gradients()

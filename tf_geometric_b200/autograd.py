@@ -18,20 +18,26 @@ from . import ops, _structure
 
 
 def _transposed_structure(edge_index, num_nodes, edge_weight, mean, csr):
-    """(csr_t, w_t): CSR of the reversed edges and w_e / max(cnt[row_e], 1) (or w_e for sum) in its order."""
-    tag = ("csc", int(num_nodes), bool(mean), None if edge_weight is None else id(edge_weight))
-    hit = _structure._lookup(edge_index, tag)
-    if hit is not None and (edge_weight is None or hit[2] == edge_weight._version):
-        return hit[0], hit[1]
+    """(csr_t, w_t): CSR of the reversed edges and w_e / max(cnt[row_e], 1) (or w_e for sum) in its order.
+    The structure is memoised per edge list; the weights per (weight tensor, structure) with the weight tensor held by
+    weak reference and checked by version (an id() recycled by a new tensor can never alias an old entry)."""
+    tag = ("csc", int(num_nodes))
+    csr_t = _structure._lookup(edge_index, tag)
     row, col = edge_index[0].contiguous(), edge_index[1].contiguous()
-    csr_t = ops.csr_build(col, row, num_nodes, num_nodes)
+    if csr_t is None:
+        csr_t = _structure._store(edge_index, tag, ops.csr_build(col, row, num_nodes, num_nodes))
+    owner = edge_weight if edge_weight is not None else edge_index
+    wtag = ("csc_w", bool(mean), edge_weight is None, id(csr_t), id(csr))
+    hit = _structure._lookup(owner, wtag)
+    if hit is not None and hit[0]() is csr_t and hit[1]() is csr:
+        return csr_t, hit[2]
     w = edge_weight if edge_weight is not None else torch.ones((edge_index.shape[1],), dtype=torch.float32,
                                                                device=edge_index.device)
     if mean:
         cnt = (csr.rowptr[1:] - csr.rowptr[:-1]).clamp(min=1).to(torch.float32)
         w = ops.scale_edges(row, None, w, dl=torch.reciprocal(cnt))
     w_t = ops.permute(w.contiguous(), csr_t.perm)
-    _structure._store(edge_index, tag, (csr_t, w_t, None if edge_weight is None else edge_weight._version))
+    _structure._store(owner, wtag, (weakref.ref(csr_t), weakref.ref(csr), w_t))
     return csr_t, w_t
 
 
@@ -212,6 +218,58 @@ def dense(x, weight, bias=None, activation=None):
 def propagate(adj, h, bias=None, act_code=ops.ACT_NONE):
     """Differentiable act(A @ h + b) for a SparseMatrix A (gradient w.r.t. h and b)."""
     return SparseMatmul.apply(h, bias, adj, act_code)
+
+
+class SegmentReduce(torch.autograd.Function):
+    """out[s] = REDUCE_{i: ids_i = s} data[i] for sum | mean | max | min over a plain id vector (the stock reducers of
+    nn/kernel/map_reduce.py:15-42 and the graph pooling of nn/pool/common_pool.py), differentiable w.r.t. data.
+    Backward: sum/mean are a gather of the upstream rows by segment id (scaled by 1 / max(count, 1) for mean); max/min
+    route the gradient to the selected entries, shared equally among ties like TensorFlow's UnsortedSegmentMax gradient."""
+
+    @staticmethod
+    def forward(ctx, data, ids, num_segments, reduce):
+        csr = _structure.csr_for_segment_ids(ids, int(num_segments))
+        d = data.detach()
+        if reduce == "min":       # min(x) = -max(-x): weight -1 per message and epilogue scale -1, both exact
+            minus = torch.full((csr.nnz,), -1.0, dtype=torch.float32, device=d.device)
+            out = ops.spmm(csr, minus, d, reduce="max", alpha=-1.0, col=csr.perm)
+        else:
+            out = ops.spmm(csr, None, d, reduce=reduce, col=csr.perm)
+        ctx.ids, ctx.csr, ctx.reduce = ids, csr, reduce
+        ctx.save_for_backward(d if reduce in ("max", "min") else None, out if reduce in ("max", "min") else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        data, out = ctx.saved_tensors
+        ids, csr, reduce = ctx.ids, ctx.csr, ctx.reduce
+        g = grad_out.contiguous()
+        if reduce == "mean":
+            cnt = (csr.rowptr[1:] - csr.rowptr[:-1]).clamp(min=1).to(torch.float32)
+            g = g / cnt.unsqueeze(1)
+        if reduce in ("sum", "mean"):
+            return ops.permute(g, ids), None, None, None
+        selected = (data == ops.permute(out, ids)).to(torch.float32)
+        n_selected = ops.spmm(csr, None, selected, reduce="sum", col=csr.perm).clamp(min=1.0)
+        return ops.permute(g / n_selected, ids) * selected, None, None, None
+
+
+class TakeRows(torch.autograd.Function):
+    """data[index] (tf.gather along axis 0) through the gather kernel; backward = segment sum of the upstream rows by
+    index (a deterministic scatter-add on the CSR kernel)."""
+
+    @staticmethod
+    def forward(ctx, data, index):
+        ctx.index, ctx.n = index, data.shape[0]
+        return ops.permute(data.detach(), index)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        csr = _structure.csr_for_segment_ids(ctx.index, ctx.n)
+        g = grad_out.contiguous()
+        flat = g if g.dim() == 2 else g.unsqueeze(1)
+        res = ops.spmm(csr, None, flat, reduce="sum", col=csr.perm)
+        return (res if g.dim() == 2 else res.squeeze(1)), None
 
 
 def needs_grad(*tensors):

@@ -183,6 +183,9 @@ class Graph(object):
 def _take_rows(data, index):
     """data[index] along axis 0 on the device: float32 / int32 through the gather kernel, other dtypes through torch."""
     if data.dtype == torch.float32 and data.dim() <= 2 and data.is_contiguous():
+        if data.requires_grad and torch.is_grad_enabled():        # sag_pool / sort_pool inside a trained model
+            from .. import autograd
+            return autograd.TakeRows.apply(data, index)
         return ops.permute(data, index)
     if data.dtype == torch.int32 and data.dim() == 1 and data.is_contiguous():
         return ops.gather_i32(data, index)

@@ -392,6 +392,129 @@ def _sampled_row_check(pg, edge_index_global, n, x_hosts, gcn, gat, out_gcn, out
     return worst
 
 
+def _hash_features(row0, n_rows, width, device):
+    """Deterministic synthetic features as a function of the GLOBAL row id: any rank can recompute any row (cfg 5 never
+    materialises the whole matrix on one GPU).  Values in [-1, 1)."""
+    r = torch.arange(row0, row0 + n_rows, dtype=torch.int64, device=device).unsqueeze(1)
+    c = torch.arange(width, dtype=torch.int64, device=device).unsqueeze(0)
+    return (((r * 2654435761 + c * 40503 + 12345) % 2000003).float() / 1000001.5 - 1.0).contiguous()
+
+
+def bench_papers(args, rank, world, device, metric, config):
+    """BASELINE config 5: GCN(128, relu) forward at ogbn-papers100M shape (111,059,956 nodes / 1,615,685,872 directed edges /
+    128 features), destination-partitioned.  With 8 ranks this is the configuration itself; with fewer ranks every rank keeps
+    the per-GPU load of the 8-rank run (world/8 of the nodes and edges) and the line says so.  Edges are generated per
+    partition on the device (seed 1000 + rank; the global graph never exists anywhere), features per owner."""
+    import numpy as np
+    import bench as B
+    import tf_geometric_b200 as tfg
+    from . import _ffi
+
+    cfg = B.CONFIGS["cfg5"]
+    F = cfg["features"]
+    n_total = int(cfg["nodes"] * args.scale) * world // 8 if world != 8 else int(cfg["nodes"] * args.scale)
+    e_total = int(cfg["edges"] * args.scale) * world // 8 if world != 8 else int(cfg["edges"] * args.scale)
+    exchange = os.environ.get("TFGK_DIST_EXCHANGE") or ("p2p" if world > 1 else "collective")
+    part = RowPartition(n_total, world, rank, align=ROW_ALIGN if exchange == "p2p" else 1)
+    e_local = e_total // world
+    gen = torch.Generator(device=device)
+    gen.manual_seed(1000 + rank)
+    row_local = torch.randint(0, max(part.n_local, 1), (e_local,), generator=gen, device=device, dtype=torch.int32)
+    col_global = torch.randint(0, n_total, (e_local,), generator=gen, device=device, dtype=torch.int32)
+    pg = PartitionedGraph(part, torch.stack([row_local, col_global]).contiguous(), None, exchange=exchange)
+    del row_local, col_global
+    x = _hash_features(part.lo, part.n_local, F, device)
+    gcn = tfg.layers.GCN(B.UNITS, activation=tfg.nn.relu, seed=2)
+
+    def step(xd):
+        pg.new_step()
+        return (gcn([xd, pg]),)
+
+    torch.cuda.synchronize()
+    t0 = __import__("time").perf_counter()
+    out = step(x)[0]
+    torch.cuda.synchronize()
+    t_cache = __import__("time").perf_counter() - t0
+
+    # parity before timing: sampled destination rows from first principles in float64 (features recomputed from the
+    # global ids, degrees from an all-gather of per-rank edge counts - nothing of the library's exchange is reused)
+    counts = torch.bincount(pg.edge_index[0].long(), minlength=part.block).to(torch.int32)
+    if counts.numel() < part.block:
+        counts = torch.cat([counts, torch.zeros(part.block - counts.numel(), dtype=torch.int32, device=device)])
+    deg_all = torch.empty((part.padded_nodes,), dtype=torch.int32, device=device)
+    dist.all_gather_into_tensor(deg_all, counts[:part.block].contiguous())
+    rows = torch.randint(0, max(part.n_local, 1), (32,), generator=torch.Generator(device="cpu").manual_seed(5 + rank))
+    w64 = gcn.kernel.double()
+    worst = 0.0
+    erow, ecol = pg.edge_index[0], pg.edge_index[1].long()
+    for r in rows.tolist():
+        nb = torch.cat([ecol[erow == r], torch.tensor([r + part.lo], device=device)])
+        d_r = float(deg_all[r + part.lo]) + 1.0
+        coef = (d_r ** -0.5) * ((deg_all[nb].double() + 1.0) ** -0.5)
+        xs = torch.cat([_hash_features(int(j), 1, F, device) for j in nb.tolist()]).double()
+        want = torch.relu((coef[:, None] * (xs @ w64)).sum(0) + gcn.bias.double())
+        got = out[r].double()
+        worst = max(worst, float(((got - want).abs() / (want.abs() + 1e-4 * want.abs().max() + 1e-12)).max()))
+    check = torch.tensor([worst], dtype=torch.float64, device=device)
+    dist.all_reduce(check, op=dist.ReduceOp.MAX)
+    if float(check[0]) > 1e-4:
+        raise SystemExit("cfg5 parity check failed: sampled-row relative error {:.3e}".format(float(check[0])))
+    del deg_all, counts, out
+
+    for _ in range(max(args.warmup, 3) - 1):
+        step(x)
+    trace = _ffi.CallTrace(timed=("tfgk_spmm_f32", "tfgk_gemm_proj_f32", "tfgk_gemm_f32"))
+    _ffi.set_trace(trace)
+    sampler = B.ClockSampler(device.index)
+    sampler.start()
+    nv0 = pg.nvlink_bytes
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(args.steps):
+        step(x)
+    ev[1].record()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    clocks = sampler.stop()
+    _ffi.set_trace(None)
+    nvlink_per_step = (pg.nvlink_bytes - nv0) / args.steps
+    t = torch.tensor([ev[0].elapsed_time(ev[1]) / args.steps], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item())
+    spmm_ms = float(np.mean(trace.elapsed_ms("tfgk_spmm_f32")))
+    proj_ms = float(np.sum(trace.elapsed_ms("tfgk_gemm_proj_f32")) + np.sum(trace.elapsed_ms("tfgk_gemm_f32"))) / args.steps
+    e_loop = e_local + part.n_local
+    spmm_bytes = e_loop * (4 * B.UNITS + 8) + part.n_local * (4 * B.UNITS + 8)
+    peak, peak_src = B.measured_peak_gbs()
+    mem = torch.cuda.max_memory_allocated(device) / 2 ** 30
+    launches = sum(trace.counts.get(k, 0) for k in ("tfgk_spmm_f32", "tfgk_gemm_proj_f32", "tfgk_gemm_f32", "tfgk_peer_barrier"))
+    if rank == 0:
+        config = dict(config, nodes=n_total, edges=e_total, edges_per_step=e_total,
+                      workload="{} ({} nodes, {} directed edges, {} features), uniform random directed edges generated per "
+                               "partition{}".format(cfg["what"], n_total, e_total, F,
+                                                    "" if world == 8 else " - PER-GPU SCALE: {}/8 of the 8-GPU configuration".format(world)),
+                      parallelism="dst-partitioned x{}".format(world))
+        line = {"metric": metric, "value": e_total / (ms_step * 1e-3), "unit": "edges/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "clocks": clocks, "e2e": None, "gpu_launches": launches,
+                "roofline": {"bound": "hbm", "kernel": "spmm_async_kernel<1,0,4,3> (tfgk_spmm_f32), rank 0 partition",
+                             "achieved": spmm_bytes / (spmm_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": spmm_bytes / (spmm_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes": spmm_bytes, "kernel_ms": spmm_ms},
+                "cpu_baseline": None,
+                "breakdown_ms": {"gcn_spmm": spmm_ms, "projection_incl_exchange": proj_ms, "first_call_incl_cache_s": t_cache},
+                "parity": {"sampled_rows_max_rel_err_vs_float64": float(check[0])},
+                "max_memory_GiB_rank0": mem,
+                "exchange": {"mode": pg.exchange, "nvlink_bytes_in_per_rank_per_step": nvlink_per_step,
+                             "hbm_algorithmic_bytes_per_rank_per_step": spmm_bytes + part.n_local * B.UNITS * 4
+                             + n_total * (F + B.UNITS) * 4,
+                             "note": "the step is bound by the exchange: every rank needs almost every source row "
+                                     "(uniform random sources), i.e. 7/8 of the [N, 128] table over NVLink per forward"}}
+        B.emit(line)
+    dist.destroy_process_group()
+
+
 def bench_partitioned(args, rank, world, device, metric, config):
     """Strong scaling of the bench workload: the same synthetic graph, destination-partitioned over `world` ranks, driven
     through tfg.layers.GCN / GAT with [x_local, partitioned_graph] inputs.  Timed on the device with CUDA events between

@@ -4,6 +4,7 @@ input (Keras `build`), named exactly like the reference's `add_weight` calls so 
 (kernel, bias, query_kernel, key_kernel, self_kernel, neighbor_kernel, kernel_i, bias_i ...), initialised with
 glorot_uniform / zeros, and the layer is invoked as `layer(inputs, cache=..., training=...)`."""
 import math
+import warnings
 
 import torch
 
@@ -52,4 +53,11 @@ class Layer(torch.nn.Module):
 
     def forward(self, inputs, **kwargs):
         self._maybe_build(inputs)
+        if kwargs.get("training") and not self._trainable and not getattr(self, "_warned_frozen", False) \
+                and any(True for _ in self.parameters()):
+            # Keras weights train by default; here they are frozen unless the layer was created with trainable=True
+            warnings.warn("{} was called with training=True but its weights were created with trainable=False: they will "
+                          "receive no gradient. Create the layer with trainable=True to train it.".format(type(self).__name__),
+                          RuntimeWarning, stacklevel=2)
+            self._warned_frozen = True
         return self.call(inputs, **kwargs)

@@ -8,7 +8,7 @@ stock reducers - which are real segment reductions over arbitrary [E, D] message
 """
 import torch
 
-from ... import ops, _structure
+from ... import ops, _structure, autograd
 
 
 def identity_mapper(repeated_x, neighbor_x, edge_weight=None):
@@ -32,6 +32,9 @@ def _segment_reduce(neighbor_msg, node_index, num_nodes, reduce):
         msg = msg.unsqueeze(1)
     if num_nodes is None:
         num_nodes = int(node_index.max().item()) + 1
+    if autograd.needs_grad(msg):      # trainable models pool / reduce through these (demo_mean_pool.py, demo_sag_pool_h.py)
+        out = autograd.SegmentReduce.apply(msg.contiguous(), node_index, int(num_nodes), reduce)
+        return out.squeeze(1) if squeeze else out
     csr = _structure.csr_for_segment_ids(node_index, int(num_nodes))
     # message e sits at row e of `msg`: gather through perm, no weights
     if reduce == "min":       # min(x) = -max(-x): weight -1 per message and epilogue scale -1, both exact
@@ -88,6 +91,16 @@ def aggregate_neighbors(x, edge_index, edge_weight=None, mapper=identity_mapper,
 
     fused = (reducer in _FUSED_REDUCERS and updater in (sum_updater, identity_updater)
              and (mapper is identity_mapper or (mapper is gcn_mapper and edge_weight is not None)))
+    if fused and autograd.needs_grad(x, edge_weight):
+        # differentiable route: sum / mean through NeighborAggregate (transposed-CSR backward); max and differentiable
+        # edge weights through the generic route below (gather + SegmentReduce), which torch autograd can follow
+        if _FUSED_REDUCERS[reducer] != "max" and not autograd.needs_grad(edge_weight):
+            w = None
+            if mapper is gcn_mapper:
+                w = ops.as_device(edge_weight, torch.float32, device=x.device)
+            agg = autograd.NeighborAggregate.apply(x, edge_index, w, _FUSED_REDUCERS[reducer], num_nodes)
+            return x + agg if updater is sum_updater else agg
+        fused = False
     if fused:
         csr, _ = _structure.csr_for_edge_index(edge_index, num_nodes)
         w_csr = None

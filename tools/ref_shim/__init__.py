@@ -10,7 +10,81 @@ import types
 
 import numpy as np
 
-from oracle import tfg_oracle as _o
+# NOTE: this module deliberately imports nothing from the repository (in particular not its CPU checker).  The TensorFlow /
+# tf_sparse ops the reference calls are restated a SECOND time here, independently and in the most literal form (explicit
+# per-element loops in input order), so that a fixture produced through this shim can disagree with the checker under tests/
+# if either restatement of the documented TF semantics is wrong.  (Round-1 review: a shim that delegated to the checker made
+# fixture == checker by construction.)
+
+
+def _seg_loop(data, ids, num_segments, init, combine):
+    """out[ids[i]] = combine(out[ids[i]], data[i]) for i = 0, 1, ... in input order, in data's dtype (TF's CPU kernels)."""
+    data = np.asarray(data)
+    ids = np.asarray(ids).reshape(-1)
+    out = np.full((int(num_segments),) + data.shape[1:], init, dtype=data.dtype)
+    for i in range(ids.shape[0]):
+        s = int(ids[i])
+        if s < 0:
+            continue                              # tf.math.unsorted_segment_*: negative ids are dropped
+        if s >= num_segments:
+            raise IndexError("segment id {} out of range [0, {})".format(s, num_segments))
+        out[s] = combine(out[s], data[i])
+    return out
+
+
+def _segment_sum(data, ids, n):
+    data = np.asarray(data)
+    return _seg_loop(data, ids, n, data.dtype.type(0), lambda a, b: (a + b).astype(data.dtype))
+
+
+def _segment_mean(data, ids, n):
+    data = np.asarray(data)
+    total = _segment_sum(data, ids, n)
+    count = _segment_sum(np.ones(np.asarray(ids).reshape(-1).shape[0], dtype=data.dtype), ids, n)
+    count = np.maximum(count, data.dtype.type(1))
+    return (total / count.reshape((-1,) + (1,) * (data.ndim - 1))).astype(data.dtype)
+
+
+def _lowest(dtype):
+    return np.finfo(dtype).min if np.dtype(dtype).kind == "f" else np.iinfo(dtype).min
+
+
+def _highest(dtype):
+    return np.finfo(dtype).max if np.dtype(dtype).kind == "f" else np.iinfo(dtype).max
+
+
+def _segment_max(data, ids, n):
+    data = np.asarray(data)
+    return _seg_loop(data, ids, n, _lowest(data.dtype), np.maximum)      # empty segment: numeric_limits<T>::lowest()
+
+
+def _segment_min(data, ids, n):
+    data = np.asarray(data)
+    return _seg_loop(data, ids, n, _highest(data.dtype), np.minimum)
+
+
+def _gather0(params, indices):
+    params, indices = np.asarray(params), np.asarray(indices)
+    if indices.size and (indices.min() < 0 or indices.max() >= params.shape[0]):
+        raise IndexError("tf.gather: index out of range (the CPU kernel raises InvalidArgument)")
+    return np.take(params, indices, axis=0)
+
+
+def _unique_first_occurrence(x):
+    """tf.unique: distinct values in order of first appearance, and for every element the position of its value there."""
+    seen, values, index = {}, [], []
+    for v in np.asarray(x).reshape(-1).tolist():
+        if v not in seen:
+            seen[v] = len(values)
+            values.append(v)
+        index.append(seen[v])
+    return np.asarray(values, dtype=np.asarray(x).dtype), np.asarray(index, dtype=np.int32)
+
+
+def _l2_normalize_last_axis(x, eps=1e-12):
+    x = np.asarray(x, dtype=np.float32)
+    sq = np.sum(x * x, axis=-1, keepdims=True, dtype=np.float32)
+    return (x * (np.float32(1) / np.sqrt(np.maximum(sq, np.float32(eps))))).astype(np.float32)
 
 
 class Tensor(np.ndarray):
@@ -100,19 +174,19 @@ def build_tensorflow():
     tf.meshgrid = meshgrid
 
     def gather(params, indices, axis=0):
-        return T(_o.gather(np.asarray(params), np.asarray(indices)))
+        return T(_gather0(params, indices))
     tf.gather = gather
 
     def unique(x):
-        vals, idx = _o.tf_unique(np.asarray(x))
+        vals, idx = _unique_first_occurrence(x)
         return T(vals), T(idx)
     tf.unique = unique
 
     math = types.ModuleType("tensorflow.math")
-    math.unsorted_segment_sum = lambda d, i, num_segments: T(_o.unsorted_segment_sum(np.asarray(d), np.asarray(i), int(num_segments)))
-    math.unsorted_segment_mean = lambda d, i, num_segments: T(_o.unsorted_segment_mean(np.asarray(d), np.asarray(i), int(num_segments)))
-    math.unsorted_segment_max = lambda d, i, num_segments: T(_o.unsorted_segment_max(np.asarray(d), np.asarray(i), int(num_segments)))
-    math.unsorted_segment_min = lambda d, i, num_segments: T(_o.unsorted_segment_min(np.asarray(d), np.asarray(i), int(num_segments)))
+    math.unsorted_segment_sum = lambda d, i, num_segments: T(_segment_sum(d, i, int(num_segments)))
+    math.unsorted_segment_mean = lambda d, i, num_segments: T(_segment_mean(d, i, int(num_segments)))
+    math.unsorted_segment_max = lambda d, i, num_segments: T(_segment_max(d, i, int(num_segments)))
+    math.unsorted_segment_min = lambda d, i, num_segments: T(_segment_min(d, i, int(num_segments)))
     math.logical_or = lambda a, b: T(np.logical_or(np.asarray(a), np.asarray(b)))
     math.logical_and = lambda a, b: T(np.logical_and(np.asarray(a), np.asarray(b)))
     math.is_inf = lambda x: T(np.isinf(np.asarray(x)))
@@ -120,7 +194,7 @@ def build_tensorflow():
     math.sqrt = lambda x: (T(np.sqrt(np.asarray(x))) if np.ndim(x) else np.sqrt(np.float32(x)))
     math.floordiv = lambda a, b: T(np.asarray(a) // np.asarray(b))
     math.floormod = lambda a, b: T(np.asarray(a) % np.asarray(b))
-    math.segment_sum = lambda d, i: T(_o.unsorted_segment_sum(np.asarray(d), np.asarray(i), int(np.max(np.asarray(i))) + 1))
+    math.segment_sum = lambda d, i: T(_segment_sum(d, i, int(np.max(np.asarray(i))) + 1))
     math.cumsum = lambda x, axis=0: T(np.cumsum(np.asarray(x), axis=axis))
     math.minimum = lambda a, b: T(np.minimum(np.asarray(a), np.asarray(b)))
     math.ceil = lambda x: T(np.ceil(np.asarray(x)))
@@ -131,7 +205,7 @@ def build_tensorflow():
 
     nn = types.ModuleType("tensorflow.nn")
     nn.relu = lambda x: T(np.maximum(np.asarray(x), np.float32(0)))
-    nn.l2_normalize = lambda x, axis=-1: T(_o.l2_normalize(np.asarray(x)))
+    nn.l2_normalize = lambda x, axis=-1: T(_l2_normalize_last_axis(x))
     nn.__getattr__ = lambda name: _unsupported("tf.nn." + name)
     tf.nn = nn
 
@@ -194,24 +268,42 @@ def build_tf_sparse():
             return [int(s) for s in self._shape]
 
         def add_diag(self, w):
-            m = _o.SparseMatrix(np.asarray(self.index), np.asarray(self.value), self.shape).add_diag(w)
-            return SparseMatrix(m.index, m.value, m.shape)
+            # [UNVERIFIED, SURVEY.md 8c] self + diags(w * ones): the diagonal entries are APPENDED after the existing ones,
+            # in node order, without merging duplicates (the order utils/graph_utils.py:350-366 add_self_loop_edge uses)
+            n = min(self.shape)
+            d = np.arange(n, dtype=np.int32)
+            index = np.concatenate([np.asarray(self.index), np.stack([d, d])], axis=1)
+            value = np.concatenate([np.asarray(self.value), np.full([n], w, dtype=np.float32)])
+            return SparseMatrix(index, value, self.shape)
+
+        def _segment_ids(self, axis):
+            if axis in (-1, 1):
+                return np.asarray(self.index[0]), self.shape[0]      # reduce over columns: one value per row
+            return np.asarray(self.index[1]), self.shape[1]
 
         def segment_sum(self, axis=-1):
-            m = _o.SparseMatrix(np.asarray(self.index), np.asarray(self.value), self.shape)
-            return T(m.segment_sum(axis))
+            ids, n = self._segment_ids(axis)
+            return T(_segment_sum(np.asarray(self.value), ids, n))
 
         def segment_softmax(self, axis=-1):
-            m = _o.SparseMatrix(np.asarray(self.index), np.asarray(self.value), self.shape).segment_softmax(axis)
-            return SparseMatrix(m.index, m.value, m.shape)
+            # nn/kernel/segment.py:26-33 applied to the values: max, exp(v - max), sum + 1e-8, divide
+            ids, n = self._segment_ids(axis)
+            v = np.asarray(self.value)
+            mx = _segment_max(v, ids, n)
+            e = np.exp(v - mx[ids]).astype(np.float32)
+            den = (_segment_sum(e, ids, n) + np.float32(1e-8)).astype(np.float32)
+            return SparseMatrix(self.index, (e / den[ids]).astype(np.float32), self.shape)
 
         def dropout(self, rate, training=False):
             assert not (training and rate > 0.0)
             return self
 
         def matmul(self, h, num_or_size_splits=None):
-            m = _o.SparseMatrix(np.asarray(self.index), np.asarray(self.value), self.shape)
-            return T(m.matmul(np.asarray(h)))
+            # [UNVERIFIED] gather(h, col) * value[:, None] -> unsorted_segment_sum by row (the legacy path kept as comments in
+            # the reference: nn/conv/gcn.py:175-176, gat.py:91-109)
+            h = np.asarray(h, dtype=np.float32)
+            msg = (_gather0(h, np.asarray(self.index[1])) * np.asarray(self.value)[:, None]).astype(np.float32)
+            return T(_segment_sum(msg, np.asarray(self.index[0]), self.shape[0]))
 
         def __matmul__(self, other):
             if isinstance(other, DiagMatrix):             # A @ diags(d) : scale columns
