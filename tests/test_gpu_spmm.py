@@ -170,3 +170,24 @@ def test_hub_rows_are_sliced_and_merged_deterministically(d):
     got = host(ops.spmm(csr, w_csr, dev(x), alpha=0.5, addend=dev(add), beta=2.0, bias=dev(bias), act=ops.ACT_RELU))
     np.testing.assert_array_equal(got[~is_hub], want[~is_hub])
     assert np.abs(got[is_hub] - want[is_hub]).max() <= 2e-5 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("d", [128, 100, 64, 32, 256, 200])
+@pytest.mark.parametrize("stages", ["2", "4", "8"])
+def test_tma_gather4_variant_is_bit_identical(d, stages, monkeypatch):
+    """K1 through TMA tile::gather4 (one instruction fetches four neighbour rows into the warp's ring): same bits as the
+    default cp.async ring for weighted sum, mean and max, ragged rows, empty rows and a hub row cut into slices."""
+    rs = np.random.RandomState(d)
+    n = 3000
+    ei = random_graph(n, 40000, seed=d, isolated=7, hub=(11, 9000))
+    csr = ops.csr_build(dev(ei[0]), dev(ei[1]), n, n)
+    w = dev((rs.rand(ei.shape[1]) + 0.1).astype(np.float32))
+    h = dev(rs.randn(n, d).astype(np.float32))
+    bias = dev(rs.randn(d).astype(np.float32))
+    for reduce, weights in (("sum", w), ("mean", None), ("max", w)):
+        monkeypatch.delenv("TFGK_SPMM_IMPL", raising=False)
+        want = ops.spmm(csr, weights, h, reduce=reduce, bias=bias, act=ops.ACT_RELU)
+        monkeypatch.setenv("TFGK_SPMM_IMPL", "gather4")
+        monkeypatch.setenv("TFGK_SPMM_GATHER4_STAGES", stages)
+        got = ops.spmm(csr, weights, h, reduce=reduce, bias=bias, act=ops.ACT_RELU)
+        assert torch.equal(got, want), "gather4 changed bits (D={}, reduce={})".format(d, reduce)

@@ -35,7 +35,7 @@ constexpr int kStageBytes = 32 * kStageRowBytes;
 struct Params {
     const float *A[kMaxParts];
     int64_t lda, part_rows;
-    int n_parts, first_tile;
+    int n_parts, first_tile, local_part;
     int M, K, nb, tiles_m, n_groups;
     const float *B[kMaxBlocks]; int64_t ldb[kMaxBlocks];
     const float *bias[kMaxBlocks]; int act[kMaxBlocks]; int ncols[kMaxBlocks];
@@ -124,11 +124,29 @@ __global__ void __launch_bounds__(kThreadsProj, 1) gemm_proj_kernel(const Params
         const uint32_t a_ring_addr = smem_u32(a_ring);
         constexpr int kChunks = (BM * BK / 4) / (kProducerWarps * 32);      // 8 per thread per k-block
         const int r8 = t & 7, kc = (t >> 3) & 7, rg0 = t >> 6;              // chunk c = t + 128 i: rows (rg0 + 2 i) * 8 + r8
+        // L2 prefetch of whole row tiles kPrefetchTiles ahead (one bulk-prefetch instruction per tile, issued by the group's
+        // first column block): the cp.async ring can only keep ~25 KB in flight per SM next to the resident W, which at
+        // DRAM latency is ~1/4 of what the tensor core consumes; with the tile already in L2 the same ring is enough.
+        // Peer-mapped parts are not prefetched (remote data bypasses the local L2).
+        constexpr int kPrefetchTiles = 4;
+        const bool can_prefetch = (cb == 0) && (t == 0) && p.lda <= 2 * (int64_t)p.K;
+        auto prefetch_tile = [&](int it) {
+            if (!can_prefetch || it >= my_tiles) return;
+            const int64_t m0 = (int64_t)tile_of(it) * BM;
+            const int part = p.n_parts > 1 ? (int)(m0 / p.part_rows) : 0;
+            if (p.n_parts > 1 && part != p.local_part) return;
+            const int64_t rows = min((int64_t)BM, (int64_t)p.M - m0);
+            const float *src = p.A[part] + (m0 - (int64_t)part * p.part_rows) * p.lda;
+            const uint32_t bytes = (uint32_t)(rows * p.lda * 4);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+        };
+        for (int i = 0; i < kPrefetchTiles; ++i) prefetch_tile(i);
         auto issue_load = [&](int G) {
             if (G < total_kb) {
                 const int stage = G % STAGES;
                 mbar_wait(&empty[stage], (uint32_t)(((G / STAGES) & 1) ^ 1));
                 const int tile = tile_of(G / nkb), kb = G % nkb;
+                if (kb == 0) prefetch_tile(G / nkb + kPrefetchTiles);
                 const int k = kb * BK + kc * 4;
                 if (k < (int)L.kpad8) {
                     const int64_t m0 = (int64_t)tile * BM;
@@ -308,6 +326,7 @@ extern "C" int tfgk_gemm_proj_f32(const float *const *A_parts, int32_t n_parts, 
     p.M = M; p.K = K; p.nb = n_blocks;
     p.tiles_m = (int)ceil_div64(M, tc::BM);
     p.first_tile = n_parts > 1 ? (int)((int64_t)first_part * part_rows / tc::BM) : 0;
+    p.local_part = n_parts > 1 ? (first_part + n_parts - 1) % n_parts : 0;      // the walk starts one past the caller's own part
     if (p.first_tile >= p.tiles_m) p.first_tile = 0;
     for (int b = 0; b < proj::kMaxBlocks; ++b) {
         const tfgk_proj_block &blk = blocks[b < n_blocks ? b : 0];

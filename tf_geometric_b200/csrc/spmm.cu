@@ -652,6 +652,190 @@ __global__ void __launch_bounds__(kAsyncWarps * 32) spmm_async_kernel(const Spmm
     while (r < r1) finalize_row();
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// TMA tile::gather4 variant (north_star: "staged through TMA into shared memory").  Same edge streaming, ring and
+// arithmetic as spmm_async_kernel, but a round of U = 4 edges is ONE instruction
+//     cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4 [ring stage], [tensor map of h, {0, c0, c1, c2, c3}], [mbarrier]
+// issued by one lane: the TMA unit fetches the four neighbour rows (box = D columns x 1 row each) and completes the
+// stage's mbarrier with 4 * row_bytes transaction bytes.  That is a quarter of the TMA issue rate that sank the 1-D
+// cp.async.bulk variant (one 512-byte copy per row, spmm_bulk_kernel) and frees the 4 LDGSTS issue slots per lane and
+// round of the cp.async ring.  Each warp owns S mbarriers; a stage is re-armed only after every lane has read it
+// (__syncwarp before the elected lane issues).  Rows beyond the edge range repeat a valid row id (the bytes still count
+// towards the stage's transaction total) and are ignored by the consumer.  Same rounding and order => same bits.
+// ------------------------------------------------------------------------------------------------------------
+struct alignas(64) TensorMap { uint64_t opaque[16]; };      // CUtensorMap (128 bytes), filled by the driver on the host
+
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const TensorMap *map, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+        ::"r"(dst), "l"(map), "r"(0), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
+
+template <bool IS_MAX, int S>
+__global__ void __launch_bounds__(kAsyncWarps * 32) spmm_gather4_kernel(const SpmmParams p, uint32_t row_bytes,
+                                                                          const __grid_constant__ TensorMap tmap) {
+    constexpr int U = 4, RPC = 32 / U;
+    static_assert(S <= 2 * RPC, "weight look-ahead registers would be overwritten before they are consumed");
+    extern __shared__ __align__(128) uint8_t g4_ring[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t tx_bytes = U * row_bytes;
+    const uint32_t stage_bytes = (tx_bytes + 127u) & ~127u;      // TMA destinations are 128-byte aligned
+    uint8_t *my_ring = g4_ring + (size_t)warp * S * stage_bytes;
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(my_ring);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(g4_ring + (size_t)kAsyncWarps * S * stage_bytes) + warp * S;
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < S; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * i));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const int64_t task = (int64_t)blockIdx.x * kAsyncWarps + warp;
+    int64_t r0, r1, e_begin, e_stop;
+    int slot = -1;
+    if (p.task_row != nullptr) {
+        if (task >= p.n_tasks) return;
+        r0 = p.task_row[task];
+        r1 = r0 + p.task_nrows[task];
+        e_begin = p.task_e0[task];
+        e_stop = p.task_e1[task];
+        slot = p.task_slot[task];
+    } else {
+        r0 = task * kAsyncRows;
+        if (r0 >= p.n_dst) return;
+        r1 = min((int64_t)p.n_dst, r0 + kAsyncRows);
+        e_begin = p.rowptr[r0];
+        e_stop = p.rowptr[r1];
+    }
+    const int64_t rp_lo = p.rowptr[min(r0 + lane, r1)];
+    const int64_t rp_hi = p.rowptr[min(r0 + lane + 1, r1)];
+    const int n_edges = (int)(e_stop - e_begin);
+    const int n_rounds = (n_edges + U - 1) / U;
+    const bool weighted = p.w != nullptr;
+    constexpr int NCX = 2;                         // up to 256 columns: two float4 slices per lane
+    int coff[NCX];
+    bool cok[NCX];
+    float acc[NCX][4];
+#pragma unroll
+    for (int k = 0; k < NCX; ++k) {
+        coff[k] = (lane + 32 * k) * 4;
+        cok[k] = coff[k] < p.D;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) acc[k][x] = IS_MAX ? -FLT_MAX : 0.0f;
+    }
+    int64_t r = r0;
+    int row_end = slot >= 0 ? 0x7fffffff : (int)(__shfl_sync(0xffffffffu, rp_hi, 0) - e_begin);
+    const bool is_mean = p.reduce == TFGK_REDUCE_MEAN;
+
+    auto finalize_row = [&]() {
+        const int64_t row_start = __shfl_sync(0xffffffffu, rp_lo, (int)(r - r0));
+        const int deg = (int)(row_end + e_begin - row_start);
+        const float cnt = (float)max(deg, 1);
+#pragma unroll
+        for (int k = 0; k < NCX; ++k) {
+            if (cok[k]) {
+                float ad[4], bs[4], o[4];
+                if (p.addend) load_vec<4>(p.addend + r * p.ld_addend + coff[k], ad);
+                if (p.bias) load_vec<4>(p.bias + coff[k], bs);
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    float a = acc[k][x];
+                    if (is_mean) a = __fdiv_rn(a, cnt);
+                    if (p.addend) a = __fadd_rn(__fmul_rn(a, p.alpha), __fmul_rn(ad[x], p.beta));
+                    else if (p.alpha != 1.0f) a = __fmul_rn(a, p.alpha);
+                    if (p.bias) a = __fadd_rn(a, bs[x]);
+                    o[x] = apply_act(a, p.act);
+                    acc[k][x] = IS_MAX ? -FLT_MAX : 0.0f;
+                }
+                store_vec<4>(p.out + r * p.ldo + coff[k], o);
+            }
+        }
+        ++r;
+        if (r < r1) row_end = (int)(__shfl_sync(0xffffffffu, rp_hi, (int)(r - r0)) - e_begin);
+    };
+    auto load_chunk = [&](int c, int &ci, float &wi) {
+        const int e = c * 32 + lane;
+        ci = 0;
+        wi = 1.0f;
+        if (e < n_edges) {
+            ci = ld_stream_i32(p.col + e_begin + e);
+            if (weighted) wi = ld_stream_f32(p.w + e_begin + e);
+        }
+    };
+    // round g (edges [4g, 4g+4)) -> ring stage g % S: one gather4, armed and issued by lane 0
+    auto issue = [&](int g, int ci) {
+        if (g < n_rounds) {
+            const int base = (g % RPC) * U;
+            const int valid = min(U, n_edges - g * U);
+            const int c0 = __shfl_sync(0xffffffffu, ci, base);
+            int c1 = __shfl_sync(0xffffffffu, ci, base + 1), c2 = __shfl_sync(0xffffffffu, ci, base + 2);
+            int c3 = __shfl_sync(0xffffffffu, ci, base + 3);
+            if (valid < 2) c1 = c0;
+            if (valid < 3) c2 = c0;
+            if (valid < 4) c3 = c0;
+            if (lane == 0) {
+                const uint32_t bar = bar0 + 8 * (uint32_t)(g % S);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx_bytes) : "memory");
+                tma_gather4(ring_addr + (uint32_t)(g % S) * stage_bytes, &tmap, c0, c1, c2, c3, bar);
+            }
+        }
+    };
+
+    int ca, cb;
+    float wa, wb, wna = 1.0f, wnb = 1.0f;
+    load_chunk(0, ca, wa);
+    load_chunk(1, cb, wb);
+#pragma unroll
+    for (int g = 0; g < S - 1; ++g) issue(g, ((g / RPC) & 1) ? cb : ca);
+    if (S - 1 >= RPC) load_chunk(2, ca, wna);
+
+    for (int g = 0; g < n_rounds; ++g) {
+        __syncwarp();                               // every lane has finished reading stage (g-1) % S, which is re-armed now
+        {
+            const int gn = g + S - 1;
+            issue(gn, ((gn / RPC) & 1) ? cb : ca);
+        }
+        mbar_wait_parity(bar0 + 8 * (uint32_t)(g % S), (uint32_t)(g / S) & 1u);
+        const int cc = g / RPC;
+        const float wi = (cc & 1) ? wb : wa;
+        const int base = (g % RPC) * U;
+        const uint8_t *sbuf = my_ring + (size_t)(g % S) * stage_bytes;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = g * U + u;
+            const float we = __shfl_sync(0xffffffffu, wi, base + u);
+            if (e < n_edges) {
+                while (e == row_end) finalize_row();
+#pragma unroll
+                for (int k = 0; k < NCX; ++k) {
+                    if (cok[k]) {
+                        const float4 v = *reinterpret_cast<const float4 *>(sbuf + (size_t)u * row_bytes + coff[k] * 4);
+                        const float m0 = __fmul_rn(v.x, we), m1 = __fmul_rn(v.y, we), m2 = __fmul_rn(v.z, we), m3 = __fmul_rn(v.w, we);
+                        acc[k][0] = IS_MAX ? fmaxf(acc[k][0], m0) : __fadd_rn(acc[k][0], m0);
+                        acc[k][1] = IS_MAX ? fmaxf(acc[k][1], m1) : __fadd_rn(acc[k][1], m1);
+                        acc[k][2] = IS_MAX ? fmaxf(acc[k][2], m2) : __fadd_rn(acc[k][2], m2);
+                        acc[k][3] = IS_MAX ? fmaxf(acc[k][3], m3) : __fadd_rn(acc[k][3], m3);
+                    }
+                }
+            }
+        }
+        if ((g + 1) % RPC == 0) {
+            if (cc & 1) wb = wnb; else wa = wna;
+        }
+        if ((g + S) % RPC == 0) {
+            const int dead = (g + S) / RPC - 1;
+            if (dead & 1) load_chunk(dead + 2, cb, wnb); else load_chunk(dead + 2, ca, wna);
+        }
+    }
+    if (slot >= 0) {
+#pragma unroll
+        for (int k = 0; k < NCX; ++k)
+            if (cok[k]) store_vec<4>(p.scratch + (int64_t)slot * p.D + coff[k], acc[k]);
+        return;
+    }
+    while (r < r1) finalize_row();
+}
+
 // merges the slices of every hub row in slice order (deterministic) and applies the epilogue; one warp per hub row
 template <bool IS_MAX>
 __global__ void __launch_bounds__(256) spmm_hub_fixup_kernel(const SpmmParams p) {
@@ -709,6 +893,60 @@ static int launch_spmm_async(const SpmmParams &p, cudaStream_t st) {
     return TFGK_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef int (*EncodeTiledFn)(void *map, int dtype, uint32_t rank, void *base, const uint64_t *dims, const uint64_t *strides,
+                             const uint32_t *box, const uint32_t *elem_strides, int interleave, int swizzle, int l2promo,
+                             int oob_fill);
+
+static int make_row_tensor_map(TensorMap *out, const float *h, int64_t ldh, int64_t n_rows, int32_t D) {
+    static EncodeTiledFn encode = nullptr;
+    if (encode == nullptr) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        TFGK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (fn == nullptr || qres != cudaDriverEntryPointSuccess)
+            return set_error(TFGK_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available from this driver");
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    const uint64_t dims[2] = {(uint64_t)D, (uint64_t)n_rows};
+    const uint64_t strides[1] = {(uint64_t)ldh * sizeof(float)};          // byte stride of dimension 1 (rows)
+    const uint32_t box[2] = {(uint32_t)D, 1u};                            // gather4: 1 in the gathered dimension
+    const uint32_t elem[2] = {1u, 1u};
+    // CU_TENSOR_MAP_DATA_TYPE_FLOAT32 = 7, INTERLEAVE_NONE = 0, SWIZZLE_NONE = 0, L2_PROMOTION_L2_128B = 2, OOB_FILL_NONE = 0
+    const int rc = encode(out, 7, 2, const_cast<float *>(h), dims, strides, box, elem, 0, 0, 2, 0);
+    if (rc != 0) return set_error(TFGK_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled failed with CUresult %d", rc);
+    return TFGK_OK;
+}
+
+template <int S>
+static int launch_spmm_gather4(const SpmmParams &p, int64_t h_rows, cudaStream_t st) {
+    if (p.D > 256 || p.D % 4 != 0 || p.ldh % 4 != 0) return TFGK_ERR_UNSUPPORTED;
+    const uint32_t row_bytes = (uint32_t)p.D * 4u;
+    const size_t stage_pitch = ((size_t)4 * row_bytes + 127) & ~(size_t)127;
+    const size_t smem = (size_t)kAsyncWarps * S * stage_pitch + (size_t)kAsyncWarps * S * 8;
+    if (smem > 200 * 1024) return TFGK_ERR_UNSUPPORTED;
+    TensorMap tmap;
+    const int rc = make_row_tensor_map(&tmap, p.h, p.ldh, h_rows, p.D);
+    if (rc != TFGK_OK) return rc;
+    const int64_t n_tasks = p.task_row ? p.n_tasks : ceil_div64(p.n_dst, kAsyncRows);
+    const unsigned blocks = (unsigned)ceil_div64(n_tasks, kAsyncWarps);
+    if (p.reduce == TFGK_REDUCE_MAX) {
+        TFGK_CUDA(cudaFuncSetAttribute(spmm_gather4_kernel<true, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        spmm_gather4_kernel<true, S><<<blocks, kAsyncWarps * 32, smem, st>>>(p, row_bytes, tmap);
+    } else {
+        TFGK_CUDA(cudaFuncSetAttribute(spmm_gather4_kernel<false, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        spmm_gather4_kernel<false, S><<<blocks, kAsyncWarps * 32, smem, st>>>(p, row_bytes, tmap);
+    }
+    TFGK_LAUNCH_CHECK();
+    if (p.task_row && p.n_hubs > 0) {
+        const unsigned fb = (unsigned)ceil_div64(p.n_hubs, 8);
+        if (p.reduce == TFGK_REDUCE_MAX) spmm_hub_fixup_kernel<true><<<fb, 256, 0, st>>>(p);
+        else spmm_hub_fixup_kernel<false><<<fb, 256, 0, st>>>(p);
+        TFGK_LAUNCH_CHECK();
+    }
+    return TFGK_OK;
+}
+
 static int dispatch_spmm_async(const SpmmParams &p, cudaStream_t st) {
     const int lanes = (p.D + 3) / 4;
     const char *cfg = getenv("TFGK_SPMM_ASYNC_CFG");      // tuning knob for NC == 1, "UxS"; default 4x3
@@ -733,6 +971,7 @@ static int spmm_impl_choice() {
     const char *e = getenv("TFGK_SPMM_IMPL");
     if (e && e[0] == 'b') return 1;
     if (e && e[0] == 's') return 2;
+    if (e && (e[0] == 'g' || e[0] == 't')) return 4;      // "gather4" / "tma": TMA tile::gather4 ring
     if (e && e[0] == 'l') return 0;
     return 3;      // cp.async ring (default); "ldg" / "stream" / "bulk" select the measured alternatives      // measured on B200 (profiles/r1_kernel_variants.json): 512 B bulk copies are TMA-issue bound
 }
@@ -829,7 +1068,7 @@ extern "C" int tfgk_spmm_f32(const int64_t *rowptr, const int32_t *col, const fl
         p.scratch = nullptr;
         // the plan applies when the whole width runs in one launch of the streaming kernel (scratch rows are D wide)
         const bool use_plan = plan != nullptr && plan->n_tasks > 0 && vec4 && D >= 32 && D <= cols_per_launch &&
-                              spmm_impl_choice() == 3;
+                              (spmm_impl_choice() == 3 || spmm_impl_choice() == 4);
         if (use_plan) {
             p.n_tasks = plan->n_tasks; p.task_row = plan->task_row; p.task_nrows = plan->task_nrows;
             p.task_e0 = plan->task_e0; p.task_e1 = plan->task_e1; p.task_slot = plan->task_slot;
@@ -837,7 +1076,19 @@ extern "C" int tfgk_spmm_f32(const int64_t *rowptr, const int32_t *col, const fl
             p.hub_nslots = plan->hub_nslots; p.scratch = plan->scratch;
         }
         const int lanes = (p.D + vec - 1) / vec;
-        if (vec4 && p.D >= 32 && spmm_impl_choice() == 3) {
+        if (vec4 && p.D >= 32 && spmm_impl_choice() == 4) {
+            // the ABI does not carry the number of source rows: the tensor map is bounded by the index type instead
+            // (column ids were validated against n_cols when the CSR was built)
+            const char *cfg = getenv("TFGK_SPMM_GATHER4_STAGES");
+            const int st = cfg ? atoi(cfg) : 4;
+            const int rcg = st == 2 ? launch_spmm_gather4<2>(p, (int64_t)1 << 31, as_stream(stream))
+                          : st == 3 ? launch_spmm_gather4<3>(p, (int64_t)1 << 31, as_stream(stream))
+                          : st == 6 ? launch_spmm_gather4<6>(p, (int64_t)1 << 31, as_stream(stream))
+                          : st == 8 ? launch_spmm_gather4<8>(p, (int64_t)1 << 31, as_stream(stream))
+                                    : launch_spmm_gather4<4>(p, (int64_t)1 << 31, as_stream(stream));
+            if (rcg != TFGK_ERR_UNSUPPORTED) { if (rcg != TFGK_OK) return rcg; continue; }
+        }
+        if (vec4 && p.D >= 32 && (spmm_impl_choice() == 3 || spmm_impl_choice() == 4)) {
             const int rca = dispatch_spmm_async(p, as_stream(stream));
             if (rca != TFGK_ERR_UNSUPPORTED) { if (rca != TFGK_OK) return rca; continue; }
         }

@@ -56,9 +56,14 @@ D = B.UNITS
 spmm_bytes = csr.nnz * (4 * D + 8) + n * (4 * D + 8)
 out = torch.empty((n, D), device=dev)
 ref_out = None
-for impl, cfg in (("ldg", ""), ("async", "4x3"), ("async", "8x2")):
+variants = [("ldg", ""), ("async", "4x3"), ("async", "4x4"), ("async", "8x3"), ("gather4", "2"), ("gather4", "3"),
+            ("gather4", "4"), ("gather4", "6"), ("gather4", "8")]
+if os.environ.get("TFGK_BENCH_QUICK"):
+    variants = [("async", "4x3"), ("async", "4x4"), ("gather4", "3"), ("gather4", "4"), ("gather4", "6"), ("gather4", "8")]
+for impl, cfg in variants:
     os.environ["TFGK_SPMM_IMPL"] = impl
     os.environ["TFGK_SPMM_ASYNC_CFG"] = cfg
+    os.environ["TFGK_SPMM_GATHER4_STAGES"] = cfg if impl == "gather4" else "4"
     tag = impl + ("_" + cfg if cfg else "")
     timed(lambda: ops.spmm(csr, w, h, out=out), "spmm_D128_" + tag, spmm_bytes)
     if ref_out is None:
@@ -69,6 +74,10 @@ for impl, cfg in (("ldg", ""), ("async", "4x3"), ("async", "8x2")):
           csr.nnz * (4 * 100 + 4) + n * (4 * 100 + 8))
 os.environ.pop("TFGK_SPMM_IMPL")
 os.environ.pop("TFGK_SPMM_ASYNC_CFG")
+os.environ.pop("TFGK_SPMM_GATHER4_STAGES")
+if os.environ.get("TFGK_BENCH_QUICK"):
+    json.dump(results, open(os.path.join(ROOT, "gpurun_out", "bench_kernels.json"), "w"), indent=1)
+    sys.exit(0)
 
 q = torch.randn((n, D), generator=gen, device=dev)
 kv = torch.randn((n, 2 * D), generator=gen, device=dev)
