@@ -186,8 +186,9 @@ int tfgk_gemm_f32(const float *A, int64_t lda, int transA, const float *B, int64
  * with a kernel on another stream).  Returns TFGK_ERR_UNSUPPORTED when the shape does not qualify (K > 512, unaligned A,
  * W too large for shared memory): the caller then uses tfgk_gemm_f32 per block. */
 typedef struct tfgk_proj_block {
-    const float *B; int64_t ldb;       /* [K, ncols] row-major weights */
+    const float *B; int64_t ldb;       /* [K, ncols] row-major weights ([ncols, K] row-major when transB != 0) */
     int32_t ncols;
+    int32_t transB;                    /* 0: C = A @ B;  1: C = A @ B^T  (the dX = dY W^T products of the backward pass) */
     const float *bias;                 /* [ncols] or NULL */
     int act;                           /* tfgk_act */
     float *C; int64_t ldc;             /* [M, ncols] output (may be a column slice of a wider buffer) */

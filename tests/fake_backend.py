@@ -126,8 +126,9 @@ def install(monkeypatch):
     def gemm_proj(a, blocks, a_parts=None, part_rows=0, first_part=0, max_ctas=0, num_rows=None):
         assert a_parts is None, "peer-mapped inputs need a GPU"
         outs = []
-        for w, bias, act, out in blocks:
-            res = gemm(a if num_rows is None else a[:num_rows], w, bias=bias, act=act)
+        for blk in blocks:
+            w, bias, act, out = blk[:4]
+            res = gemm(a if num_rows is None else a[:num_rows], w, bias=bias, act=act, trans_b=len(blk) > 4 and bool(blk[4]))
             if out is not None:
                 out.copy_(res)
                 res = out

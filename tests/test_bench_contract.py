@@ -30,7 +30,7 @@ def _check_line(stdout, n_gpus):
 
 
 def test_reference_arm_prints_one_contract_line():
-    out = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1"], cwd=ROOT,
+    out = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-sample-div", "400"], cwd=ROOT,
                          capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-2000:]
     _check_line(out.stdout, 1)
@@ -40,9 +40,21 @@ def test_reference_arm_under_torchrun_only_rank0_speaks():
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                           "--master-addr", "127.0.0.1", "--master-port", "29731", "bench.py", "--impl", "reference", "--gpus", "2",
-                          "--steps", "1", "--warmup", "1"], cwd=ROOT, capture_output=True, text=True, timeout=900, env=env)
+                          "--steps", "1", "--warmup", "1", "--cpu-sample-div", "400"], cwd=ROOT, capture_output=True, text=True, timeout=900, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     _check_line(out.stdout, 2)
+
+
+def test_reference_arm_covers_every_baseline_config():
+    """--config cfg1..cfg5 on the CPU arm: each BASELINE.json configuration has its own op sequence and declares its sample."""
+    for name in ("cfg1", "cfg2", "cfg3", "cfg4", "cfg5"):
+        out = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--config", name, "--steps", "1", "--warmup", "1",
+                              "--cpu-sample-div", "1" if name == "cfg1" else "2000"], cwd=ROOT, capture_output=True, text=True,
+                             timeout=600)
+        assert out.returncode == 0, (name, out.stderr[-2000:])
+        rec = _check_line(out.stdout, 1)
+        assert rec["config"]["name"] == name and "reference_sample" in rec["config"]
+        assert rec["metric"].startswith("edges/sec")
 
 
 def test_gpu_arm_refuses_to_run_without_a_gpu():

@@ -353,3 +353,43 @@ def test_degenerate_graphs_empty_edges_single_node():
         assert_close(host(tfg.nn.mean_graph_sage(dev(x), dev(ei), None, dev(k), dev(k), dev(np.concatenate([b, b])), tfg.nn.relu)),
                      o.mean_graph_sage(x, ei, None, k, k, np.concatenate([b, b]), o.relu), what="sage " + what)
         assert host(tfg.nn.segment_count(dev(ei[0]), n)).tolist() == np.bincount(ei[0], minlength=n).tolist()
+
+
+def test_sparse_features_and_column_splits():
+    """tf.SparseTensor features (nn/conv/gcn.py:269-272, gat.py:45-70; Cora's bag of words) as SparseMatrix / torch sparse /
+    scipy sparse inputs: same result as the dense matrix; num_or_size_splits (gcn.py:274-280) changes no bit."""
+    import scipy.sparse as sp
+    rs = np.random.RandomState(12)
+    n, f, u, heads = 700, 300, 16, 4
+    dense = ((rs.rand(n, f) < 0.05) * rs.rand(n, f)).astype(np.float32)
+    dense[3] = 0.0                                                  # a node without features
+    ei = random_graph(n, 6000, seed=13, symmetric=True, isolated=2)
+    k, b = glorot(rs, f, u), rs.randn(u).astype(np.float32)
+    wq, wk, wv = glorot(rs, f, u), glorot(rs, f, u), glorot(rs, f, u)
+    bq, bk = rs.randn(u).astype(np.float32) * .1, rs.randn(u).astype(np.float32) * .1
+    adj = o.SparseMatrix(ei, None, [n, n])
+    want_gcn = o.gcn(dense, adj, k, b, o.relu)
+    want_gat = o.gat(dense, ei, wq, bq, o.relu, wk, bk, o.relu, wv, b, o.relu, num_heads=heads)
+    eid = dev(ei, torch.int32)
+    nz = np.nonzero(dense)
+    forms = {
+        "SparseMatrix": tfg.SparseMatrix(np.stack(nz).astype(np.int32), dense[nz], [n, f]),
+        "scipy": sp.csr_matrix(dense),
+    }
+    if torch.cuda.is_available():
+        forms["torch_coo"] = torch.from_numpy(dense).to_sparse().cuda()
+    for name, xs in forms.items():
+        got = tfg.nn.gcn(xs, tfg.SparseMatrix(eid, None, [n, n]), dev(k), dev(b), tfg.nn.relu)
+        assert_close(host(got), want_gcn, rtol=1e-4, atol_scale=1e-4, what="gcn with {} features".format(name))
+        got = tfg.nn.gat(xs, eid, dev(wq), dev(bq), tfg.nn.relu, dev(wk), dev(bk), tfg.nn.relu, dev(wv), dev(b), tfg.nn.relu,
+                         num_heads=heads)
+        assert_close(host(got), want_gat, rtol=1e-4, atol_scale=1e-4, what="gat with {} features".format(name))
+    layer = tfg.layers.GCN(u, activation=tfg.nn.relu, seed=4)
+    a = layer([forms["SparseMatrix"], eid])
+    assert tuple(a.shape) == (n, u)
+    full = tfg.nn.gcn(dev(dense), tfg.SparseMatrix(eid, None, [n, n]), dev(k), dev(b), tfg.nn.relu)
+    for splits in (2, 4, [5, 11], [16]):
+        part = tfg.nn.gcn(dev(dense), tfg.SparseMatrix(eid, None, [n, n]), dev(k), dev(b), tfg.nn.relu, num_or_size_splits=splits)
+        assert torch.equal(part, full), splits
+    with pytest.raises(ValueError):
+        tfg.nn.gcn(dev(dense), tfg.SparseMatrix(eid, None, [n, n]), dev(k), dev(b), num_or_size_splits=3)

@@ -87,6 +87,7 @@ def test_model_paths(fake):
     test_gpu_models.test_pool_and_gcn_graph_sage_and_layers()
     test_gpu_models.test_appnp(10, 0.1)
     test_gpu_models.test_appnp(0, 0.1)
+    test_gpu_models.test_sparse_features_and_column_splits()
     test_gpu_models.test_graph_sage_forward_backward("mean", False, True)
     test_gpu_models.test_graph_sage_forward_backward("mean", True, False)
     test_gpu_models.test_graph_sage_forward_backward("sum", True, True)

@@ -92,7 +92,8 @@ class PlanStruct(ctypes.Structure):
 
 class ProjBlock(ctypes.Structure):
     """struct tfgk_proj_block of include/tfgk.h."""
-    _fields_ = [("B", _ptr), ("ldb", _i64), ("ncols", _i32), ("bias", _ptr), ("act", _int), ("C", _ptr), ("ldc", _i64)]
+    _fields_ = [("B", _ptr), ("ldb", _i64), ("ncols", _i32), ("transB", _i32), ("bias", _ptr), ("act", _int), ("C", _ptr),
+                ("ldc", _i64)]
 
 
 PEER_HANDLE_BYTES = 64

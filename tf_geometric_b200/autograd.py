@@ -272,5 +272,59 @@ class TakeRows(torch.autograd.Function):
         return (res if g.dim() == 2 else res.squeeze(1)), None
 
 
+class SagePair(torch.autograd.Function):
+    """mean / sum GraphSAGE (nn/conv/graph_sage.py:9-115) as ONE differentiable op:
+        out = act([x Ws || agg Wn] + b)   (or x Ws + agg Wn + b),   agg = REDUCE_{e: row_e = r} w_e x[col_e].
+    Compared with composing NeighborAggregate and two Dense Functions this writes both projections straight into the
+    output (no concat copy), masks the upstream gradient once, and folds dX_self into the epilogue of the transposed
+    aggregation (grad_x = A^T d_agg + dX_self in one pass, tfgk_spmm_f32's addend).  dX products run on the tensor-core
+    projection kernel (transB), dW products are split-K over the node dimension."""
+
+    @staticmethod
+    def forward(ctx, x, ws, wn, bias, edge_index, edge_weight, reduce, act_code, concat):
+        n = x.shape[0]
+        csr, _ = _structure.csr_for_edge_index(edge_index, n)
+        w_csr = None if edge_weight is None else _structure.weights_in_csr_order(edge_weight, csr)
+        xd, wsd, wnd = x.detach(), ws.detach(), wn.detach()
+        b = None if bias is None else bias.detach()
+        agg = ops.spmm(csr, w_csr, xd, reduce=reduce)
+        u = wsd.shape[1]
+        if concat:
+            out = torch.empty((n, u + wnd.shape[1]), dtype=torch.float32, device=xd.device)
+            ops.gemm(xd, wsd, bias=None if b is None else b[:u].contiguous(), act=act_code, out=out[:, :u])
+            ops.gemm(agg, wnd, bias=None if b is None else b[u:].contiguous(), act=act_code, out=out[:, u:])
+        else:
+            out = ops.gemm(xd, wsd)
+            ops.gemm(agg, wnd, bias=b, act=act_code, beta=1.0, out=out)
+        ctx.save_for_backward(x, ws, wn, agg, out if act_code == ops.ACT_RELU else None)
+        ctx.meta = (edge_index, edge_weight, reduce, act_code, concat, csr, bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, ws, wn, agg, out = ctx.saved_tensors
+        edge_index, edge_weight, reduce, act_code, concat, csr, has_bias = ctx.meta
+        gm = grad_out.contiguous()
+        if act_code == ops.ACT_RELU:
+            gm = gm * (out > 0).to(gm.dtype)
+        u = ws.shape[1]
+        gs, gn = (gm[:, :u], gm[:, u:]) if concat else (gm, gm)
+        xd, wsd, wnd = x.detach(), ws.detach(), wn.detach()
+        grad_x = grad_ws = grad_wn = grad_b = None
+        if ctx.needs_input_grad[0]:
+            d_agg = ops.gemm(gn, wnd, trans_b=True)
+            dx_self = ops.gemm(gs, wsd, trans_b=True)
+            csr_t, w_t = _transposed_structure(edge_index, x.shape[0], edge_weight, reduce == "mean", csr)
+            grad_x = ops.spmm(csr_t, w_t, d_agg, reduce="sum", alpha=1.0, addend=dx_self, beta=1.0)
+        if ctx.needs_input_grad[1]:
+            grad_ws = ops.gemm(xd, gs, trans_a=True)
+        if ctx.needs_input_grad[2]:
+            grad_wn = ops.gemm(agg, gn, trans_a=True)
+        if has_bias and ctx.needs_input_grad[3]:
+            ones = torch.ones((gm.shape[0], 1), dtype=torch.float32, device=gm.device)
+            grad_b = ops.gemm(ones, gm, trans_a=True).reshape(-1)
+        return grad_x, grad_ws, grad_wn, grad_b, None, None, None, None, None
+
+
 def needs_grad(*tensors):
     return torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in tensors)

@@ -166,9 +166,29 @@ extern "C" int tfgk_gemm_f32(const float *A, int64_t lda, int transA, const floa
     TFGK_CHECK_ARG(K == 0 || (lda >= (transA ? M : K) && ldb >= (transB ? K : N)), "gemm: leading dimension too small");
     cudaStream_t st = as_stream(stream);
 
-    if (!transA && !transB && beta == 0.0f && K > 0) {
-        const int rc = tfgk_gemm_tc_f32(A, lda, B, ldb, bias, act, M, N, K, C, ldc, stream);
-        if (rc != TFGK_ERR_UNSUPPORTED) return rc;
+    if (!transA && beta == 0.0f && K > 0) {
+        // tall projections (and dX = dY W^T with transB): the multi-block tcgen05 kernel (gemm_proj.cu), N cut into blocks
+        // of <= 128 columns
+        const char *env = getenv("TFGK_GEMM_TC");
+        const bool tc_on = !(env != nullptr && env[0] == '0');
+        if (tc_on && N <= 512 && (int64_t)M * K >= (1 << 14)) {
+            tfgk_proj_block blocks[4];
+            int nb = 0;
+            for (int c0 = 0; c0 < N; c0 += 128, ++nb) {
+                const int w = N - c0 < 128 ? N - c0 : 128;
+                blocks[nb].B = transB ? B + (int64_t)c0 * ldb : B + c0; blocks[nb].ldb = ldb; blocks[nb].ncols = w;
+                blocks[nb].transB = transB ? 1 : 0;
+                blocks[nb].bias = bias ? bias + c0 : nullptr; blocks[nb].act = act;
+                blocks[nb].C = C + c0; blocks[nb].ldc = ldc;
+            }
+            const float *parts[1] = {A};
+            const int rcp = tfgk_gemm_proj_f32(parts, 1, 0, lda, M, K, blocks, nb, 0, 0, stream);
+            if (rcp != TFGK_ERR_UNSUPPORTED) return rcp;
+        }
+        if (!transB) {
+            const int rc = tfgk_gemm_tc_f32(A, lda, B, ldb, bias, act, M, N, K, C, ldc, stream);
+            if (rc != TFGK_ERR_UNSUPPORTED) return rc;
+        }
     }
 
     GemmParams p;

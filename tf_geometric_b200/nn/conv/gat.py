@@ -8,6 +8,7 @@ segment_softmax over H*E' scores and finally a SpMM.  Here: three dense projecti
 import torch
 
 from ... import ops, _structure, _rng, autograd
+from ...sparse import as_sparse_features, project_features
 
 
 def project(x, blocks):
@@ -41,10 +42,29 @@ def gat(x, edge_index,
     """
     edge_index = ops.as_device(edge_index, torch.int32)
     dev = edge_index.device
-    x = ops.as_device(x, torch.float32, device=dev)
-    num_nodes = x.shape[0]
+    x_sparse = as_sparse_features(x)             # tf.SparseTensor features (reference gat.py:45-70)
+    if x_sparse is None:
+        x = ops.as_device(x, torch.float32, device=dev)
+    num_nodes = len(x_sparse) if x_sparse is not None else x.shape[0]
     csr, edge_index_used = _structure.csr_for_edge_index(edge_index, num_nodes, add_self_loop=True, cache=cache)
     drop_rate = float(edge_drop_rate) if training else 0.0
+    if x_sparse is not None:
+        if drop_rate > 0.0 or autograd.needs_grad(query_kernel, query_bias, key_kernel, key_bias, kernel, bias):
+            raise NotImplementedError("training with sparse features: pass x.to_dense()")
+        q_act, q_left = ops.activation_code(query_activation)
+        k_act, k_left = ops.activation_code(key_activation)
+        f32 = lambda t: None if t is None else ops.as_device(t, torch.float32, device=dev)     # noqa: E731
+        Q = project_features(x_sparse, query_kernel, bias=f32(query_bias), act=q_act)
+        K = project_features(x_sparse, key_kernel, bias=f32(key_bias), act=k_act)
+        V = project_features(x_sparse, kernel)
+        Q = q_left(Q) if q_left is not None else Q
+        K = k_left(K) if k_left is not None else K
+        act_code, leftover = ops.activation_code(activation)
+        res = ops.gat_fused(csr, Q, K, V, num_heads, split_value_heads=split_value_heads, bias=f32(bias), act=act_code,
+                            return_attention=return_attention)
+        h, att = res if return_attention else (res, None)
+        h = leftover(h) if leftover is not None else h
+        return (h, ops.permute(att, csr.perm, inverse=True)) if return_attention else h
     if drop_rate > 0.0 or autograd.needs_grad(x, query_kernel, query_bias, key_kernel, key_bias, kernel, bias):
         if return_attention:
             raise NotImplementedError("return_attention is an inference-path extension")

@@ -11,7 +11,7 @@ with bias + activation fused into its epilogue).
 import torch
 
 from ... import ops, autograd
-from ...sparse import SparseMatrix
+from ...sparse import SparseMatrix, as_sparse_features, project_features
 from ..kernel.map_reduce import gcn_mapper  # noqa: F401  (re-exported like the reference)
 
 CACHE_KEY_GCN_NORMED_ADJ_TEMPLATE = "gcn_normed_adj_{}_{}_{}_{}_{}"
@@ -121,9 +121,19 @@ def gcn(x, sparse_adj, kernel, bias=None, activation=None,
                           improved=improved, cache=cache)
     normed = normed.dropout(edge_drop_rate, training=training)
     dev = normed.index.device
-    x = ops.as_device(x, torch.float32, device=dev)
     act_code, leftover = ops.activation_code(activation)
     bias = None if bias is None else ops.as_device(bias, torch.float32, device=dev)
+    x_sparse = as_sparse_features(x)
+    if x_sparse is not None:                   # tf.SparseTensor features (gcn.py:269-272): sparse x dense projection
+        if kernel is None:
+            raise ValueError("a sparse feature matrix needs a kernel (reference gcn.py:266-272)")
+        if autograd.needs_grad(kernel, bias):
+            raise NotImplementedError("training with sparse features: pass x.to_dense() (the backward of the sparse "
+                                      "projection is not built)")
+        h = project_features(x_sparse, kernel)
+        h = normed.matmul(h, num_or_size_splits=num_or_size_splits, bias=bias, act=act_code)
+        return leftover(h) if leftover is not None else h
+    x = ops.as_device(x, torch.float32, device=dev)
     if autograd.needs_grad(x, kernel, bias):
         # training path (demo/demo_gcn.py:60-75 uses tf.GradientTape): same kernels behind autograd Functions
         h = x if kernel is None else autograd.Dense.apply(x, ops.as_device(kernel, torch.float32, device=dev), None,

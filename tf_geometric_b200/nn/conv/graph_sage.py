@@ -38,6 +38,9 @@ def _project_pair(x, agg, self_kernel, neighbor_kernel, bias, activation, concat
 
 def _plain_sage_autograd(reduce, x, edge_index, edge_weight, ws, wn, bias, activation, concat, normalize):
     """Training path (any input requires grad): the same kernels wrapped in autograd Functions (autograd.py)."""
+    act_code, leftover = ops.activation_code(activation)
+    if leftover is None and not normalize and not autograd.needs_grad(edge_weight):
+        return autograd.SagePair.apply(x, ws, wn, bias, edge_index, edge_weight, reduce, act_code, bool(concat))
     agg = autograd.NeighborAggregate.apply(x, edge_index, edge_weight, reduce, x.shape[0])
     return _project_pair_autograd(x, agg, ws, wn, bias, activation, concat, normalize)
 

@@ -524,14 +524,18 @@ def gemm_proj(a, blocks, a_parts=None, part_rows=0, first_part=0, max_ctas=0, nu
     K = a.shape[1]
     structs = (_ffi.ProjBlock * len(blocks))()
     outs = []
-    for i, (w, bias, act, out) in enumerate(blocks):
-        if not (w.is_cuda and w.dtype == torch.float32 and w.dim() == 2 and w.shape[0] == K):
-            raise TypeError("gemm_proj: weight {} must be a float32 CUDA tensor [{}, n]".format(i, K))
+    for i, blk in enumerate(blocks):
+        w, bias, act, out = blk[:4]
+        trans_b = bool(blk[4]) if len(blk) > 4 else False          # weight given as [n, K]: C = A @ w^T
+        k_dim, n_dim = (1, 0) if trans_b else (0, 1)
+        if not (w.is_cuda and w.dtype == torch.float32 and w.dim() == 2 and w.shape[k_dim] == K):
+            raise TypeError("gemm_proj: weight {} must be a float32 CUDA tensor with inner dimension {}".format(i, K))
+        n_cols = w.shape[n_dim]
         if out is None:
-            out = torch.empty((M, w.shape[1]), dtype=torch.float32, device=a.device)
+            out = torch.empty((M, n_cols), dtype=torch.float32, device=a.device)
         if bias is not None:
             _check(bias, torch.float32, "bias")
-        structs[i] = _ffi.ProjBlock(w.data_ptr(), _row_major_2d(w, "weight"), w.shape[1],
+        structs[i] = _ffi.ProjBlock(w.data_ptr(), _row_major_2d(w, "weight"), n_cols, 1 if trans_b else 0,
                                     None if bias is None else bias.data_ptr(), int(act), out.data_ptr(),
                                     _row_major_2d(out, "out"))
         outs.append(out)
@@ -547,8 +551,8 @@ def gemm_proj(a, blocks, a_parts=None, part_rows=0, first_part=0, max_ctas=0, nu
     except _ffi.TfgkError as err:
         if err.code != _ffi.ERR_UNSUPPORTED or n_parts != 1:
             raise
-        for (w, bias, act, _), out in zip(blocks, outs):
-            gemm(a[:M], w, bias=bias, act=act, out=out)
+        for blk, out in zip(blocks, outs):
+            gemm(a[:M], blk[0], bias=blk[1], act=blk[2], trans_b=bool(blk[4]) if len(blk) > 4 else False, out=out)
     return outs
 
 

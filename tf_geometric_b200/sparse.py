@@ -110,10 +110,35 @@ class SparseMatrix(object):
         return out
 
     def matmul(self, h, num_or_size_splits=None, **epilogue):
-        """A @ h (gcn.py:280).  `num_or_size_splits` is accepted for signature parity; the fused kernel never
-        materialises the [E, D] temporary that the split bounds in the reference, so it is a no-op here."""
+        """A @ h (gcn.py:280).  `num_or_size_splits` (tf.split semantics: a count of equal column chunks or a list of
+        chunk widths, utils/tf_sparse_utils.py:71-90) runs one launch per column chunk into slices of one output, like the
+        reference's split -> matmul -> concat; the fused kernel has no [E, D] temporary to bound, so the results are the
+        same bits with or without it."""
         h = ops.as_device(h, torch.float32, device=self.index.device)
-        return ops.spmm(self.csr, self.value_csr, h, reduce="sum", **epilogue)
+        if num_or_size_splits is None or h.dim() != 2:
+            return ops.spmm(self.csr, self.value_csr, h, reduce="sum", **epilogue)
+        d = h.shape[1]
+        if isinstance(num_or_size_splits, int):
+            if num_or_size_splits <= 0 or d % num_or_size_splits:
+                raise ValueError("num_or_size_splits={} does not evenly divide {} columns".format(num_or_size_splits, d))
+            sizes = [d // num_or_size_splits] * num_or_size_splits
+        else:
+            sizes = [int(v) for v in num_or_size_splits]
+            if sum(sizes) != d:
+                raise ValueError("split sizes {} do not add up to {} columns".format(sizes, d))
+        out = epilogue.pop("out", None)
+        if out is None:
+            out = torch.empty((self._shape[0], d), dtype=torch.float32, device=h.device)
+        bias, addend = epilogue.pop("bias", None), epilogue.pop("addend", None)
+        c0 = 0
+        for width in sizes:
+            c1 = c0 + width
+            if width:
+                ops.spmm(self.csr, self.value_csr, h[:, c0:c1], reduce="sum", out=out[:, c0:c1],
+                         bias=None if bias is None else bias[c0:c1].contiguous(),
+                         addend=None if addend is None else addend[:, c0:c1], **epilogue)
+            c0 = c1
+        return out
 
     def __matmul__(self, h):
         return self.matmul(h)
@@ -126,5 +151,39 @@ class SparseMatrix(object):
         out.index_put_((self.index[0].long(), self.index[1].long()), self.value, accumulate=True)
         return out
 
+    def __len__(self):
+        return self._shape[0]
+
     def __repr__(self):
         return "SparseMatrix(shape={}, nnz={})".format(self._shape, self.nnz)
+
+
+def as_sparse_features(x):
+    """A sparse FEATURE matrix (the tf.SparseTensor `x` of nn/conv/gcn.py:269-272, gat.py:45-70; Cora's bag of words) as
+    a SparseMatrix, or None when x is dense.  Accepts SparseMatrix, torch sparse COO / CSR tensors and scipy sparse
+    matrices; entries keep their order (canonical row-major for TF's SparseTensor), which is the summation order."""
+    if isinstance(x, SparseMatrix):
+        return x
+    if torch.is_tensor(x):
+        if x.layout == torch.sparse_coo:
+            x = x.coalesce()
+            return SparseMatrix(x.indices().to(torch.int32), x.values().to(torch.float32), list(x.shape))
+        if x.layout == torch.sparse_csr:
+            return as_sparse_features(x.to_sparse_coo())
+        return None
+    if hasattr(x, "tocoo") and hasattr(x, "nnz"):          # scipy.sparse
+        import numpy as np
+        coo = x.tocsr().tocoo()                            # row-major order
+        return SparseMatrix(np.stack([coo.row, coo.col]).astype(np.int32), coo.data.astype(np.float32), list(coo.shape))
+    return None
+
+
+def project_features(x, kernel, bias=None, act=0):
+    """act(x @ kernel + bias) for a dense or sparse x: the sparse product gathers rows of the kernel by the column ids of
+    x's non-zeros - the same gather / edge-apply / segment-reduce kernel as the aggregation (tf.sparse.sparse_dense_matmul
+    at gcn.py:272)."""
+    sp = as_sparse_features(x)
+    if sp is None:
+        return None
+    kernel = ops.as_device(kernel, torch.float32, device=sp.index.device)
+    return sp.matmul(kernel, bias=bias, act=act)
