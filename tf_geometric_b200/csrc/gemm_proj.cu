@@ -17,6 +17,7 @@
 //     `first_part` so that every rank pulls from a different peer at any moment.
 #include "common.cuh"
 #include "tfgk_tc.cuh"
+#include <stdlib.h>
 
 namespace tfgk {
 namespace proj {
@@ -37,6 +38,7 @@ struct Params {
     int64_t lda, part_rows;
     int n_parts, first_tile, local_part;
     int M, K, nb, tiles_m, n_groups;
+    int dbg;           // measurement switches (TFGK_PROJ_DEBUG): 1 no lo conversion, 2 hi*hi MMA only, 4 no stores, 8 no loads
     const float *B[kMaxBlocks]; int64_t ldb[kMaxBlocks];
     const float *bias[kMaxBlocks]; int act[kMaxBlocks]; int ncols[kMaxBlocks]; int transb[kMaxBlocks];
     float *C[kMaxBlocks]; int64_t ldc[kMaxBlocks];
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(kThreadsProj, 1) gemm_proj_kernel(const Params
                 const int tile = tile_of(G / nkb), kb = G % nkb;
                 if (kb == 0) prefetch_tile(G / nkb + kPrefetchTiles);
                 const int k = kb * BK + kc * 4;
-                if (k < (int)L.kpad8) {
+                if (k < (int)L.kpad8 && !(p.dbg & 8)) {
                     const int64_t m0 = (int64_t)tile * BM;
                     const int part = p.n_parts > 1 ? (int)(m0 / p.part_rows) : 0;
                     const float *base = p.A[part] + (m0 - (int64_t)part * p.part_rows) * p.lda + k;
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(kThreadsProj, 1) gemm_proj_kernel(const Params
             // finished, so tensor core and producers alternated instead of overlapping (tensor pipe 25% busy).
             asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
             const int stage = G % STAGES, kb = G % nkb;
-            if (kb * BK + kc * 4 < (int)L.kpad8) {
+            if (kb * BK + kc * 4 < (int)L.kpad8 && !(p.dbg & 1)) {
                 uint8_t *sraw = a_ring + stage * L.a_stage_bytes + t * 16;
 #pragma unroll
                 for (int i = 0; i < kChunks; ++i) {
@@ -210,6 +212,7 @@ __global__ void __launch_bounds__(kThreadsProj, 1) gemm_proj_kernel(const Params
                     const uint32_t off = (uint32_t)j * 2u * 128u;
                     const uint64_t dah = make_desc_sbo(a_raw + off, 1024u), dal = make_desc_sbo(a_lo + off, 1024u);
                     const uint64_t dbh = make_desc_sbo(b_hi + off, sbo_b), dbl = make_desc_sbo(b_lo + off, sbo_b);
+                    if (p.dbg & 2) { umma_tf32(d_tmem, dah, dbh, idesc, (kb | j) != 0); continue; }
                     umma_tf32(d_tmem, dal, dbh, idesc, (kb | j) != 0);
                     umma_tf32(d_tmem, dah, dbl, idesc, 1u);
                     umma_tf32(d_tmem, dah, dbh, idesc, 1u);
@@ -267,7 +270,7 @@ __global__ void __launch_bounds__(kThreadsProj, 1) gemm_proj_kernel(const Params
                     const int rl = j * 4 + seg_row;
                     const int64_t row = row0 + rl;
                     const float4 v = *reinterpret_cast<const float4 *>(stg + rl * kStageRowBytes + seg_chunk * 16);
-                    if (row < p.M) {
+                    if (row < p.M && !(p.dbg & 4)) {
                         float *dst = Cb + row * ldc + col;
                         if (vec_ok && col + 4 <= ncols) {
                             *reinterpret_cast<float4 *>(dst) = v;
@@ -329,6 +332,7 @@ extern "C" int tfgk_gemm_proj_f32(const float *const *A_parts, int32_t n_parts, 
     }
     p.lda = lda; p.part_rows = n_parts > 1 ? part_rows : (int64_t)1 << 40; p.n_parts = n_parts;
     p.M = M; p.K = K; p.nb = n_blocks;
+    { const char *d = getenv("TFGK_PROJ_DEBUG"); p.dbg = d ? atoi(d) : 0; }
     p.tiles_m = (int)ceil_div64(M, tc::BM);
     p.first_tile = n_parts > 1 ? (int)((int64_t)first_part * part_rows / tc::BM) : 0;
     p.local_part = n_parts > 1 ? (first_part + n_parts - 1) % n_parts : 0;      // the walk starts one past the caller's own part
