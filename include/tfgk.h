@@ -216,6 +216,12 @@ int tfgk_peer_open(const void *handle, void **ptr);
 int tfgk_peer_close(void *ptr);
 int tfgk_peer_barrier(uint32_t *const *flags, int32_t rank, int32_t world, uint32_t value, int32_t timeout_ms, void *stream);
 
+/* out[c] = sum_r x[r, c]: the bias gradients db = 1^T dY of the backward passes (TensorFlow autodiff's BiasAddGrad under
+ * gcn.py:283-284, gat.py:116-117, graph_sage.py:51-52).  Deterministic: per-block partial sums added in block order. */
+int tfgk_colsum_workspace_bytes(int64_t n_rows, int32_t D, size_t *out_bytes);
+int tfgk_colsum_f32(const float *x, int64_t ldx, int64_t n_rows, int32_t D, float *out, void *workspace,
+                    size_t workspace_bytes, void *stream);
+
 /* tf.nn.l2_normalize(x, axis=-1) (graph_sage.py:57-58): out = x * rsqrt(max(sum(x^2), 1e-12)). */
 int tfgk_l2_normalize_f32(const float *x, int64_t ldx, int32_t N, int32_t D, float *out, int64_t ldo, void *stream);
 

@@ -101,3 +101,20 @@ def test_gat_layer_uses_one_projection_launch():
     finally:
         _ffi.set_trace(None)
     assert trace.counts.get("tfgk_gemm_proj_f32") == 1 and trace.counts.get("tfgk_gemm_f32", 0) == 0
+
+
+def test_gemm_proj_transposed_weights_and_colsum():
+    """dX = dY W^T on the tensor-core kernel (weights given as [n, K]) and the deterministic column sum used for db."""
+    rs = np.random.RandomState(8)
+    m, k = 7001, 128
+    g = rs.randn(m, 2 * k).astype(np.float32)
+    w1, w2 = (rs.randn(100, k) / 10).astype(np.float32), (rs.randn(60, k) / 10).astype(np.float32)
+    gd = dev(g)
+    d1, d2 = ops.gemm_proj(gd[:, :k], [(dev(w1), None, ops.ACT_NONE, None, True)])[0], \
+        ops.gemm(gd[:, k:], dev(w2), trans_b=True)
+    assert_close(d1.cpu().numpy(), g[:, :k].astype(np.float64) @ w1.T, rtol=1e-5, atol_scale=5e-6, what="dY W^T (gemm_proj)")
+    assert_close(d2.cpu().numpy(), g[:, k:].astype(np.float64) @ w2.T, rtol=1e-5, atol_scale=5e-6, what="dY W^T (gemm)")
+    for view in (gd, gd[:, :k], gd[:, 3:40]):
+        got = ops.colsum(view)
+        assert_close(got.cpu().numpy(), view.cpu().numpy().astype(np.float64).sum(0), rtol=1e-5, atol_scale=2e-6, what="colsum")
+        assert torch.equal(got, ops.colsum(view))

@@ -82,8 +82,7 @@ class Dense(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             grad_w = ops.gemm(x.detach(), g, trans_a=True)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            ones = torch.ones((g.shape[0], 1), dtype=torch.float32, device=g.device)
-            grad_b = ops.gemm(ones, g, trans_a=True).reshape(-1)
+            grad_b = ops.colsum(g)
         return grad_x, grad_w, grad_b, None
 
 
@@ -115,8 +114,7 @@ class SparseMatmul(torch.autograd.Function):
         grad_h = ops.spmm(csr_t, adj._value_csc, g, reduce="sum") if ctx.needs_input_grad[0] else None
         grad_b = None
         if ctx.has_bias and ctx.needs_input_grad[1]:
-            ones = torch.ones((g.shape[0], 1), dtype=torch.float32, device=g.device)
-            grad_b = ops.gemm(ones, g, trans_a=True).reshape(-1)
+            grad_b = ops.colsum(g)
         return grad_h, grad_b, None, None
 
 
@@ -181,8 +179,7 @@ class GatAttention(torch.autograd.Function):
                 grad_v = ops.spmm_heads(csr_t, att, g, H, mode=ops.HEADS_SPLIT if split else ops.HEADS_BROADCAST,
                                         emap=emap, drop_rate=drop_rate, seed=seed, alpha=1.0 if split else 1.0 / H)
         if has_bias and ctx.needs_input_grad[3]:
-            ones = torch.ones((g.shape[0], 1), dtype=torch.float32, device=g.device)
-            grad_b = ops.gemm(ones, g, trans_a=True).reshape(-1)
+            grad_b = ops.colsum(g)
         return grad_q, grad_k, grad_v, grad_b, None, None, None, None, None, None, None, None
 
 
@@ -321,8 +318,7 @@ class SagePair(torch.autograd.Function):
         if ctx.needs_input_grad[2]:
             grad_wn = ops.gemm(agg, gn, trans_a=True)
         if has_bias and ctx.needs_input_grad[3]:
-            ones = torch.ones((gm.shape[0], 1), dtype=torch.float32, device=gm.device)
-            grad_b = ops.gemm(ones, gm, trans_a=True).reshape(-1)
+            grad_b = ops.colsum(gm)
         return grad_x, grad_ws, grad_wn, grad_b, None, None, None, None, None
 
 

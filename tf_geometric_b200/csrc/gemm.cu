@@ -139,6 +139,72 @@ __global__ void __launch_bounds__(256) l2_normalize_kernel(const float *__restri
     for (int c = lane; c < D; c += 32) out[r * ldo + c] = x[r * ldx + c] * inv;
 }
 
+// Column sums of a tall matrix: out[c] = sum_r x[r, c] (the bias gradients db = 1^T dY of every layer's backward pass).
+// Two deterministic stages: each block sums a contiguous slab of rows per column (threads own columns, so a warp reads a
+// contiguous row segment), partials are then added in block order.
+constexpr int kColsumThreads = 256;
+
+__global__ void __launch_bounds__(kColsumThreads) colsum_partial_kernel(const float *__restrict__ x, int64_t ldx, int64_t n_rows,
+                                                                       int32_t D, int64_t rows_per_block, float *__restrict__ partial) {
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = r0 + rows_per_block < n_rows ? r0 + rows_per_block : n_rows;
+    // a block covers the columns in passes of blockDim.x; inside a pass thread t owns column c0 + t
+    for (int c = threadIdx.x; c < D; c += kColsumThreads) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int64_t r = r0;
+        for (; r + 4 <= r1; r += 4) {
+            a0 += x[r * ldx + c];
+            a1 += x[(r + 1) * ldx + c];
+            a2 += x[(r + 2) * ldx + c];
+            a3 += x[(r + 3) * ldx + c];
+        }
+        for (; r < r1; ++r) a0 += x[r * ldx + c];
+        partial[(int64_t)blockIdx.x * D + c] = (a0 + a1) + (a2 + a3);
+    }
+}
+
+__global__ void __launch_bounds__(kColsumThreads) colsum_final_kernel(const float *__restrict__ partial, int32_t n_blocks, int32_t D,
+                                                                     float *__restrict__ out) {
+    const int c = blockIdx.x * kColsumThreads + threadIdx.x;
+    if (c >= D) return;
+    float acc = 0.f;
+    for (int b = 0; b < n_blocks; ++b) acc += partial[(int64_t)b * D + c];
+    out[c] = acc;
+}
+
+}  // namespace tfgk
+
+using namespace tfgk;
+
+static int colsum_blocks(int64_t n_rows) {
+    int64_t b = ceil_div64(n_rows, 512);
+    if (b > 148 * 8) b = 148 * 8;
+    return (int)(b < 1 ? 1 : b);
+}
+
+extern "C" int tfgk_colsum_workspace_bytes(int64_t n_rows, int32_t D, size_t *out_bytes) {
+    TFGK_CHECK_ARG(out_bytes != nullptr && n_rows >= 0 && D >= 0, "colsum_workspace_bytes: bad argument");
+    *out_bytes = (size_t)colsum_blocks(n_rows) * (size_t)(D > 0 ? D : 1) * sizeof(float);
+    return TFGK_OK;
+}
+
+extern "C" int tfgk_colsum_f32(const float *x, int64_t ldx, int64_t n_rows, int32_t D, float *out, void *workspace,
+                               size_t workspace_bytes, void *stream) {
+    TFGK_CHECK_ARG(n_rows >= 0 && D >= 0, "colsum: negative size");
+    if (D == 0) return TFGK_OK;
+    TFGK_CHECK_ARG(out != nullptr && (n_rows == 0 || (x != nullptr && ldx >= D)), "colsum: bad argument");
+    const int nb = colsum_blocks(n_rows);
+    TFGK_CHECK_ARG(workspace != nullptr && workspace_bytes >= (size_t)nb * D * sizeof(float), "colsum: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    const int64_t rows_per_block = ceil_div64(n_rows > 0 ? n_rows : 1, nb);
+    colsum_partial_kernel<<<nb, kColsumThreads, 0, st>>>(x, ldx, n_rows, D, rows_per_block, static_cast<float *>(workspace));
+    TFGK_LAUNCH_CHECK();
+    colsum_final_kernel<<<(unsigned)ceil_div64(D, kColsumThreads), kColsumThreads, 0, st>>>(static_cast<float *>(workspace), nb, D, out);
+    TFGK_LAUNCH_CHECK();
+    return TFGK_OK;
+}
+
+namespace tfgk {
 }  // namespace tfgk
 
 using namespace tfgk;

@@ -556,6 +556,20 @@ def gemm_proj(a, blocks, a_parts=None, part_rows=0, first_part=0, max_ctas=0, nu
     return outs
 
 
+def colsum(x):
+    """Column sums of a [N, D] float32 matrix (bias gradients), deterministic."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2):
+        raise TypeError("colsum: x must be a 2-D float32 CUDA tensor")
+    ldx = _row_major_2d(x, "x")
+    n, d = x.shape
+    need = ctypes.c_size_t()
+    _ffi.call("tfgk_colsum_workspace_bytes", n, d, ctypes.byref(need))
+    ws = torch.empty((max(need.value, 4),), dtype=torch.uint8, device=x.device)
+    out = torch.empty((d,), dtype=torch.float32, device=x.device)
+    _ffi.call("tfgk_colsum_f32", _p(x), ldx, n, d, _p(out), _p(ws), need.value, _stream(x))
+    return out
+
+
 def l2_normalize(x, out=None):
     if out is None:
         out = torch.empty_like(x)
