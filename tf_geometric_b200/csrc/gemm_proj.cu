@@ -26,8 +26,12 @@ using namespace tc;
 
 constexpr int kMaxBlocks = 4;
 constexpr int kMaxParts = 8;
-constexpr int kProducerWarps = 4, kEpilogueWarps = 4;
-constexpr int kThreadsProj = (kProducerWarps + kEpilogueWarps + 1) * 32;      // 288
+// warp roles: 0-3 converters (lo = a - trunc(a) on landed k-blocks), 4-7 epilogue (TMEM lane quarter = warp % 4),
+// 8 MMA issuer, 9-10 loaders (cp.async into the ring as soon as a stage is free)
+constexpr int kProducerWarps = 4, kEpilogueWarps = 4, kLoaderWarps = 2;
+constexpr int kLoaderWarp0 = kProducerWarps + kEpilogueWarps + 1;
+constexpr int kThreadsProj = (kProducerWarps + kEpilogueWarps + 1 + kLoaderWarps) * 32;      // 352
+constexpr int kBarrierBytes = 192;
 constexpr int kUN = 128;                 // accumulator columns per buffer
 constexpr int kTmemColsProj = 256;       // 2 accumulator buffers
 constexpr int kStageRowBytes = 144;      // 32 floats + 16 B pad: conflict-free for row-wise STS.128 and segment-wise LDS.128
@@ -38,7 +42,8 @@ struct Params {
     int64_t lda, part_rows;
     int n_parts, first_tile, local_part;
     int M, K, nb, tiles_m, n_groups;
-    int dbg;           // measurement switches (TFGK_PROJ_DEBUG): 1 no lo conversion, 2 hi*hi MMA only, 4 no stores, 8 no loads
+    int dbg;           // measurement switches (TFGK_PROJ_DEBUG): 1 no lo conversion, 2 hi*hi MMA only, 4 no stores, 8 no loads,
+                       // 16 no TMEM reads, 32 no staging / stores after the TMEM read
     const float *B[kMaxBlocks]; int64_t ldb[kMaxBlocks];
     const float *bias[kMaxBlocks]; int act[kMaxBlocks]; int ncols[kMaxBlocks]; int transb[kMaxBlocks];
     float *C[kMaxBlocks]; int64_t ldc[kMaxBlocks];
@@ -50,7 +55,7 @@ struct Plan {
         kpad8 = (uint32_t)((K + 7) / 8) * 8;
         b_bytes = (uint32_t)kUN * kpad8 * 4u;
         a_stage_bytes = 2u * BM * BK * 4u;
-        const uint32_t fixed = 2u * b_bytes + kEpilogueWarps * kStageBytes + 128u + kUN * 4u;
+        const uint32_t fixed = 2u * b_bytes + kEpilogueWarps * kStageBytes + kBarrierBytes + kUN * 4u;
         const uint32_t budget = 227u * 1024u;
         stages = 0;
         for (uint32_t st = 4; st >= 2; --st)
@@ -67,9 +72,9 @@ __global__ void __launch_bounds__(kThreadsProj, 1) gemm_proj_kernel(const Params
     uint8_t *a_ring = smem + 2 * L.b_bytes;
     uint8_t *stage_base = a_ring + STAGES * L.a_stage_bytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(stage_base + kEpilogueWarps * kStageBytes);
-    uint64_t *empty = full + STAGES, *acc_full = empty + STAGES, *acc_empty = acc_full + 2;
+    uint64_t *empty = full + STAGES, *landed = empty + STAGES, *acc_full = landed + STAGES, *acc_empty = acc_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
-    float *s_bias = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(full) + 128);
+    float *s_bias = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(full) + kBarrierBytes);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int cb = (int)blockIdx.x % p.nb, group = (int)blockIdx.x / p.nb;
     const int ncols = p.ncols[cb];
@@ -80,7 +85,9 @@ __global__ void __launch_bounds__(kThreadsProj, 1) gemm_proj_kernel(const Params
 
     for (int i = t; i < kUN; i += kThreadsProj) s_bias[i] = (p.bias[cb] != nullptr && i < ncols) ? __ldg(p.bias[cb] + i) : 0.0f;
     if (t == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], kProducerWarps); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full[i], kProducerWarps); mbar_init(&empty[i], 1); mbar_init(&landed[i], kLoaderWarps * 32);
+        }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpilogueWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -122,17 +129,20 @@ __global__ void __launch_bounds__(kThreadsProj, 1) gemm_proj_kernel(const Params
         return tl >= p.tiles_m ? tl - p.tiles_m : tl;
     };
 
-    if (warp < kProducerWarps) {
-        // ===================== producers: cp.async A (possibly from a peer GPU) -> UMMA layout, lo = a - trunc(a) =====================
+    if (warp >= kLoaderWarp0) {
+        // ===================== loaders: cp.async A (possibly from a peer GPU) straight into the UMMA layout =====================
+        // The round-1 kernel (and the first version of this one) let the same threads load AND convert: a k-block could only be
+        // published after the thread had blocked on the stage for a later load, so producer, tensor core and the commit
+        // round trip (~1000 cycles, measured with the TFGK_PROJ_DEBUG switches) ran one after the other.  Here every
+        // role blocks only on its own dependency: loaders on `empty`, converters on `landed`, the MMA issuer on `full`.
+        const int tl = t - kLoaderWarp0 * 32;                                // 0..63
         const uint32_t a_ring_addr = smem_u32(a_ring);
-        constexpr int kChunks = (BM * BK / 4) / (kProducerWarps * 32);      // 8 per thread per k-block
-        const int r8 = t & 7, kc = (t >> 3) & 7, rg0 = t >> 6;              // chunk c = t + 128 i: rows (rg0 + 2 i) * 8 + r8
+        constexpr int kChunks = (BM * BK / 4) / (kLoaderWarps * 32);        // 16 per thread per k-block
+        const int r8 = tl & 7, kc = (tl >> 3) & 7;                          // chunk c = tl + 64 i: rows i * 8 + r8
         // L2 prefetch of whole row tiles kPrefetchTiles ahead (one bulk-prefetch instruction per tile, issued by the group's
-        // first column block): the cp.async ring can only keep ~25 KB in flight per SM next to the resident W, which at
-        // DRAM latency is ~1/4 of what the tensor core consumes; with the tile already in L2 the same ring is enough.
-        // Peer-mapped parts are not prefetched (remote data bypasses the local L2).
+        // first column block).  Peer-mapped parts are not prefetched (remote data bypasses the local L2).
         constexpr int kPrefetchTiles = 4;
-        const bool can_prefetch = (cb == 0) && (t == 0) && p.lda <= 2 * (int64_t)p.K;
+        const bool can_prefetch = (cb == 0) && (tl == 0) && p.lda <= 2 * (int64_t)p.K;
         auto prefetch_tile = [&](int it) {
             if (!can_prefetch || it >= my_tiles) return;
             const int64_t m0 = (int64_t)tile_of(it) * BM;
@@ -144,38 +154,35 @@ __global__ void __launch_bounds__(kThreadsProj, 1) gemm_proj_kernel(const Params
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
         };
         for (int i = 0; i < kPrefetchTiles; ++i) prefetch_tile(i);
-        auto issue_load = [&](int G) {
-            if (G < total_kb) {
-                const int stage = G % STAGES;
-                mbar_wait(&empty[stage], (uint32_t)(((G / STAGES) & 1) ^ 1));
-                const int tile = tile_of(G / nkb), kb = G % nkb;
-                if (kb == 0) prefetch_tile(G / nkb + kPrefetchTiles);
-                const int k = kb * BK + kc * 4;
-                if (k < (int)L.kpad8 && !(p.dbg & 8)) {
-                    const int64_t m0 = (int64_t)tile * BM;
-                    const int part = p.n_parts > 1 ? (int)(m0 / p.part_rows) : 0;
-                    const float *base = p.A[part] + (m0 - (int64_t)part * p.part_rows) * p.lda + k;
-                    const uint32_t kbytes = k < p.K ? (uint32_t)min(4, p.K - k) * 4u : 0u;
-                    const uint32_t dst0 = a_ring_addr + stage * L.a_stage_bytes + (uint32_t)t * 16u;
+        for (int G = 0; G < total_kb; ++G) {
+            const int stage = G % STAGES;
+            mbar_wait(&empty[stage], (uint32_t)(((G / STAGES) & 1) ^ 1));      // MMAs of k-block G - STAGES retired
+            const int tile = tile_of(G / nkb), kb = G % nkb;
+            if (kb == 0) prefetch_tile(G / nkb + kPrefetchTiles);
+            const int k = kb * BK + kc * 4;
+            if (k < (int)L.kpad8 && !(p.dbg & 8)) {
+                const int64_t m0 = (int64_t)tile * BM;
+                const int part = p.n_parts > 1 ? (int)(m0 / p.part_rows) : 0;
+                const float *base = p.A[part] + (m0 - (int64_t)part * p.part_rows) * p.lda + k;
+                const uint32_t kbytes = k < p.K ? (uint32_t)min(4, p.K - k) * 4u : 0u;
+                const uint32_t dst0 = a_ring_addr + stage * L.a_stage_bytes + (uint32_t)tl * 16u;
 #pragma unroll
-                    for (int i = 0; i < kChunks; ++i) {
-                        const int rl = (rg0 + 2 * i) * 8 + r8;
-                        const bool ok = m0 + rl < p.M;
-                        cp_async16_zfill(dst0 + (uint32_t)i * 2048u, ok ? base + (int64_t)rl * p.lda : p.A[0], ok ? kbytes : 0u);
-                    }
+                for (int i = 0; i < kChunks; ++i) {
+                    const int rl = i * 8 + r8;
+                    const bool ok = m0 + rl < p.M;
+                    cp_async16_zfill(dst0 + (uint32_t)i * 1024u, ok ? base + (int64_t)rl * p.lda : p.A[0], ok ? kbytes : 0u);
                 }
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-#pragma unroll
-        for (int G = 0; G < STAGES - 1; ++G) issue_load(G);
+            // the stage's `landed` barrier completes when the copies of all 64 loader threads have arrived
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&landed[stage])) : "memory");
+        }
+    } else if (warp < kProducerWarps) {
+        // ===================== converters: lo = a - trunc_tf32(a) for every landed k-block =====================
+        constexpr int kChunks = (BM * BK / 4) / (kProducerWarps * 32);      // 8 per thread per k-block
+        const int kc = (t >> 3) & 7;                                        // chunk c = t + 128 i
         for (int G = 0; G < total_kb; ++G) {
-            // k-block G has landed when at most STAGES-2 younger groups are pending.  Convert and publish it FIRST, and only
-            // then block on the stage that k-block G+STAGES-1 will overwrite (free once the MMAs of k-block G-1 retire): in the
-            // round-1 order (issue, then convert) the conversion of k-block G could not start before the MMAs of G-1 had
-            // finished, so tensor core and producers alternated instead of overlapping (tensor pipe 25% busy).
-            asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
             const int stage = G % STAGES, kb = G % nkb;
+            mbar_wait(&landed[stage], (uint32_t)((G / STAGES) & 1));
             if (kb * BK + kc * 4 < (int)L.kpad8 && !(p.dbg & 1)) {
                 uint8_t *sraw = a_ring + stage * L.a_stage_bytes + t * 16;
 #pragma unroll
@@ -192,7 +199,6 @@ __global__ void __launch_bounds__(kThreadsProj, 1) gemm_proj_kernel(const Params
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[stage]);
-            issue_load(G + STAGES - 1);
         }
     } else if (warp == kProducerWarps + kEpilogueWarps) {
         // ===================== MMA issuer =====================
@@ -240,6 +246,10 @@ __global__ void __launch_bounds__(kThreadsProj, 1) gemm_proj_kernel(const Params
             for (int c0 = 0; c0 < un; c0 += 32) {
                 uint32_t r[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kUN + c0);
+                if (p.dbg & 16) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = 0;
+                } else
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
@@ -255,6 +265,7 @@ __global__ void __launch_bounds__(kThreadsProj, 1) gemm_proj_kernel(const Params
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 }
+                if (p.dbg & 32) continue;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const float v0 = apply_act(__uint_as_float(r[j]) + s_bias[c0 + j], act);
