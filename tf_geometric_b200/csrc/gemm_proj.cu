@@ -26,15 +26,16 @@ using namespace tc;
 
 constexpr int kMaxBlocks = 4;
 constexpr int kMaxParts = 8;
-// warp roles: 0-3 converters (lo = a - trunc(a) on landed k-blocks), 4-7 epilogue (TMEM lane quarter = warp % 4),
-// 8 MMA issuer, 9-10 loaders (cp.async into the ring as soon as a stage is free)
-constexpr int kProducerWarps = 4, kEpilogueWarps = 4, kLoaderWarps = 2;
+// warp roles: 0-3 converters (lo = a - trunc(a) on landed k-blocks), 4-11 epilogue (TMEM lane quarter = warp % 4, two
+// warps per quarter split the columns), 12 MMA issuer, 13-14 loaders (cp.async into the ring as soon as a stage is free)
+constexpr int kProducerWarps = 4, kEpilogueWarps = 8, kLoaderWarps = 2;
 constexpr int kLoaderWarp0 = kProducerWarps + kEpilogueWarps + 1;
-constexpr int kThreadsProj = (kProducerWarps + kEpilogueWarps + 1 + kLoaderWarps) * 32;      // 352
+constexpr int kThreadsProj = (kProducerWarps + kEpilogueWarps + 1 + kLoaderWarps) * 32;      // 480
 constexpr int kBarrierBytes = 192;
 constexpr int kUN = 128;                 // accumulator columns per buffer
 constexpr int kTmemColsProj = 256;       // 2 accumulator buffers
-constexpr int kStageRowBytes = 144;      // 32 floats + 16 B pad: conflict-free for row-wise STS.128 and segment-wise LDS.128
+constexpr int kPassCols = 16;             // accumulator columns per TMEM round trip of an epilogue warp
+constexpr int kStageRowBytes = 80;       // 16 floats + 16 B pad: conflict-free row-wise STS.128, segment-wise LDS.128
 constexpr int kStageBytes = 32 * kStageRowBytes;
 
 struct Params {
@@ -229,45 +230,51 @@ __global__ void __launch_bounds__(kThreadsProj, 1) gemm_proj_kernel(const Params
         }
     } else {
         // ===================== epilogue: TMEM -> registers -> staging tile -> 128-byte row segments =====================
-        const int q = warp & 3;                               // TMEM lane quarter of this warp (warps 4..7 -> 0..3)
-        uint8_t *stg = stage_base + q * kStageBytes;
+        const int ew = warp - kProducerWarps;                 // 0..7
+        const int q = warp & 3, half = ew >> 2;               // TMEM lane quarter (= warp % 4) and column half of this warp
+        uint8_t *stg = stage_base + ew * kStageBytes;
         const uint32_t stg_addr = smem_u32(stg);
         float *__restrict__ Cb = p.C[cb];
         const int64_t ldc = p.ldc[cb];
         const int act = p.act[cb];
         const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cb) & 15) == 0);
-        const int seg_row = lane >> 3, seg_chunk = lane & 7;
+        const int seg_row = lane >> 2, seg_chunk = lane & 3;  // store phase: 8 rows x 64 bytes per instruction
+        const int n_pass = un / kPassCols;
+        const int pass0 = half == 0 ? 0 : (n_pass + 1) / 2, pass1 = half == 0 ? (n_pass + 1) / 2 : n_pass;
         for (int it = 0; it < my_tiles; ++it) {
             const int buf = it & 1;
             const int tile = tile_of(it);
             mbar_wait(&acc_full[buf], (uint32_t)((it >> 1) & 1));
             tc_fence_after();
             const int64_t row0 = (int64_t)tile * BM + q * 32;
-            for (int c0 = 0; c0 < un; c0 += 32) {
-                uint32_t r[32];
+            if (pass0 >= pass1) {                             // nothing to read (a single pass belongs to the other half)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            }
+            for (int ps = pass0; ps < pass1; ++ps) {
+                const int c0 = ps * kPassCols;
+                uint32_t r[16];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kUN + c0);
                 if (p.dbg & 16) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] = 0;
+                    for (int j = 0; j < 16; ++j) r[j] = 0;
                 } else
                 asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-                    "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c0 + 32 >= un) {                          // accumulator drained: the MMA issuer may reuse this buffer
+                if (ps + 1 == pass1) {                        // this warp's share is drained: one arrive per warp frees the buffer
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 }
                 if (p.dbg & 32) continue;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
+                for (int j = 0; j < 16; j += 4) {
                     const float v0 = apply_act(__uint_as_float(r[j]) + s_bias[c0 + j], act);
                     const float v1 = apply_act(__uint_as_float(r[j + 1]) + s_bias[c0 + j + 1], act);
                     const float v2 = apply_act(__uint_as_float(r[j + 2]) + s_bias[c0 + j + 2], act);
@@ -277,8 +284,8 @@ __global__ void __launch_bounds__(kThreadsProj, 1) gemm_proj_kernel(const Params
                 __syncwarp();
                 const int col = c0 + seg_chunk * 4;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int rl = j * 4 + seg_row;
+                for (int j = 0; j < 4; ++j) {
+                    const int rl = j * 8 + seg_row;
                     const int64_t row = row0 + rl;
                     const float4 v = *reinterpret_cast<const float4 *>(stg + rl * kStageRowBytes + seg_chunk * 16);
                     if (row < p.M && !(p.dbg & 4)) {
