@@ -256,6 +256,29 @@ int tfgk_gat_softmax_bwd_f32(const int64_t *rowptr, const int32_t *col, const fl
                              int32_t n_dst, int32_t H, int32_t dv, int split_value_heads,
                              float drop_rate, uint64_t seed, uint32_t rng_stream, float *ds, void *stream);
 
+/* Training without the [E, H] coefficient table (round 2).  The forward pass is the same streaming kernel as
+ * tfgk_gat_fused_f32 (heads concatenated, dqk == dv, H * dqk <= 128) and additionally keeps stats[N, 2H]: per (row, head)
+ * the softmax maximum and the denominator (+1e-8).  The backward pass recomputes every coefficient from Q, K and stats:
+ *   _prepare: GS[N, H*dqk + 32] = [ G * act'(Y) | max (8) | denominator (8) | delta = <G, Y - bias> per head (8) | pad (8) ]
+ *   _dst    : dQ[r] = (1/scale) sum_{e in row r} ds_e K[col_e]                     forward CSR
+ *   _src    : dK[c] = (1/scale) sum ds_e Q[row_e],  dV[c] = sum a_e G[row_e]       transposed CSR (rows = sources)
+ * with a_e = exp(<Q_r, K_c>/scale - max_r) / den_r and ds_e = a_e (<G_r, V_c> - delta_r) per head.  Replaces TensorFlow
+ * autodiff over gat.py:73-114.  TFGK_ERR_UNSUPPORTED for H > 8, non power-of-two head sizes or unaligned operands. */
+int tfgk_gat_fused_stats_f32(const int64_t *rowptr, const int32_t *col,
+                             const float *Q, int64_t ldq, const float *K, int64_t ldk, const float *V, int64_t ldv,
+                             int32_t N, int32_t H, int32_t dqk, int32_t dv, float scale,
+                             const float *bias, int act, float *out, int64_t ldo, float *stats,
+                             const tfgk_plan *plan, void *stream);
+int tfgk_gat_bwd_prepare_f32(const float *G, int64_t ldg, const float *Y, int64_t ldy, const float *bias, int act,
+                             const float *stats, int32_t N, int32_t H, int32_t dqk, float *GS, int64_t ldgs, void *stream);
+int tfgk_gat_bwd_dst_f32(const int64_t *rowptr, const int32_t *col, const float *Q, int64_t ldq,
+                         const float *K, int64_t ldk, const float *V, int64_t ldv, const float *GS, int64_t ldgs,
+                         int32_t N, int32_t H, int32_t dqk, float scale, float *dQ, int64_t lddq, void *stream);
+int tfgk_gat_bwd_src_f32(const int64_t *rowptr_t, const int32_t *col_t, const float *Q, int64_t ldq,
+                         const float *K, int64_t ldk, const float *V, int64_t ldv, const float *GS, int64_t ldgs,
+                         int32_t N, int32_t H, int32_t dqk, float scale, float *dK, int64_t lddk, float *dV, int64_t lddv,
+                         void *stream);
+
 /* ---- device-side edge sampling -------------------------------------------------------------- */
 
 /* flag[e] = structural(e) && bernoulli(e):

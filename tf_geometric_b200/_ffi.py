@@ -73,6 +73,13 @@ SIGNATURES = {
                             _int, _ptr, _i64, _ptr],
     "tfgk_gat_softmax_bwd_f32": [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _int, _f32, _u64, _u32,
                                  _ptr, _ptr],
+    "tfgk_gat_fused_stats_f32": [_ptr, _ptr, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _i32, _f32, _ptr, _int,
+                                 _ptr, _i64, _ptr, _ptr, _ptr],
+    "tfgk_gat_bwd_prepare_f32": [_ptr, _i64, _ptr, _i64, _ptr, _int, _ptr, _i32, _i32, _i32, _ptr, _i64, _ptr],
+    "tfgk_gat_bwd_dst_f32": [_ptr, _ptr, _ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _f32, _ptr, _i64,
+                             _ptr],
+    "tfgk_gat_bwd_src_f32": [_ptr, _ptr, _ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i32, _i32, _i32, _f32, _ptr, _i64,
+                             _ptr, _i64, _ptr],
     "tfgk_edge_flags_i32": [_ptr, _ptr, _i64, _int, _ptr, _ptr, _int, _f32, _u64, _u32, _ptr, _ptr],
     "tfgk_select_workspace_bytes": [_i64, ctypes.POINTER(_size)],
     "tfgk_select_flagged_i32": [_ptr, _i64, _ptr, ctypes.POINTER(_i64), _ptr, _size, _ptr],

@@ -153,8 +153,21 @@ class GatAttention(torch.autograd.Function):
             y = ops.spmm_heads(csr, att, Vd, H, mode=ops.HEADS_SPLIT if split else ops.HEADS_REDUCE,
                                drop_rate=drop_rate, seed=seed, alpha=1.0 if split else 1.0 / H, bias=b, act=act_code)
         else:
+            # no dropout: keep (max, denominator) per (row, head) instead of the [E', H] coefficients and recompute them in
+            # the backward pass; shapes the streaming kernel does not take, and hub-row plans, keep the coefficient table
+            res = None
+            plan = getattr(csr, "plan", None)
+            if split and (plan is None or plan.n_hubs == 0) and csr.n_rows == Qd.shape[0]:
+                res = ops.gat_fused_stats(csr, Qd, Kd, Vd, H, bias=b, act=act_code, scale=scale)
+            if res is not None:
+                y, stats = res
+                ctx.save_for_backward(Qd, Kd, Vd, stats, y)
+                ctx.meta = (csr, edge_index_used, H, bool(split), act_code, 0.0, seed, bias is not None, float(scale))
+                ctx.recompute, ctx.bias = True, b
+                return y
             y, att = ops.gat_fused(csr, Qd, Kd, Vd, H, split_value_heads=split, bias=b, act=act_code,
                                    return_attention=True, scale=scale)
+        ctx.recompute = False
         ctx.save_for_backward(Qd, Kd, Vd, att, y if act_code == ops.ACT_RELU else None)
         ctx.meta = (csr, edge_index_used, H, bool(split), act_code, float(drop_rate), seed, bias is not None, float(scale))
         return y
@@ -164,6 +177,16 @@ class GatAttention(torch.autograd.Function):
         Q, K, V, att, y = ctx.saved_tensors
         csr, edge_index_used, H, split, act_code, drop_rate, seed, has_bias, scale = ctx.meta
         g = grad_y.contiguous()
+        if ctx.recompute:
+            csr_t, _ = _transposed_of_csr(csr, edge_index_used)
+            res = ops.gat_backward_recompute(csr, csr_t, Q, K, V, g, y, ctx.bias, act_code, att, H, scale)
+            if res is None:
+                raise RuntimeError("GatAttention: the recompute backward refused a shape its forward accepted")
+            grad_b = None
+            if has_bias and ctx.needs_input_grad[3]:
+                gm = g * (y > 0).to(g.dtype) if act_code == ops.ACT_RELU else g
+                grad_b = ops.colsum(gm)
+            return res[0], res[1], res[2], grad_b, None, None, None, None, None, None, None, None
         if act_code == ops.ACT_RELU:
             g = g * (y > 0).to(g.dtype)
         inv_scale = 1.0 / scale

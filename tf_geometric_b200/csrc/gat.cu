@@ -42,6 +42,7 @@ struct GatParams {
     int32_t n_hubs;
     const int32_t *hub_row, *hub_slot0, *hub_nslots;
     float *scratch;      // per slot: [A] partial sums | [32] running max per lane | [32] denominators per lane
+    float *stats;        // optional [N, 2H]: per (row, head) softmax maximum and denominator (+1e-8), kept for the backward pass
 };
 
 // ---- fast path: float4 lanes, H | 32, dqk/4 a power of two, heads concatenated ---------------------------------
@@ -383,6 +384,10 @@ __global__ void __launch_bounds__(kGatAsyncWarps * 32) gat_async_kernel(const Ga
             o.z = apply_act(a2 * inv + bias.z, p.act);
             o.w = apply_act(a3 * inv + bias.w, p.act);
             *reinterpret_cast<float4 *>(p.out + r * p.ldo + ccol) = o;
+            if (p.stats != nullptr && (lane % lanes_per_head) == 0) {      // training: (max, denominator) instead of [E, H] coefficients
+                p.stats[r * 2 * p.H + lane / lanes_per_head] = mx;
+                p.stats[r * 2 * p.H + p.H + lane / lanes_per_head] = den + 1e-8f;
+            }
         }
         mx = -FLT_MAX; den = 0.0f; a0 = a1 = a2 = a3 = 0.0f;
         ++r;
@@ -485,6 +490,10 @@ __global__ void __launch_bounds__(256) gat_hub_fixup_kernel(const GatParams p) {
             const float4 v = *reinterpret_cast<const float4 *>(src + ccol);
             a0 = fmaf(v.x, sc, a0); a1 = fmaf(v.y, sc, a1); a2 = fmaf(v.z, sc, a2); a3 = fmaf(v.w, sc, a3);
         }
+    }
+    if (cok && p.stats != nullptr && (lane % (p.dqk >> 2)) == 0) {
+        p.stats[r * 2 * p.H + lane / (p.dqk >> 2)] = m;
+        p.stats[r * 2 * p.H + p.H + lane / (p.dqk >> 2)] = den + 1e-8f;
     }
     if (cok) {
         const float inv = 1.0f / (den + 1e-8f);
@@ -684,11 +693,11 @@ extern "C" int tfgk_segment_softmax_f32(const int64_t *rowptr, const float *scor
     return TFGK_OK;
 }
 
-extern "C" int tfgk_gat_fused_f32(const int64_t *rowptr, const int32_t *col,
-                                  const float *Q, int64_t ldq, const float *K, int64_t ldk, const float *V, int64_t ldv,
-                                  int32_t N, int32_t H, int32_t dqk, int32_t dv, float scale, int split_value_heads,
-                                  const float *bias, int act, float *att, int write_att, float *out, int64_t ldo,
-                                  const tfgk_plan *plan, void *stream) {
+static int gat_fused_impl(const int64_t *rowptr, const int32_t *col,
+                          const float *Q, int64_t ldq, const float *K, int64_t ldk, const float *V, int64_t ldv,
+                          int32_t N, int32_t H, int32_t dqk, int32_t dv, float scale, int split_value_heads,
+                          const float *bias, int act, float *att, int write_att, float *out, int64_t ldo,
+                          const tfgk_plan *plan, float *stats, void *stream) {
     TFGK_CHECK_ARG(N >= 0 && H >= 1 && dqk >= 1 && dv >= 1, "gat: bad size (N=%d H=%d dqk=%d dv=%d)", N, H, dqk, dv);
     TFGK_CHECK_ARG(act == TFGK_ACT_NONE || act == TFGK_ACT_RELU, "gat: unknown activation %d", act);
     TFGK_CHECK_ARG(scale > 0.0f, "gat: scale must be positive");
@@ -706,6 +715,7 @@ extern "C" int tfgk_gat_fused_f32(const int64_t *rowptr, const int32_t *col,
     p.bias = bias; p.act = act; p.att = att; p.write_att = write_att; p.out = out; p.ldo = ldo;
     p.n_tasks = 0; p.task_row = nullptr; p.task_nrows = nullptr; p.task_e0 = nullptr; p.task_e1 = nullptr;
     p.task_slot = nullptr; p.n_hubs = 0; p.hub_row = nullptr; p.hub_slot0 = nullptr; p.hub_nslots = nullptr; p.scratch = nullptr;
+    p.stats = stats;
     if (plan != nullptr && plan->n_tasks > 0) {
         if (plan->n_hubs > 0)
             TFGK_CHECK_ARG(plan->scratch != nullptr && plan->scratch_bytes >= (size_t)plan->n_slots * (H * dv + 64) * sizeof(float),
@@ -722,8 +732,9 @@ extern "C" int tfgk_gat_fused_f32(const int64_t *rowptr, const int32_t *col,
                       ldv % 4 == 0 && ldo % 4 == 0 && aligned16(Q) && aligned16(K) && aligned16(V) && aligned16(out) &&
                       (!bias || aligned16(bias));
     const char *impl = getenv("TFGK_GAT_IMPL");          // "twopass" forces the reference-order kernel
-    if (fast && dqk == dv && A <= 128 && !write_att && !(impl && (impl[0] == 't' || impl[0] == 'o')))
+    if (fast && dqk == dv && A <= 128 && !write_att && (stats != nullptr || !(impl && (impl[0] == 't' || impl[0] == 'o'))))
         return dispatch_gat_async(p, st);                    // "online" forces the register-staged single-pass kernel
+    if (stats != nullptr) return TFGK_ERR_UNSUPPORTED;      // only the streaming kernel keeps (max, denominator)
     if (fast && dqk == dv && !(impl && impl[0] == 't')) {
         switch ((A + 127) / 128) {
             case 1: return launch_gat_online<1>(p, st);
@@ -747,4 +758,23 @@ extern "C" int tfgk_gat_fused_f32(const int64_t *rowptr, const int32_t *col,
     gat_generic_kernel<<<(unsigned)ceil_div64(N, kGatWarps), kGatThreads, smem, st>>>(p);
     TFGK_LAUNCH_CHECK();
     return TFGK_OK;
+}
+
+extern "C" int tfgk_gat_fused_f32(const int64_t *rowptr, const int32_t *col,
+                                  const float *Q, int64_t ldq, const float *K, int64_t ldk, const float *V, int64_t ldv,
+                                  int32_t N, int32_t H, int32_t dqk, int32_t dv, float scale, int split_value_heads,
+                                  const float *bias, int act, float *att, int write_att, float *out, int64_t ldo,
+                                  const tfgk_plan *plan, void *stream) {
+    return gat_fused_impl(rowptr, col, Q, ldq, K, ldk, V, ldv, N, H, dqk, dv, scale, split_value_heads, bias, act, att, write_att,
+                          out, ldo, plan, nullptr, stream);
+}
+
+extern "C" int tfgk_gat_fused_stats_f32(const int64_t *rowptr, const int32_t *col,
+                                        const float *Q, int64_t ldq, const float *K, int64_t ldk, const float *V, int64_t ldv,
+                                        int32_t N, int32_t H, int32_t dqk, int32_t dv, float scale,
+                                        const float *bias, int act, float *out, int64_t ldo, float *stats,
+                                        const tfgk_plan *plan, void *stream) {
+    TFGK_CHECK_ARG(stats != nullptr, "gat_fused_stats: stats buffer is required");
+    return gat_fused_impl(rowptr, col, Q, ldq, K, ldk, V, ldv, N, H, dqk, dv, scale, 1, bias, act, nullptr, 0, out, ldo, plan,
+                          stats, stream);
 }

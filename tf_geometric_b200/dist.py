@@ -360,6 +360,13 @@ def gcn_gat_overlapped(pg, x_local, gcn_kernel, gcn_bias, gcn_activation,
 
 # ---- bench.py --gpus N ------------------------------------------------------------------------------------------------
 
+def _tolerance_fraction(got, want):
+    """max |got - want| / (1e-4 * max|want| + 1e-4 * |want|): <= 1 means inside north_star's fp32 gate
+    (allclose(rtol=1e-4, atol=1e-4 * max|ref|))."""
+    bound = 1e-4 * want.abs().max() + 1e-4 * want.abs() + 1e-30
+    return float(((got - want).abs() / bound).max())
+
+
 def _sampled_row_check(pg, edge_index_global, n, x_hosts, gcn, gat, out_gcn, out_gat, heads, samples=48):
     """Independent float64 restatement (plain torch on the device, no kernel of this library) of GCN and GAT for a few
     of this rank's rows, from the GLOBAL edge list and the features of every rank: guards the path that is timed."""
@@ -380,7 +387,7 @@ def _sampled_row_check(pg, edge_index_global, n, x_hosts, gcn, gat, out_gcn, out
         coef = (deg[r] ** -0.5) * (deg[nb] ** -0.5)
         want = torch.relu((coef[:, None] * (x_all[nb] @ w_gcn)).sum(0) + gcn.bias.double())
         got = out_gcn[r - p.lo].double()
-        worst = max(worst, float(((got - want).abs() / (want.abs() + 1e-4 * want.abs().max() + 1e-12)).max()))
+        worst = max(worst, _tolerance_fraction(got, want))
         # GAT: per head softmax over the neighbours (self loop included) of <q_r, k_j> / sqrt(d)
         q = torch.relu(x_all[r] @ wq + gat.query_bias.double()).view(heads, -1)
         k = torch.relu(x_all[nb] @ wk + gat.key_bias.double()).view(len(nb), heads, -1)
@@ -388,7 +395,7 @@ def _sampled_row_check(pg, edge_index_global, n, x_hosts, gcn, gat, out_gcn, out
         att = torch.softmax((k * q[None]).sum(-1) / (q.shape[1] ** 0.5), dim=0)
         want = torch.relu((att[:, :, None] * v).sum(0).reshape(-1) + gat.bias.double())
         got = out_gat[r - p.lo].double()
-        worst = max(worst, float(((got - want).abs() / (want.abs() + 1e-4 * want.abs().max() + 1e-12)).max()))
+        worst = max(worst, _tolerance_fraction(got, want))
     return worst
 
 
@@ -454,11 +461,11 @@ def bench_papers(args, rank, world, device, metric, config):
         xs = torch.cat([_hash_features(int(j), 1, F, device) for j in nb.tolist()]).double()
         want = torch.relu((coef[:, None] * (xs @ w64)).sum(0) + gcn.bias.double())
         got = out[r].double()
-        worst = max(worst, float(((got - want).abs() / (want.abs() + 1e-4 * want.abs().max() + 1e-12)).max()))
+        worst = max(worst, _tolerance_fraction(got, want))
     check = torch.tensor([worst], dtype=torch.float64, device=device)
     dist.all_reduce(check, op=dist.ReduceOp.MAX)
-    if float(check[0]) > 1e-4:
-        raise SystemExit("cfg5 parity check failed: sampled-row relative error {:.3e}".format(float(check[0])))
+    if float(check[0]) > 1.0:
+        raise SystemExit("cfg5 parity check failed: sampled-row error is {:.3e} of the tolerance".format(float(check[0])))
     del deg_all, counts, out
 
     for _ in range(max(args.warmup, 3) - 1):
@@ -504,7 +511,8 @@ def bench_papers(args, rank, world, device, metric, config):
                              "algorithmic_bytes": spmm_bytes, "kernel_ms": spmm_ms},
                 "cpu_baseline": None,
                 "breakdown_ms": {"gcn_spmm": spmm_ms, "projection_incl_exchange": proj_ms, "first_call_incl_cache_s": t_cache},
-                "parity": {"sampled_rows_max_rel_err_vs_float64": float(check[0])},
+                "parity": {"sampled_rows_error_as_fraction_of_tolerance_vs_float64": float(check[0]),
+                           "tolerance": "allclose(rtol=1e-4, atol=1e-4*max|ref|)"},
                 "max_memory_GiB_rank0": mem,
                 "exchange": {"mode": pg.exchange, "nvlink_bytes_in_per_rank_per_step": nvlink_per_step,
                              "hbm_algorithmic_bytes_per_rank_per_step": spmm_bytes + part.n_local * B.UNITS * 4
@@ -563,8 +571,8 @@ def bench_partitioned(args, rank, world, device, metric, config):
         del a2, b2
     check = torch.tensor([err, 0.0 if identical in (None, True) else 1.0], dtype=torch.float64, device=device)
     dist.all_reduce(check, op=dist.ReduceOp.MAX)
-    if float(check[0]) > 1e-4 or float(check[1]) != 0.0:
-        raise SystemExit("partitioned path failed its parity check: sampled-row error {:.3e}, p2p == collective: {}".format(
+    if float(check[0]) > 1.0 or float(check[1]) != 0.0:
+        raise SystemExit("partitioned path failed its parity check: sampled-row error {:.3e} of the tolerance, p2p == collective: {}".format(
             float(check[0]), float(check[1]) == 0.0))
     del a, b
     torch.cuda.empty_cache()
@@ -623,7 +631,8 @@ def bench_partitioned(args, rank, world, device, metric, config):
                              "algorithmic_bytes": gat_bytes, "kernel_ms": gat_ms},
                 "cpu_baseline": None,
                 "breakdown_ms": {"gat_fused": gat_ms, "gcn_spmm": spmm_ms, "projections_incl_exchange": proj_ms},
-                "parity": {"sampled_rows_max_rel_err_vs_float64": float(check[0]),
+                "parity": {"sampled_rows_error_as_fraction_of_tolerance_vs_float64": float(check[0]),
+                           "tolerance": "allclose(rtol=1e-4, atol=1e-4*max|ref|)",
                            "all_rows_bit_identical_to_collective_path": identical},
                 "exchange": {"mode": mode,
                              "what": ("x rows pulled over NVLink peer mappings inside the projection GEMM (fused all-gather -> "

@@ -347,6 +347,54 @@ def gat_fused(csr, Q, K, V, num_heads, split_value_heads=True, bias=None, act=AC
     return out
 
 
+def gat_fused_stats(csr, Q, K, V, num_heads, bias=None, act=ACT_NONE, scale=None):
+    """Training forward without the [E, H] coefficient table: returns (out, stats[N, 2H]) or None when the shape is not
+    taken by the streaming kernel (tfgk_gat_fused_stats_f32)."""
+    N, H = csr.n_rows, int(num_heads)
+    A = Q.shape[1]
+    if A % H or V.shape[1] != A or K.shape[1] != A:
+        return None
+    dqk = A // H
+    scale = float(np.sqrt(np.float32(dqk))) if scale is None else float(scale)
+    out = torch.empty((N, A), dtype=torch.float32, device=Q.device)
+    stats = torch.empty((N, 2 * H), dtype=torch.float32, device=Q.device)
+    plan = getattr(csr, "plan", None)
+    plan_struct = plan.struct(A + 64, Q.device) if plan is not None else None
+    try:
+        _ffi.call("tfgk_gat_fused_stats_f32", _p(csr.rowptr), _p(csr.col), _p(Q), _row_major_2d(Q, "Q"), _p(K),
+                  _row_major_2d(K, "K"), _p(V), _row_major_2d(V, "V"), N, H, dqk, dqk, scale, _p(bias), act, _p(out),
+                  _row_major_2d(out, "out"), _p(stats), ctypes.byref(plan_struct) if plan_struct is not None else None, _stream(Q))
+    except _ffi.TfgkError as err:
+        if err.code != _ffi.ERR_UNSUPPORTED:
+            raise
+        return None
+    return out, stats
+
+
+def gat_backward_recompute(csr, csr_t, Q, K, V, G, Y, bias, act, stats, num_heads, scale):
+    """(dQ, dK, dV) of the fused attention aggregation from (max, denominator) per row (tfgk_gat_bwd_*); None when the
+    kernels do not take the shape."""
+    N, H = csr.n_rows, int(num_heads)
+    A = Q.shape[1]
+    dqk = A // H
+    GS = torch.empty((N, A + 32), dtype=torch.float32, device=Q.device)
+    dQ, dK, dV = torch.empty_like(Q), torch.empty_like(K), torch.empty_like(V)
+    try:
+        _ffi.call("tfgk_gat_bwd_prepare_f32", _p(G), _row_major_2d(G, "G"), _p(Y), _row_major_2d(Y, "Y"), _p(bias), act,
+                  _p(stats), N, H, dqk, _p(GS), A + 32, _stream(Q))
+        _ffi.call("tfgk_gat_bwd_dst_f32", _p(csr.rowptr), _p(csr.col), _p(Q), _row_major_2d(Q, "Q"), _p(K),
+                  _row_major_2d(K, "K"), _p(V), _row_major_2d(V, "V"), _p(GS), A + 32, N, H, dqk, float(scale), _p(dQ),
+                  _row_major_2d(dQ, "dQ"), _stream(Q))
+        _ffi.call("tfgk_gat_bwd_src_f32", _p(csr_t.rowptr), _p(csr_t.col), _p(Q), _row_major_2d(Q, "Q"), _p(K),
+                  _row_major_2d(K, "K"), _p(V), _row_major_2d(V, "V"), _p(GS), A + 32, N, H, dqk, float(scale), _p(dK),
+                  _row_major_2d(dK, "dK"), _p(dV), _row_major_2d(dV, "dV"), _stream(Q))
+    except _ffi.TfgkError as err:
+        if err.code != _ffi.ERR_UNSUPPORTED:
+            raise
+        return None
+    return dQ, dK, dV
+
+
 # ---- training-mode extras: dropout, per-head aggregation, GAT softmax backward -----------------------------------
 
 RNG_STREAM_DROPOUT, RNG_STREAM_SAMPLER = 0, 1      # rng_stream ids: independent draws for the same (seed, element)
