@@ -385,8 +385,9 @@ def gat_backward_recompute(csr, csr_t, Q, K, V, G, Y, bias, act, stats, num_head
         _ffi.call("tfgk_gat_bwd_dst_f32", _p(csr.rowptr), _p(csr.col), _p(Q), _row_major_2d(Q, "Q"), _p(K),
                   _row_major_2d(K, "K"), _p(V), _row_major_2d(V, "V"), _p(GS), A + 32, N, H, dqk, float(scale), _p(dQ),
                   _row_major_2d(dQ, "dQ"), _stream(Q))
+        # the transposed pass walks the SOURCE rows (set2set: nodes, while the forward rows are graphs)
         _ffi.call("tfgk_gat_bwd_src_f32", _p(csr_t.rowptr), _p(csr_t.col), _p(Q), _row_major_2d(Q, "Q"), _p(K),
-                  _row_major_2d(K, "K"), _p(V), _row_major_2d(V, "V"), _p(GS), A + 32, N, H, dqk, float(scale), _p(dK),
+                  _row_major_2d(K, "K"), _p(V), _row_major_2d(V, "V"), _p(GS), A + 32, csr_t.n_rows, H, dqk, float(scale), _p(dK),
                   _row_major_2d(dK, "dK"), _p(dV), _row_major_2d(dV, "dV"), _stream(Q))
     except _ffi.TfgkError as err:
         if err.code != _ffi.ERR_UNSUPPORTED:

@@ -44,7 +44,9 @@ def main():
             step()
         torch.cuda.synchronize()
         trace = _ffi.CallTrace(timed=("tfgk_gat_fused_f32", "tfgk_spmm_f32", "tfgk_gemm_f32", "tfgk_spmm_heads_f32",
-                                      "tfgk_gat_softmax_bwd_f32", "tfgk_dropout_f32"))
+                                      "tfgk_gat_softmax_bwd_f32", "tfgk_dropout_f32", "tfgk_gat_fused_stats_f32",
+                                      "tfgk_gat_bwd_prepare_f32", "tfgk_gat_bwd_dst_f32", "tfgk_gat_bwd_src_f32",
+                                      "tfgk_gemm_proj_f32", "tfgk_colsum_f32"))
         _ffi.set_trace(trace)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         ev[0].record()
