@@ -65,6 +65,7 @@ SIGNATURES = {
     "tfgk_peer_open": [_ptr, ctypes.POINTER(_ptr)],
     "tfgk_peer_close": [_ptr],
     "tfgk_peer_barrier": [_ptr, _i32, _i32, _u32, _i32, _ptr],
+    "tfgk_peer_pull": [_ptr, _ptr, _i64, _i32, _ptr],
     "tfgk_colsum_workspace_bytes": [_i64, _i32, ctypes.POINTER(_size)],
     "tfgk_colsum_f32": [_ptr, _i64, _i64, _i32, _ptr, _ptr, _size, _ptr],
     "tfgk_l2_normalize_f32": [_ptr, _i64, _i32, _i32, _ptr, _i64, _ptr],

@@ -30,9 +30,40 @@ __global__ void peer_barrier_kernel(const FlagTable tab, int rank, int world, ui
     }
 }
 
+// Pull a contiguous block of rows out of another rank's published buffer: every lane moves 16 bytes per load, a warp 512
+// contiguous bytes, eight loads in flight per thread - NVLink wants large contiguous requests and ~2 MB in flight per GPU
+// (latency ~2 us).  A handful of CTAs is enough, so the kernel runs next to the projection GEMM that consumes the previous block.
+__global__ void __launch_bounds__(256) peer_pull_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, int64_t n_vec) {
+    constexpr int kUnroll = 8;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (kUnroll - 1) * stride < n_vec; i += kUnroll * stride) {
+        uint4 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) v[u] = src[i + u * stride];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) dst[i + u * stride] = v[u];
+    }
+    for (; i < n_vec; i += stride) dst[i] = src[i];
+}
+
 }  // namespace tfgk
 
 using namespace tfgk;
+
+extern "C" int tfgk_peer_pull(const void *src, void *dst, int64_t bytes, int32_t max_ctas, void *stream) {
+    TFGK_CHECK_ARG(bytes >= 0, "peer_pull: negative size");
+    if (bytes == 0) return TFGK_OK;
+    TFGK_CHECK_ARG(src != nullptr && dst != nullptr && bytes % 16 == 0 && aligned16(src) && aligned16(dst),
+                   "peer_pull: buffers must be 16-byte aligned and a multiple of 16 bytes");
+    const int64_t n_vec = bytes / 16;
+    int64_t blocks = ceil_div64(n_vec, 256 * 8);
+    const int cap = max_ctas > 0 ? max_ctas : 64;
+    if (blocks > cap) blocks = cap;
+    peer_pull_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(static_cast<const uint4 *>(src), static_cast<uint4 *>(dst), n_vec);
+    TFGK_LAUNCH_CHECK();
+    return TFGK_OK;
+}
 
 extern "C" int tfgk_peer_alloc(size_t bytes, void **ptr) {
     TFGK_CHECK_ARG(ptr != nullptr && bytes > 0, "peer_alloc: bad argument");

@@ -68,6 +68,8 @@ class PartitionedGraph(object):
         self.exchange = exchange or os.environ.get("TFGK_DIST_EXCHANGE") or (
             "p2p" if local_edge_index.is_cuda and partition.world_size > 1 else "collective")
         self._row_exchanges = {}
+        self._pull_stream = None
+        self.pull_ctas = int(os.environ.get("TFGK_DIST_PULL_CTAS", "32"))      # CTAs of the pull kernel next to the GEMM
         self.nvlink_bytes = 0                       # bytes pulled from / received from peers so far (accounting)
 
     @classmethod
@@ -78,7 +80,7 @@ class PartitionedGraph(object):
         edge_index = ops.as_device(edge_index, torch.int32)
         exchange = exchange or os.environ.get("TFGK_DIST_EXCHANGE") or (
             "p2p" if edge_index.is_cuda and world_size > 1 else "collective")
-        part = RowPartition(num_nodes, world_size, rank, align=ROW_ALIGN if exchange == "p2p" else 1)
+        part = RowPartition(num_nodes, world_size, rank, align=ROW_ALIGN if exchange.startswith("p2p") else 1)
         row = edge_index[0]
         mask = (row >= part.lo) & (row < part.hi)
         local = torch.stack([row[mask] - part.lo, edge_index[1][mask]]).contiguous()
@@ -177,8 +179,10 @@ class PartitionedGraph(object):
         p = self.part
         dev = x_local.device
         widths = [sum(int(w.shape[1]) for w, _, _ in g) for g in groups]
-        fused_ok = x_local.shape[1] % 4 == 0 and x_local.shape[1] <= 512 and x_local.is_cuda      # tfgk_gemm_proj_f32 limits
-        if p.world_size == 1 or self.exchange != "p2p" or not fused_ok \
+        fused_ok = x_local.is_cuda and x_local.shape[1] % 4 == 0 and sum(widths) % 4 == 0        # 16-byte rows for the pulls
+        if self.exchange == "p2p_fused":
+            fused_ok = fused_ok and x_local.shape[1] <= 512                                         # tfgk_gemm_proj_f32 limit
+        if p.world_size == 1 or self.exchange not in ("p2p", "p2p_fused") or not fused_ok \
                 or self._row_exchange(x_local.shape[1], dev) is None:
             send = torch.empty((p.block, sum(widths)), dtype=torch.float32, device=dev)
             if p.n_local < p.block:
@@ -192,15 +196,79 @@ class PartitionedGraph(object):
                 outs.append(full[:, c0:c0 + wd])
                 c0 += wd
             return outs
-        ex = self._row_exchange(x_local.shape[1], dev)
-        slot = ex.publish(x_local)
-        outs = [torch.empty((p.padded_nodes, wd), dtype=torch.float32, device=dev) for wd in widths]
-        pieces = _pieces(groups, outs)
-        first = (p.rank + 1) % p.world_size
-        for i in range(0, len(pieces), 4):
-            ops.gemm_proj(ex.local_slot(slot), pieces[i:i + 4], a_parts=ex.slot_ptrs(slot), part_rows=p.block,
-                          first_part=first, num_rows=p.num_nodes)
+        if self.exchange == "p2p_fused":
+            # measured alternative: the GEMM's producers read the owners' rows in place (tfgk_gemm_proj_f32 a_parts).  Peer
+            # reads bypass the local L2, so every column block re-reads the remote tile, in 64-byte pieces: 54-160 GB/s.
+            ex = self._row_exchange(x_local.shape[1], dev)
+            slot = ex.publish(x_local)
+            outs = [torch.empty((p.padded_nodes, wd), dtype=torch.float32, device=dev) for wd in widths]
+            pieces = _pieces(groups, outs)
+            first = (p.rank + 1) % p.world_size
+            for i in range(0, len(pieces), 4):
+                ops.gemm_proj(ex.local_slot(slot), pieces[i:i + 4], a_parts=ex.slot_ptrs(slot), part_rows=p.block,
+                              first_part=first, num_rows=p.num_nodes)
+                self.nvlink_bytes += (p.num_nodes - p.n_local) * x_local.shape[1] * 4
+            return outs
+        main = torch.cuda.current_stream(dev)
+        if self._pull_stream is None:
+            self._pull_stream = torch.cuda.Stream(dev)
+        side = self._pull_stream
+        order = [(p.rank + k) % p.world_size for k in range(1, p.world_size)]       # every rank pulls from a different peer
+        bounds = lambda r: (min(r * p.block, p.num_nodes), min((r + 1) * p.block, p.num_nodes))      # noqa: E731
+        if x_local.shape[1] < sum(widths):
+            # (1) the input is narrower than what is aggregated: publish x, pull the peers' blocks over NVLink into a local
+            # [N, F] table on a side stream, and project every block as soon as it has landed - the pull of block j+1
+            # travels while the tensor core works on block j; no collective, no halo of projected rows
+            ex = self._row_exchange(x_local.shape[1], dev)
+            slot = ex.publish(x_local)
+            outs = [torch.empty((p.padded_nodes, wd), dtype=torch.float32, device=dev) for wd in widths]
+            x_full = torch.empty((p.padded_nodes, x_local.shape[1]), dtype=torch.float32, device=dev)
+            side.wait_stream(main)
+            events = []
+            with torch.cuda.stream(side):
+                for r in order:
+                    lo, hi = bounds(r)
+                    ex.pull(r, slot, hi - lo, x_full[lo:hi], max_ctas=self.pull_ctas)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    events.append(ev)
+            x_full.record_stream(side)
+
+            def project(rows, lo, hi):
+                if hi <= lo:
+                    return
+                pieces = _pieces(groups, [o[lo:hi] for o in outs])
+                for i in range(0, len(pieces), 4):
+                    ops.gemm_proj(rows, pieces[i:i + 4])
+            project(x_local, p.lo, p.hi)
+            for r, ev in zip(order, events):
+                main.wait_event(ev)
+                lo, hi = bounds(r)
+                project(x_full[lo:hi], lo, hi)
             self.nvlink_bytes += (p.num_nodes - p.n_local) * x_local.shape[1] * 4
+            return outs
+        # (2) the input is at least as wide as the projections: project the local rows straight into the published slot and
+        # pull the peers' projected rows (no replicated GEMM)
+        total = sum(widths)
+        ex = self._row_exchange(total, dev)
+        slot = ex.next_slot()
+        mine = ex.local_slot(slot)
+        _project_into(x_local, groups, mine, p.n_local)
+        ex.commit(slot)
+        full = torch.empty((p.padded_nodes, total), dtype=torch.float32, device=dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for r in order:
+                lo, hi = bounds(r)
+                ex.pull(r, slot, hi - lo, full[lo:hi], max_ctas=0)
+        full.record_stream(side)
+        full[p.lo:p.hi].copy_(mine[:p.n_local])
+        main.wait_stream(side)
+        self.nvlink_bytes += (p.num_nodes - p.n_local) * total * 4
+        outs, c0 = [], 0
+        for wd in widths:
+            outs.append(full[:, c0:c0 + wd])
+            c0 += wd
         return outs
 
     def share(self, x_local, layers):
@@ -422,7 +490,7 @@ def bench_papers(args, rank, world, device, metric, config):
     n_total = int(cfg["nodes"] * args.scale) * world // 8 if world != 8 else int(cfg["nodes"] * args.scale)
     e_total = int(cfg["edges"] * args.scale) * world // 8 if world != 8 else int(cfg["edges"] * args.scale)
     exchange = os.environ.get("TFGK_DIST_EXCHANGE") or ("p2p" if world > 1 else "collective")
-    part = RowPartition(n_total, world, rank, align=ROW_ALIGN if exchange == "p2p" else 1)
+    part = RowPartition(n_total, world, rank, align=ROW_ALIGN if exchange.startswith("p2p") else 1)
     e_local = e_total // world
     gen = torch.Generator(device=device)
     gen.manual_seed(1000 + rank)
@@ -540,7 +608,7 @@ def bench_partitioned(args, rank, world, device, metric, config):
     p = pg.part
 
     def features(r):
-        part = RowPartition(n, world, r, align=ROW_ALIGN if pg.exchange == "p2p" else 1)
+        part = RowPartition(n, world, r, align=ROW_ALIGN if pg.exchange.startswith("p2p") else 1)
         gen = torch.Generator(device="cpu")
         gen.manual_seed(100 + r)
         return torch.randn((part.n_local, B.FEATURES), generator=gen, dtype=torch.float32)
@@ -563,10 +631,10 @@ def bench_partitioned(args, rank, world, device, metric, config):
     del edge_index
     mode = pg.exchange
     identical = None
-    if mode == "p2p":
+    if mode.startswith("p2p"):
         pg.exchange = "collective"
         a2, b2 = step(x)
-        pg.exchange = "p2p"
+        pg.exchange = mode
         identical = bool(torch.equal(a, a2) and torch.equal(b, b2))
         del a2, b2
     check = torch.tensor([err, 0.0 if identical in (None, True) else 1.0], dtype=torch.float64, device=device)
@@ -635,9 +703,10 @@ def bench_partitioned(args, rank, world, device, metric, config):
                            "tolerance": "allclose(rtol=1e-4, atol=1e-4*max|ref|)",
                            "all_rows_bit_identical_to_collective_path": identical},
                 "exchange": {"mode": mode,
-                             "what": ("x rows pulled over NVLink peer mappings inside the projection GEMM (fused all-gather -> "
-                                      "GEMM, no collective)") if mode == "p2p" else
-                                     "all_gather_into_tensor of the projected rows (NCCL)",
+                             "what": {"p2p": "x rows pulled block by block over NVLink peer mappings (tfgk_peer_pull on a side stream) "
+                                             "while tfgk_gemm_proj_f32 projects the blocks that have landed; no collective",
+                                      "p2p_fused": "x rows read over NVLink inside the projection GEMM (a_parts)",
+                                      }.get(mode, "all_gather_into_tensor of the projected rows (NCCL)"),
                              "nvlink_bytes_in_per_rank_per_step": nvlink_per_step,
                              "hbm_algorithmic_bytes_per_rank_per_step": hbm_step}}
         B.emit(line)

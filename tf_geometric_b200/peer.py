@@ -100,6 +100,20 @@ class RowExchange(object):
         self._published = None           # (tensor id, version, data_ptr, slot)
         self.nvlink_bytes = 0            # bytes this rank pulled from peers (accounting for bench.py)
 
+    def next_slot(self):
+        """Slot the caller may fill for the next publication (it last held publication count-1, which every rank has
+        finished reading: see the class comment)."""
+        self.count += 1
+        self._published = None
+        return self.count & 1
+
+    def commit(self, slot):
+        """Device-side barrier on the current stream: after it every rank's slot of this publication is complete and may be
+        read, and every rank is done with the previous publication."""
+        main = torch.cuda.current_stream(self.buf.device)
+        _ffi.call("tfgk_peer_barrier", self._flag_table, self.rank, self.world, self.count, self.timeout_ms,
+                  ctypes.c_void_p(main.cuda_stream))
+
     def publish(self, x_local):
         """Make `x_local` ([n_local <= block, width], float32, CUDA) readable by every rank; returns the slot index.
         The same tensor (identity and version) is published once, however many layers ask for it."""
@@ -107,14 +121,22 @@ class RowExchange(object):
         if self._published is not None and self._published[:3] == key and self._published[4]() is x_local:
             return self._published[3]
         import weakref
-        main = torch.cuda.current_stream(self.buf.device)
-        self.count += 1
-        slot = self.count & 1
+        slot = self.next_slot()
         self._slots[slot][:x_local.shape[0]].copy_(x_local)
-        _ffi.call("tfgk_peer_barrier", self._flag_table, self.rank, self.world, self.count, self.timeout_ms,
-                  ctypes.c_void_p(main.cuda_stream))
+        self.commit(slot)
         self._published = key + (slot, weakref.ref(x_local))
         return slot
+
+    def pull(self, rank, slot, n_rows, dst, max_ctas=0):
+        """Copy the first n_rows rows of `rank`'s slot into `dst` ([n_rows, width], local, contiguous) on the current stream
+        (tfgk_peer_pull: wide contiguous loads over the NVLink peer mapping)."""
+        if n_rows <= 0:
+            return
+        nbytes = int(n_rows) * self.width * 4
+        src = int(self.buf.ptrs[rank]) + self.FLAG_BYTES + slot * self.slot_bytes
+        _ffi.call("tfgk_peer_pull", ctypes.c_void_p(src), ctypes.c_void_p(dst.data_ptr()), nbytes, int(max_ctas),
+                  ctypes.c_void_p(torch.cuda.current_stream(self.buf.device).cuda_stream))
+        self.nvlink_bytes += nbytes
 
     def slot_ptrs(self, slot):
         off = self.FLAG_BYTES + slot * self.slot_bytes
