@@ -65,6 +65,91 @@ struct Plan {
     }
 };
 
+// ---- epilogue shared by both kernels: TMEM -> registers -> per-warp staging tile -> full row segments per store ----------
+__device__ __forceinline__ int tile_index(const Params &p, int group, int it) {
+    int tl = group + it * p.n_groups + p.first_tile;
+    return tl >= p.tiles_m ? tl - p.tiles_m : tl;
+}
+
+__device__ __forceinline__ void epilogue_loop(const Params &p, int cb, int group, int un, int ncols, uint32_t tmem_base,
+                                              uint8_t *stage_base, const float *s_bias, uint64_t *acc_full, uint64_t *acc_empty,
+                                              int my_tiles, int warp, int lane) {
+    auto tile_of = [&](int it) { return tile_index(p, group, it); };
+        const int ew = warp - kProducerWarps;                 // 0..7
+        const int q = warp & 3, half = ew >> 2;               // TMEM lane quarter (= warp % 4) and column half of this warp
+        uint8_t *stg = stage_base + ew * kStageBytes;
+        const uint32_t stg_addr = smem_u32(stg);
+        float *__restrict__ Cb = p.C[cb];
+        const int64_t ldc = p.ldc[cb];
+        const int act = p.act[cb];
+        const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cb) & 15) == 0);
+        const int seg_row = lane >> 2, seg_chunk = lane & 3;  // store phase: 8 rows x 64 bytes per instruction
+        const int n_pass = un / kPassCols;
+        const int pass0 = half == 0 ? 0 : (n_pass + 1) / 2, pass1 = half == 0 ? (n_pass + 1) / 2 : n_pass;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int buf = it & 1;
+            const int tile = tile_of(it);
+            mbar_wait(&acc_full[buf], (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            const int64_t row0 = (int64_t)tile * BM + q * 32;
+            if (pass0 >= pass1) {                             // nothing to read (a single pass belongs to the other half)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            }
+            for (int ps = pass0; ps < pass1; ++ps) {
+                const int c0 = ps * kPassCols;
+                uint32_t r[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kUN + c0);
+                if (p.dbg & 16) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) r[j] = 0;
+                } else
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (ps + 1 == pass1) {                        // this warp's share is drained: one arrive per warp frees the buffer
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                }
+                if (p.dbg & 32) continue;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float v0 = apply_act(__uint_as_float(r[j]) + s_bias[c0 + j], act);
+                    const float v1 = apply_act(__uint_as_float(r[j + 1]) + s_bias[c0 + j + 1], act);
+                    const float v2 = apply_act(__uint_as_float(r[j + 2]) + s_bias[c0 + j + 2], act);
+                    const float v3 = apply_act(__uint_as_float(r[j + 3]) + s_bias[c0 + j + 3], act);
+                    st_shared_v4(stg_addr + (uint32_t)lane * kStageRowBytes + (uint32_t)j * 4u, v0, v1, v2, v3);
+                }
+                __syncwarp();
+                const int col = c0 + seg_chunk * 4;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int rl = j * 8 + seg_row;
+                    const int64_t row = row0 + rl;
+                    const float4 v = *reinterpret_cast<const float4 *>(stg + rl * kStageRowBytes + seg_chunk * 16);
+                    if (row < p.M && !(p.dbg & 4)) {
+                        float *dst = Cb + row * ldc + col;
+                        if (vec_ok && col + 4 <= ncols) {
+                            *reinterpret_cast<float4 *>(dst) = v;
+                        } else {
+                            if (col < ncols) dst[0] = v.x;
+                            if (col + 1 < ncols) dst[1] = v.y;
+                            if (col + 2 < ncols) dst[2] = v.z;
+                            if (col + 3 < ncols) dst[3] = v.w;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+}
+
 template <int STAGES>
 __global__ void __launch_bounds__(kThreadsProj, 1) gemm_proj_kernel(const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -229,85 +314,238 @@ __global__ void __launch_bounds__(kThreadsProj, 1) gemm_proj_kernel(const Params
             }
         }
     } else {
-        // ===================== epilogue: TMEM -> registers -> staging tile -> 128-byte row segments =====================
-        const int ew = warp - kProducerWarps;                 // 0..7
-        const int q = warp & 3, half = ew >> 2;               // TMEM lane quarter (= warp % 4) and column half of this warp
-        uint8_t *stg = stage_base + ew * kStageBytes;
-        const uint32_t stg_addr = smem_u32(stg);
-        float *__restrict__ Cb = p.C[cb];
-        const int64_t ldc = p.ldc[cb];
-        const int act = p.act[cb];
-        const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cb) & 15) == 0);
-        const int seg_row = lane >> 2, seg_chunk = lane & 3;  // store phase: 8 rows x 64 bytes per instruction
-        const int n_pass = un / kPassCols;
-        const int pass0 = half == 0 ? 0 : (n_pass + 1) / 2, pass1 = half == 0 ? (n_pass + 1) / 2 : n_pass;
-        for (int it = 0; it < my_tiles; ++it) {
-            const int buf = it & 1;
-            const int tile = tile_of(it);
-            mbar_wait(&acc_full[buf], (uint32_t)((it >> 1) & 1));
-            tc_fence_after();
-            const int64_t row0 = (int64_t)tile * BM + q * 32;
-            if (pass0 >= pass1) {                             // nothing to read (a single pass belongs to the other half)
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[buf]);
-            }
-            for (int ps = pass0; ps < pass1; ++ps) {
-                const int c0 = ps * kPassCols;
-                uint32_t r[16];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kUN + c0);
-                if (p.dbg & 16) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) r[j] = 0;
-                } else
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (ps + 1 == pass1) {                        // this warp's share is drained: one arrive per warp frees the buffer
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&acc_empty[buf]);
-                }
-                if (p.dbg & 32) continue;
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    const float v0 = apply_act(__uint_as_float(r[j]) + s_bias[c0 + j], act);
-                    const float v1 = apply_act(__uint_as_float(r[j + 1]) + s_bias[c0 + j + 1], act);
-                    const float v2 = apply_act(__uint_as_float(r[j + 2]) + s_bias[c0 + j + 2], act);
-                    const float v3 = apply_act(__uint_as_float(r[j + 3]) + s_bias[c0 + j + 3], act);
-                    st_shared_v4(stg_addr + (uint32_t)lane * kStageRowBytes + (uint32_t)j * 4u, v0, v1, v2, v3);
-                }
-                __syncwarp();
-                const int col = c0 + seg_chunk * 4;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int rl = j * 8 + seg_row;
-                    const int64_t row = row0 + rl;
-                    const float4 v = *reinterpret_cast<const float4 *>(stg + rl * kStageRowBytes + seg_chunk * 16);
-                    if (row < p.M && !(p.dbg & 4)) {
-                        float *dst = Cb + row * ldc + col;
-                        if (vec_ok && col + 4 <= ncols) {
-                            *reinterpret_cast<float4 *>(dst) = v;
-                        } else {
-                            if (col < ncols) dst[0] = v.x;
-                            if (col + 1 < ncols) dst[1] = v.y;
-                            if (col + 2 < ncols) dst[2] = v.z;
-                            if (col + 3 < ncols) dst[3] = v.w;
-                        }
-                    }
-                }
-                __syncwarp();
-            }
-        }
+        epilogue_loop(p, cb, group, un, ncols, tmem_base, stage_base, s_bias, acc_full, acc_empty, my_tiles, warp, lane);
     }
     __syncthreads();
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemColsProj) : "memory");
     }
+}
+
+// ---- variant with the A operands in tensor memory ("TS" form of tcgen05.mma) -----------------------------------------------
+// Measured on the kernel above (TFGK_PROJ_DEBUG switches, profiles/r2_notes.md): a ring stage makes one trip
+// free -> load -> convert -> MMA -> commit -> free in ~3000 cycles whatever its size, and next to the resident W the ring
+// holds raw + lo tiles for only 96 K-columns - less than one 128 x 104 row tile - so a row tile costs about one full trip
+// (4.3 us) where its 39 MMAs need 1.3 us.  Here the ring in shared memory holds RAW k-blocks only (16 KB per 32 columns,
+// up to six stages) and the split operands live in TENSOR MEMORY: the converter warps read their own row of a landed
+// k-block, compute hi = trunc_tf32(a) and lo = a - hi in registers and store both with tcgen05.st into a 4-slot ring
+// (2 x 32 columns per slot) next to the two accumulators: 256 + 256 = all 512 TMEM columns.  The MMAs then take A from
+// tensor memory and only W from shared memory, which also halves their shared-memory traffic.  Twice the K-columns in
+// flight in shared memory plus four k-blocks in tensor memory cover the trip latency.
+constexpr int kTsSlots = 4;
+constexpr int kTsTmemCols = 512;
+constexpr int kTsBarrierBytes = 256;
+constexpr int kTsAcol0 = 2 * kUN;                 // first TMEM column of the A ring
+
+struct PlanTS {
+    uint32_t kpad8, b_bytes, raw_bytes, stages, total;
+    __host__ __device__ explicit PlanTS(int K) {
+        kpad8 = (uint32_t)((K + 7) / 8) * 8;
+        b_bytes = (uint32_t)kUN * kpad8 * 4u;
+        raw_bytes = BM * BK * 4u;
+        const uint32_t fixed = 2u * b_bytes + kEpilogueWarps * kStageBytes + kTsBarrierBytes + kUN * 4u;
+        const uint32_t budget = 227u * 1024u;
+        stages = 0;
+        for (uint32_t st = 6; st >= 2; --st)
+            if (fixed + st * raw_bytes <= budget) { stages = st; break; }
+        total = fixed + stages * raw_bytes;
+    }
+};
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+#define TFGK_ST32(taddr, v)                                                                                                    \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                              \
+                 "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"                                                   \
+                 "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"                                          \
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),         \
+                   "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),               \
+                   "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),             \
+                   "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory")
+
+template <int STAGES>
+__global__ void __launch_bounds__(kThreadsProj, 1) gemm_proj_ts_kernel(const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const PlanTS L(p.K);
+    uint8_t *b_hi_ptr = smem, *b_lo_ptr = smem + L.b_bytes;
+    uint8_t *raw_ring = smem + 2 * L.b_bytes;
+    uint8_t *stage_base = raw_ring + STAGES * L.raw_bytes;
+    uint64_t *landed = reinterpret_cast<uint64_t *>(stage_base + kEpilogueWarps * kStageBytes);
+    uint64_t *smem_free = landed + STAGES, *full_t = smem_free + STAGES, *tmem_free = full_t + kTsSlots;
+    uint64_t *acc_full = tmem_free + kTsSlots, *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    float *s_bias = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(landed) + kTsBarrierBytes);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int cb = (int)blockIdx.x % p.nb, group = (int)blockIdx.x / p.nb;
+    const int ncols = p.ncols[cb];
+    const int un = ((ncols + 15) / 16) * 16;
+    const float *__restrict__ Bm = p.B[cb];
+    const int64_t ldb = p.ldb[cb];
+    const bool tb = p.transb[cb] != 0;
+
+    for (int i = t; i < kUN; i += kThreadsProj) s_bias[i] = (p.bias[cb] != nullptr && i < ncols) ? __ldg(p.bias[cb] + i) : 0.0f;
+    if (t == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&landed[i], kLoaderWarps * 32); mbar_init(&smem_free[i], kProducerWarps); }
+        for (int i = 0; i < kTsSlots; ++i) { mbar_init(&full_t[i], kProducerWarps); mbar_init(&tmem_free[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpilogueWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTsTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {   // W_b: transpose + RNA split into the K-major core-matrix layout, once per CTA
+        const int kchunks = (int)L.kpad8 / 4;
+        const int total = un * kchunks;
+        const uint32_t bh = smem_u32(b_hi_ptr), bl = smem_u32(b_lo_ptr);
+        for (int c = t; c < total; c += kThreadsProj) {
+            const int n8 = c & 7, kc = (c >> 3) % kchunks, ng = (c >> 3) / kchunks;
+            const int n = ng * 8 + n8, k = kc * 4;
+            float w[4] = {0.f, 0.f, 0.f, 0.f}, h[4], l[4];
+            if (n < ncols) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (k + i < p.K) w[i] = __ldg(tb ? Bm + (int64_t)n * ldb + (k + i) : Bm + (int64_t)(k + i) * ldb + n);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_tf32(w[i], h[i], l[i]);
+            st_shared_v4(bh + c * 16, h[0], h[1], h[2], h[3]);
+            st_shared_v4(bl + c * 16, l[0], l[1], l[2], l[3]);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nkb = (int)(L.kpad8 + BK - 1) / BK;
+    const int last_steps = ((int)L.kpad8 - (nkb - 1) * BK) / UMMA_K;
+    const int my_tiles = group < p.tiles_m ? (p.tiles_m - 1 - group) / p.n_groups + 1 : 0;
+    const int total_kb = my_tiles * nkb;
+
+    if (warp >= kLoaderWarp0) {
+        // ===================== loaders: raw k-blocks, row-major with the 16-byte chunks XOR-swizzled by row =====================
+        const int tl = t - kLoaderWarp0 * 32;                                // 0..63
+        const uint32_t ring_addr = smem_u32(raw_ring);
+        const int kc = tl & 7, rsub = tl >> 3;                               // a warp covers 4 rows x 128 contiguous bytes
+        constexpr int kPrefetchTiles = 4;
+        const bool can_prefetch = (cb == 0) && (tl == 0) && p.lda <= 2 * (int64_t)p.K;
+        auto prefetch_tile = [&](int it) {
+            if (!can_prefetch || it >= my_tiles) return;
+            const int64_t m0 = (int64_t)tile_index(p, group, it) * BM;
+            const int part = p.n_parts > 1 ? (int)(m0 / p.part_rows) : 0;
+            if (p.n_parts > 1 && part != p.local_part) return;
+            const int64_t rows = min((int64_t)BM, (int64_t)p.M - m0);
+            const float *src = p.A[part] + (m0 - (int64_t)part * p.part_rows) * p.lda;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)(rows * p.lda * 4)) : "memory");
+        };
+        for (int i = 0; i < kPrefetchTiles; ++i) prefetch_tile(i);
+        for (int G = 0; G < total_kb; ++G) {
+            const int stage = G % STAGES;
+            mbar_wait(&smem_free[stage], (uint32_t)(((G / STAGES) & 1) ^ 1));
+            const int tile = tile_index(p, group, G / nkb), kb = G % nkb;
+            if (kb == 0) prefetch_tile(G / nkb + kPrefetchTiles);
+            const int k = kb * BK + kc * 4;
+            if (k < (int)L.kpad8 && !(p.dbg & 8)) {
+                const int64_t m0 = (int64_t)tile * BM;
+                const int part = p.n_parts > 1 ? (int)(m0 / p.part_rows) : 0;
+                const float *base = p.A[part] + (m0 - (int64_t)part * p.part_rows) * p.lda + k;
+                const uint32_t kbytes = k < p.K ? (uint32_t)min(4, p.K - k) * 4u : 0u;
+                const uint32_t dst0 = ring_addr + stage * L.raw_bytes;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int rl = i * 8 + rsub;
+                    const bool ok = m0 + rl < p.M;
+                    cp_async16_zfill(dst0 + (uint32_t)rl * 128u + (uint32_t)((kc ^ (rl & 7)) * 16),
+                                     ok ? base + (int64_t)rl * p.lda : p.A[0], ok ? kbytes : 0u);
+                }
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&landed[stage])) : "memory");
+        }
+    } else if (warp < kProducerWarps) {
+        // ===================== converters: own row of a landed k-block -> (hi, lo) -> tensor memory =====================
+        const uint32_t lane_field = (uint32_t)(warp * 32) << 16;             // this warp's TMEM lane quarter
+        for (int G = 0; G < total_kb; ++G) {
+            const int stage = G % STAGES, slot = G % kTsSlots, kb = G % nkb;
+            mbar_wait(&landed[stage], (uint32_t)((G / STAGES) & 1));
+            mbar_wait(&tmem_free[slot], (uint32_t)(((G / kTsSlots) & 1) ^ 1));      // MMAs of k-block G - 4 retired
+            tc_fence_after();
+            uint32_t hi[32], lo[32];
+            const uint8_t *row = raw_ring + stage * L.raw_bytes + t * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (kb * BK + c * 4 < (int)L.kpad8 && !(p.dbg & 1)) v = *reinterpret_cast<const float4 *>(row + ((c ^ (t & 7)) * 16));
+                const float a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t h = __float_as_uint(a[e]) & 0xFFFFE000u;
+                    hi[c * 4 + e] = h;
+                    lo[c * 4 + e] = __float_as_uint(a[e] - __uint_as_float(h));
+                }
+            }
+            const uint32_t taddr = tmem_base + lane_field + (uint32_t)(kTsAcol0 + slot * 64);
+            TFGK_ST32(taddr, hi);
+            TFGK_ST32(taddr + 32u, lo);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&full_t[slot]); mbar_arrive(&smem_free[stage]); }
+        }
+    } else if (warp == kProducerWarps + kEpilogueWarps) {
+        // ===================== MMA issuer: A from tensor memory, W from shared memory =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(un);
+            const uint32_t sbo_b = (L.kpad8 / 4) * 128u;
+            for (int G = 0; G < total_kb; ++G) {
+                const int slot = G % kTsSlots, it = G / nkb, kb = G % nkb, buf = it & 1;
+                if (kb == 0) mbar_wait(&acc_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
+                mbar_wait(&full_t[slot], (uint32_t)((G / kTsSlots) & 1));
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kUN);
+                const uint32_t a_hi = tmem_base + (uint32_t)(kTsAcol0 + slot * 64), a_lo = a_hi + 32u;
+                const uint32_t b_hi = smem_u32(b_hi_ptr) + (uint32_t)kb * (BK / 4) * 128u, b_lo = b_hi + L.b_bytes;
+                const int steps = kb == nkb - 1 ? last_steps : BK / UMMA_K;
+                for (int j = 0; j < steps; ++j) {
+                    const uint32_t off = (uint32_t)j * 2u * 128u;
+                    const uint64_t dbh = make_desc_sbo(b_hi + off, sbo_b), dbl = make_desc_sbo(b_lo + off, sbo_b);
+                    const uint32_t ah = a_hi + (uint32_t)j * UMMA_K, al = a_lo + (uint32_t)j * UMMA_K;
+                    if (p.dbg & 2) { umma_tf32_ts(d_tmem, ah, dbh, idesc, (kb | j) != 0); continue; }
+                    umma_tf32_ts(d_tmem, al, dbh, idesc, (kb | j) != 0);
+                    umma_tf32_ts(d_tmem, ah, dbl, idesc, 1u);
+                    umma_tf32_ts(d_tmem, ah, dbh, idesc, 1u);
+                }
+                umma_commit(&tmem_free[slot]);
+                if (kb == nkb - 1) umma_commit(&acc_full[buf]);
+            }
+        }
+    } else {
+        epilogue_loop(p, cb, group, un, ncols, tmem_base, stage_base, s_bias, acc_full, acc_empty, my_tiles, warp, lane);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTsTmemCols) : "memory");
+    }
+}
+
+template <int STAGES>
+static int launch_ts(const Params &p, int grid, uint32_t smem_bytes, cudaStream_t st) {
+    static int configured[16] = {0};
+    int dev = 0;
+    TFGK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16 || configured[dev] < (int)smem_bytes) {
+        TFGK_CUDA(cudaFuncSetAttribute(gemm_proj_ts_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        if (dev >= 0 && dev < 16) configured[dev] = (int)smem_bytes;
+    }
+    gemm_proj_ts_kernel<STAGES><<<grid, kThreadsProj, smem_bytes, st>>>(p);
+    TFGK_LAUNCH_CHECK();
+    return TFGK_OK;
 }
 
 template <int STAGES>
@@ -380,6 +618,19 @@ extern "C" int tfgk_gemm_proj_f32(const float *const *A_parts, int32_t n_parts, 
     p.n_groups = n_groups;
     const int grid = n_groups * n_blocks;
     cudaStream_t st = as_stream(stream);
+    {   // A operands through tensor memory (TFGK_PROJ_IMPL=ss selects the all-shared-memory kernel)
+        const char *impl = getenv("TFGK_PROJ_IMPL");
+        const proj::PlanTS LT(K);
+        if (impl != nullptr && impl[0] == 't' && LT.stages >= 2) {
+            switch (LT.stages) {
+                case 6: return proj::launch_ts<6>(p, grid, LT.total, st);
+                case 5: return proj::launch_ts<5>(p, grid, LT.total, st);
+                case 4: return proj::launch_ts<4>(p, grid, LT.total, st);
+                case 3: return proj::launch_ts<3>(p, grid, LT.total, st);
+                default: return proj::launch_ts<2>(p, grid, LT.total, st);
+            }
+        }
+    }
     if (L.stages >= 4) return proj::launch<4>(p, grid, L.total, st);
     if (L.stages == 3) return proj::launch<3>(p, grid, L.total, st);
     return proj::launch<2>(p, grid, L.total, st);
