@@ -65,6 +65,12 @@ struct Plan {
     }
 };
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- epilogue shared by both kernels: TMEM -> registers -> per-warp staging tile -> full row segments per store ----------
 __device__ __forceinline__ int tile_index(const Params &p, int group, int it) {
     int tl = group + it * p.n_groups + p.first_tile;
@@ -287,31 +293,40 @@ __global__ void __launch_bounds__(kThreadsProj, 1) gemm_proj_kernel(const Params
             if (lane == 0) mbar_arrive(&full[stage]);
         }
     } else if (warp == kProducerWarps + kEpilogueWarps) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(un);
-            const uint32_t sbo_b = (L.kpad8 / 4) * 128u;
-            for (int G = 0; G < total_kb; ++G) {
-                const int stage = G % STAGES, it = G / nkb, kb = G % nkb, buf = it & 1;
-                if (kb == 0) mbar_wait(&acc_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
-                mbar_wait(&full[stage], (uint32_t)((G / STAGES) & 1));
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kUN);
-                const uint32_t a_raw = smem_u32(a_ring + stage * L.a_stage_bytes), a_lo = a_raw + BM * BK * 4;
-                const uint32_t b_hi = smem_u32(b_hi_ptr) + (uint32_t)kb * (BK / 4) * 128u, b_lo = b_hi + L.b_bytes;
-                const int steps = kb == nkb - 1 ? last_steps : BK / UMMA_K;
-                for (int j = 0; j < steps; ++j) {
-                    const uint32_t off = (uint32_t)j * 2u * 128u;
-                    const uint64_t dah = make_desc_sbo(a_raw + off, 1024u), dal = make_desc_sbo(a_lo + off, 1024u);
-                    const uint64_t dbh = make_desc_sbo(b_hi + off, sbo_b), dbl = make_desc_sbo(b_lo + off, sbo_b);
-                    if (p.dbg & 2) { umma_tf32(d_tmem, dah, dbh, idesc, (kb | j) != 0); continue; }
-                    umma_tf32(d_tmem, dal, dbh, idesc, (kb | j) != 0);
-                    umma_tf32(d_tmem, dah, dbl, idesc, 1u);
-                    umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+        // ===================== MMA issuer (warp-uniform loop, one elected lane issues; see the TS kernel) =====================
+        const uint32_t idesc = make_idesc(un);
+        const uint32_t sbo_b = (L.kpad8 / 4) * 128u;
+        const uint64_t dbh0 = make_desc_sbo(smem_u32(b_hi_ptr), sbo_b), dbl0 = make_desc_sbo(smem_u32(b_lo_ptr), sbo_b);
+        const uint32_t a_ring0 = smem_u32(a_ring);
+        int stage = 0, kb = 0, it = 0;
+        uint32_t stage_phase = 0;
+        for (int G = 0; G < total_kb; ++G) {
+            const int buf = it & 1;
+            if (kb == 0) mbar_wait(&acc_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
+            mbar_wait(&full[stage], stage_phase);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kUN);
+            const uint32_t a_raw = a_ring0 + (uint32_t)stage * L.a_stage_bytes;
+            const uint64_t dah0 = make_desc_sbo(a_raw, 1024u), dal0 = make_desc_sbo(a_raw + BM * BK * 4, 1024u);
+            const uint64_t dbh = dbh0 + (uint64_t)(kb * 64), dbl = dbl0 + (uint64_t)(kb * 64);
+            const int steps = kb == nkb - 1 ? last_steps : BK / UMMA_K;
+            if (elect_one()) {
+#pragma unroll
+                for (int j = 0; j < BK / UMMA_K; ++j) {
+                    if (j < steps) {
+                        const uint64_t o = (uint64_t)(j * 16);
+                        if (p.dbg & 2) { umma_tf32(d_tmem, dah0 + o, dbh + o, idesc, (kb | j) != 0); continue; }
+                        umma_tf32(d_tmem, dal0 + o, dbh + o, idesc, (kb | j) != 0);
+                        umma_tf32(d_tmem, dah0 + o, dbl + o, idesc, 1u);
+                        umma_tf32(d_tmem, dah0 + o, dbh + o, idesc, 1u);
+                    }
                 }
                 umma_commit(&empty[stage]);
                 if (kb == nkb - 1) umma_commit(&acc_full[buf]);
             }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; stage_phase ^= 1u; }
+            if (++kb == nkb) { kb = 0; ++it; }
         }
     } else {
         epilogue_loop(p, cb, group, un, ncols, tmem_base, stage_base, s_bias, acc_full, acc_empty, my_tiles, warp, lane);
@@ -471,11 +486,19 @@ __global__ void __launch_bounds__(kThreadsProj, 1) gemm_proj_ts_kernel(const Par
     } else if (warp < kProducerWarps) {
         // ===================== converters: own row of a landed k-block -> (hi, lo) -> tensor memory =====================
         const uint32_t lane_field = (uint32_t)(warp * 32) << 16;             // this warp's TMEM lane quarter
+        // software pipelined: the tensor-memory stores of k-block G are issued, and only after the shared-memory reads and
+        // the split of k-block G+1 does the warp wait for them and publish G (tcgen05.wait::st latency off the critical path)
+        int prev_slot = -1, prev_stage = -1;
+        auto publish_prev = [&]() {
+            if (prev_slot < 0) return;
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&full_t[prev_slot]); mbar_arrive(&smem_free[prev_stage]); }
+        };
         for (int G = 0; G < total_kb; ++G) {
             const int stage = G % STAGES, slot = G % kTsSlots, kb = G % nkb;
             mbar_wait(&landed[stage], (uint32_t)((G / STAGES) & 1));
-            mbar_wait(&tmem_free[slot], (uint32_t)(((G / kTsSlots) & 1) ^ 1));      // MMAs of k-block G - 4 retired
-            tc_fence_after();
             uint32_t hi[32], lo[32];
             const uint8_t *row = raw_ring + stage * L.raw_bytes + t * 128;
 #pragma unroll
@@ -490,40 +513,55 @@ __global__ void __launch_bounds__(kThreadsProj, 1) gemm_proj_ts_kernel(const Par
                     lo[c * 4 + e] = __float_as_uint(a[e] - __uint_as_float(h));
                 }
             }
+            publish_prev();
+            mbar_wait(&tmem_free[slot], (uint32_t)(((G / kTsSlots) & 1) ^ 1));      // MMAs of k-block G - 4 retired
+            tc_fence_after();
             const uint32_t taddr = tmem_base + lane_field + (uint32_t)(kTsAcol0 + slot * 64);
             TFGK_ST32(taddr, hi);
             TFGK_ST32(taddr + 32u, lo);
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) { mbar_arrive(&full_t[slot]); mbar_arrive(&smem_free[stage]); }
+            prev_slot = slot; prev_stage = stage;
         }
+        publish_prev();
     } else if (warp == kProducerWarps + kEpilogueWarps) {
         // ===================== MMA issuer: A from tensor memory, W from shared memory =====================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(un);
-            const uint32_t sbo_b = (L.kpad8 / 4) * 128u;
-            for (int G = 0; G < total_kb; ++G) {
-                const int slot = G % kTsSlots, it = G / nkb, kb = G % nkb, buf = it & 1;
-                if (kb == 0) mbar_wait(&acc_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
-                mbar_wait(&full_t[slot], (uint32_t)((G / kTsSlots) & 1));
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kUN);
-                const uint32_t a_hi = tmem_base + (uint32_t)(kTsAcol0 + slot * 64), a_lo = a_hi + 32u;
-                const uint32_t b_hi = smem_u32(b_hi_ptr) + (uint32_t)kb * (BK / 4) * 128u, b_lo = b_hi + L.b_bytes;
-                const int steps = kb == nkb - 1 ? last_steps : BK / UMMA_K;
-                for (int j = 0; j < steps; ++j) {
-                    const uint32_t off = (uint32_t)j * 2u * 128u;
-                    const uint64_t dbh = make_desc_sbo(b_hi + off, sbo_b), dbl = make_desc_sbo(b_lo + off, sbo_b);
-                    const uint32_t ah = a_hi + (uint32_t)j * UMMA_K, al = a_lo + (uint32_t)j * UMMA_K;
-                    if (p.dbg & 2) { umma_tf32_ts(d_tmem, ah, dbh, idesc, (kb | j) != 0); continue; }
-                    umma_tf32_ts(d_tmem, al, dbh, idesc, (kb | j) != 0);
-                    umma_tf32_ts(d_tmem, ah, dbl, idesc, 1u);
-                    umma_tf32_ts(d_tmem, ah, dbh, idesc, 1u);
+        // The whole warp walks the loop with warp-uniform values and one elected lane issues: written as `if (lane == 0)`
+        // the compiler wrapped every tcgen05.mma in an ELECT / BRA.U.ANY sequence and rebuilt both descriptors with integer
+        // divisions per k-block - ~130 issue cycles per MMA against the 64 cycles the tensor core needs for it, which made
+        // this single thread the critical path of the kernel (profiles/r2_notes.md).  Counters are carried, the W descriptors
+        // advance by constants (the address field counts 16-byte units).
+        const uint32_t idesc = make_idesc(un);
+        const uint32_t sbo_b = (L.kpad8 / 4) * 128u;
+        const uint64_t dbh0 = make_desc_sbo(smem_u32(b_hi_ptr), sbo_b), dbl0 = make_desc_sbo(smem_u32(b_lo_ptr), sbo_b);
+        const uint32_t a_ring0 = tmem_base + (uint32_t)kTsAcol0;
+        int slot = 0, kb = 0, it = 0;
+        uint32_t slot_phase = 0;
+        for (int G = 0; G < total_kb; ++G) {
+            const int buf = it & 1;
+            if (kb == 0) mbar_wait(&acc_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
+            mbar_wait(&full_t[slot], slot_phase);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kUN);
+            const uint32_t a_hi = a_ring0 + (uint32_t)(slot * 64);
+            const uint64_t dbh = dbh0 + (uint64_t)(kb * 64), dbl = dbl0 + (uint64_t)(kb * 64);      // + kb * 1024 bytes
+            const int steps = kb == nkb - 1 ? last_steps : BK / UMMA_K;
+            if (elect_one()) {
+#pragma unroll
+                for (int j = 0; j < BK / UMMA_K; ++j) {
+                    if (j < steps) {
+                        const uint64_t bh = dbh + (uint64_t)(j * 16), bl = dbl + (uint64_t)(j * 16);           // + j * 256 bytes
+                        const uint32_t ah = a_hi + (uint32_t)(j * UMMA_K), al = ah + 32u;
+                        if (p.dbg & 2) { umma_tf32_ts(d_tmem, ah, bh, idesc, (kb | j) != 0); continue; }
+                        umma_tf32_ts(d_tmem, al, bh, idesc, (kb | j) != 0);
+                        umma_tf32_ts(d_tmem, ah, bl, idesc, 1u);
+                        umma_tf32_ts(d_tmem, ah, bh, idesc, 1u);
+                    }
                 }
                 umma_commit(&tmem_free[slot]);
                 if (kb == nkb - 1) umma_commit(&acc_full[buf]);
             }
+            __syncwarp();
+            if (++slot == kTsSlots) { slot = 0; slot_phase ^= 1u; }
+            if (++kb == nkb) { kb = 0; ++it; }
         }
     } else {
         epilogue_loop(p, cb, group, un, ncols, tmem_base, stage_base, s_bias, acc_full, acc_empty, my_tiles, warp, lane);
