@@ -44,7 +44,7 @@ struct Params {
     int n_parts, first_tile, local_part;
     int M, K, nb, tiles_m, n_groups;
     int dbg;           // measurement switches (TFGK_PROJ_DEBUG): 1 no lo conversion, 2 hi*hi MMA only, 4 no stores, 8 no loads,
-                       // 16 no TMEM reads, 32 no staging / stores after the TMEM read
+                       // 16 no TMEM reads, 32 no staging / stores after the TMEM read, 64 epilogue stores straight from registers
     const float *B[kMaxBlocks]; int64_t ldb[kMaxBlocks];
     const float *bias[kMaxBlocks]; int act[kMaxBlocks]; int ncols[kMaxBlocks]; int transb[kMaxBlocks];
     float *C[kMaxBlocks]; int64_t ldc[kMaxBlocks];
@@ -102,6 +102,57 @@ __device__ __forceinline__ void epilogue_loop(const Params &p, int cb, int group
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            }
+            if (p.dbg & 64) {
+                // direct variant: every thread stores the 16 columns of its own row straight from registers (64 contiguous
+                // bytes per row in four 16-byte stores), the tensor-memory read of the next pass is issued before the stores
+                // of this one - no staging tile, no warp barriers on the path
+                uint32_t ra[16], rb[16];
+                auto ldtm = [&](int ps, uint32_t (&r)[16]) {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kUN + ps * kPassCols);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                        : "r"(taddr));
+                };
+                auto store = [&](int ps, const uint32_t (&r)[16]) {
+                    const int c0 = ps * kPassCols;
+                    const int64_t row = row0 + lane;
+                    if (row >= p.M || (p.dbg & 4)) return;
+                    float *dst = Cb + row * ldc + c0;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        float4 v;
+                        v.x = apply_act(__uint_as_float(r[j]) + s_bias[c0 + j], act);
+                        v.y = apply_act(__uint_as_float(r[j + 1]) + s_bias[c0 + j + 1], act);
+                        v.z = apply_act(__uint_as_float(r[j + 2]) + s_bias[c0 + j + 2], act);
+                        v.w = apply_act(__uint_as_float(r[j + 3]) + s_bias[c0 + j + 3], act);
+                        if (vec_ok && c0 + j + 4 <= ncols) {
+                            *reinterpret_cast<float4 *>(dst + j) = v;
+                        } else {
+                            if (c0 + j < ncols) dst[j] = v.x;
+                            if (c0 + j + 1 < ncols) dst[j + 1] = v.y;
+                            if (c0 + j + 2 < ncols) dst[j + 2] = v.z;
+                            if (c0 + j + 3 < ncols) dst[j + 3] = v.w;
+                        }
+                    }
+                };
+                if (pass0 < pass1) ldtm(pass0, ra);
+                for (int ps = pass0; ps < pass1; ps += 2) {
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (ps + 1 < pass1) ldtm(ps + 1, rb);
+                    else { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&acc_empty[buf]); }
+                    store(ps, ra);
+                    if (ps + 1 < pass1) {
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (ps + 2 < pass1) ldtm(ps + 2, ra);
+                        else { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&acc_empty[buf]); }
+                        store(ps + 1, rb);
+                    }
+                }
+                continue;
             }
             for (int ps = pass0; ps < pass1; ++ps) {
                 const int c0 = ps * kPassCols;
@@ -659,7 +710,7 @@ extern "C" int tfgk_gemm_proj_f32(const float *const *A_parts, int32_t n_parts, 
     {   // A operands through tensor memory (TFGK_PROJ_IMPL=ss selects the all-shared-memory kernel)
         const char *impl = getenv("TFGK_PROJ_IMPL");
         const proj::PlanTS LT(K);
-        if (impl != nullptr && impl[0] == 't' && LT.stages >= 2) {
+        if (!(impl != nullptr && impl[0] == 's') && LT.stages >= 2) {
             switch (LT.stages) {
                 case 6: return proj::launch_ts<6>(p, grid, LT.total, st);
                 case 5: return proj::launch_ts<5>(p, grid, LT.total, st);
