@@ -185,7 +185,7 @@ def test_tma_gather4_variant_is_bit_identical(d, stages, monkeypatch):
     h = dev(rs.randn(n, d).astype(np.float32))
     bias = dev(rs.randn(d).astype(np.float32))
     for reduce, weights in (("sum", w), ("mean", None), ("max", w)):
-        monkeypatch.delenv("TFGK_SPMM_IMPL", raising=False)
+        monkeypatch.setenv("TFGK_SPMM_IMPL", "async")
         want = ops.spmm(csr, weights, h, reduce=reduce, bias=bias, act=ops.ACT_RELU)
         monkeypatch.setenv("TFGK_SPMM_IMPL", "gather4")
         monkeypatch.setenv("TFGK_SPMM_GATHER4_STAGES", stages)

@@ -17,6 +17,12 @@ import torch
 from . import ops, _structure
 
 
+def _relu_grad(g, y):
+    """dL/d(pre-activation) of y = relu(.): g where y > 0, else 0 - one elementwise pass (aten's relu backward) instead of
+    compare + cast + multiply."""
+    return torch.ops.aten.threshold_backward(g, y, 0.0)
+
+
 def _transposed_structure(edge_index, num_nodes, edge_weight, mean, csr):
     """(csr_t, w_t): CSR of the reversed edges and w_e / max(cnt[row_e], 1) (or w_e for sum) in its order.
     The structure is memoised per edge list; the weights per (weight tensor, structure) with the weight tensor held by
@@ -75,7 +81,7 @@ class Dense(torch.autograd.Function):
         x, weight, y = ctx.saved_tensors
         g = grad_y.contiguous()
         if ctx.act_code == ops.ACT_RELU:
-            g = g * (y > 0).to(g.dtype)                      # elementwise mask (torch: plumbing, not a hot op)
+            g = _relu_grad(g, y)                      # elementwise mask (torch: plumbing, not a hot op)
         grad_x = grad_w = grad_b = None
         if ctx.needs_input_grad[0]:
             grad_x = ops.gemm(g, weight.detach(), trans_b=True)
@@ -106,7 +112,7 @@ class SparseMatmul(torch.autograd.Function):
         (y,) = ctx.saved_tensors
         g = grad_y.contiguous()
         if ctx.act_code == ops.ACT_RELU:
-            g = g * (y > 0).to(g.dtype)
+            g = _relu_grad(g, y)
         adj = ctx.adj
         csr_t = adj._transposed_csr()
         if getattr(adj, "_value_csc", None) is None:
@@ -184,11 +190,11 @@ class GatAttention(torch.autograd.Function):
                 raise RuntimeError("GatAttention: the recompute backward refused a shape its forward accepted")
             grad_b = None
             if has_bias and ctx.needs_input_grad[3]:
-                gm = g * (y > 0).to(g.dtype) if act_code == ops.ACT_RELU else g
+                gm = _relu_grad(g, y) if act_code == ops.ACT_RELU else g
                 grad_b = ops.colsum(gm)
             return res[0], res[1], res[2], grad_b, None, None, None, None, None, None, None, None
         if act_code == ops.ACT_RELU:
-            g = g * (y > 0).to(g.dtype)
+            g = _relu_grad(g, y)
         inv_scale = 1.0 / scale
         ds = ops.gat_softmax_bwd(csr, att, g, V, H, split_value_heads=split, drop_rate=drop_rate, seed=seed)
         grad_q = grad_k = grad_v = grad_b = None
@@ -326,7 +332,7 @@ class SagePair(torch.autograd.Function):
         edge_index, edge_weight, reduce, act_code, concat, csr, has_bias = ctx.meta
         gm = grad_out.contiguous()
         if act_code == ops.ACT_RELU:
-            gm = gm * (out > 0).to(gm.dtype)
+            gm = _relu_grad(gm, out)
         u = ws.shape[1]
         gs, gn = (gm[:, :u], gm[:, u:]) if concat else (gm, gm)
         xd, wsd, wnd = x.detach(), ws.detach(), wn.detach()

@@ -966,6 +966,11 @@ static int dispatch_spmm_async(const SpmmParams &p, cudaStream_t st) {
     return launch_spmm_async<4, 2, 4>(p, st);
 }
 
+// Default kernel by row shape (profiles/r2_kernel_variants.json): rows whose byte length is a multiple of 512 fill every lane of
+// the cp.async ring (one 16-byte LDGSTS per lane per row) and that kernel is ~4% faster there; other widths leave lanes idle
+// (D = 100: 25 of 32) and the TMA gather4 ring, whose copies do not depend on the lane mapping, is ~8% faster.
+static bool spmm_prefers_gather4(int D) { return D >= 36 && D <= 256 && (D % 128) != 0; }
+
 static int spmm_impl_choice() {
     // 0 = register-staged LDG gather, 1 = TMA bulk gather.  TFGK_SPMM_IMPL overrides (read per call: cheap).
     const char *e = getenv("TFGK_SPMM_IMPL");
@@ -973,7 +978,8 @@ static int spmm_impl_choice() {
     if (e && e[0] == 's') return 2;
     if (e && (e[0] == 'g' || e[0] == 't')) return 4;      // "gather4" / "tma": TMA tile::gather4 ring
     if (e && e[0] == 'l') return 0;
-    return 3;      // cp.async ring (default); "ldg" / "stream" / "bulk" select the measured alternatives      // measured on B200 (profiles/r1_kernel_variants.json): 512 B bulk copies are TMA-issue bound
+    if (e && e[0] == 'a') return 3;      // "async": the cp.async ring for every shape
+    return 5;                            // default: by row shape (spmm_prefers_gather4); "ldg" / "stream" / "bulk" are the measured alternatives
 }
 
 template <int NC>
@@ -1068,7 +1074,7 @@ extern "C" int tfgk_spmm_f32(const int64_t *rowptr, const int32_t *col, const fl
         p.scratch = nullptr;
         // the plan applies when the whole width runs in one launch of the streaming kernel (scratch rows are D wide)
         const bool use_plan = plan != nullptr && plan->n_tasks > 0 && vec4 && D >= 32 && D <= cols_per_launch &&
-                              (spmm_impl_choice() == 3 || spmm_impl_choice() == 4);
+                              (spmm_impl_choice() >= 3);
         if (use_plan) {
             p.n_tasks = plan->n_tasks; p.task_row = plan->task_row; p.task_nrows = plan->task_nrows;
             p.task_e0 = plan->task_e0; p.task_e1 = plan->task_e1; p.task_slot = plan->task_slot;
@@ -1076,7 +1082,8 @@ extern "C" int tfgk_spmm_f32(const int64_t *rowptr, const int32_t *col, const fl
             p.hub_nslots = plan->hub_nslots; p.scratch = plan->scratch;
         }
         const int lanes = (p.D + vec - 1) / vec;
-        if (vec4 && p.D >= 32 && spmm_impl_choice() == 4) {
+        const int choice = spmm_impl_choice() == 5 ? (spmm_prefers_gather4(p.D) ? 4 : 3) : spmm_impl_choice();
+        if (vec4 && p.D >= 32 && choice == 4) {
             // the ABI does not carry the number of source rows: the tensor map is bounded by the index type instead
             // (column ids were validated against n_cols when the CSR was built)
             const char *cfg = getenv("TFGK_SPMM_GATHER4_STAGES");
@@ -1088,15 +1095,15 @@ extern "C" int tfgk_spmm_f32(const int64_t *rowptr, const int32_t *col, const fl
                                     : launch_spmm_gather4<4>(p, (int64_t)1 << 31, as_stream(stream));
             if (rcg != TFGK_ERR_UNSUPPORTED) { if (rcg != TFGK_OK) return rcg; continue; }
         }
-        if (vec4 && p.D >= 32 && (spmm_impl_choice() == 3 || spmm_impl_choice() == 4)) {
+        if (vec4 && p.D >= 32 && (choice == 3 || choice == 4)) {
             const int rca = dispatch_spmm_async(p, as_stream(stream));
             if (rca != TFGK_ERR_UNSUPPORTED) { if (rca != TFGK_OK) return rca; continue; }
         }
-        if (vec4 && p.D >= 32 && spmm_impl_choice() == 2) {
+        if (vec4 && p.D >= 32 && choice == 2) {
             const int rcs = dispatch_spmm_stream(p, as_stream(stream));
             if (rcs != TFGK_ERR_UNSUPPORTED) { if (rcs != TFGK_OK) return rcs; continue; }
         }
-        if (vec4 && p.D >= 32 && spmm_impl_choice() == 1) {
+        if (vec4 && p.D >= 32 && choice == 1) {
             const int rcb = dispatch_spmm_bulk(p, as_stream(stream));
             if (rcb != TFGK_ERR_UNSUPPORTED) { if (rcb != TFGK_OK) return rcb; continue; }
         }
