@@ -69,7 +69,9 @@ class PartitionedGraph(object):
             "p2p" if local_edge_index.is_cuda and partition.world_size > 1 else "collective")
         self._row_exchanges = {}
         self._pull_stream = None
-        self.pull_ctas = int(os.environ.get("TFGK_DIST_PULL_CTAS", "32"))      # CTAs of the pull kernel next to the GEMM
+        # peer pulls: copy engine (-1, default: 741 GB/s and no SMs taken from the GEMM running beside it) or the copy kernel
+        # on this many CTAs (TFGK_DIST_PULL_CTAS > 0; 663 GB/s from 148 CTAs on)
+        self.pull_ctas = int(os.environ.get("TFGK_DIST_PULL_CTAS", "-1"))
         self.nvlink_bytes = 0                       # bytes pulled from / received from peers so far (accounting)
 
     @classmethod
@@ -260,7 +262,7 @@ class PartitionedGraph(object):
         with torch.cuda.stream(side):
             for r in order:
                 lo, hi = bounds(r)
-                ex.pull(r, slot, hi - lo, full[lo:hi], max_ctas=0)
+                ex.pull(r, slot, hi - lo, full[lo:hi], max_ctas=self.pull_ctas)
         full.record_stream(side)
         full[p.lo:p.hi].copy_(mine[:p.n_local])
         main.wait_stream(side)
