@@ -402,9 +402,9 @@ def run_e2e(args, device, x_host, step_fn, n_out_rows, edges_per_layer, barrier=
 
 
 TIMED_CALLS = ("tfgk_gat_fused_f32", "tfgk_spmm_f32", "tfgk_gemm_f32", "tfgk_gemm_proj_f32")
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from committed `ncu --set full` captures (constants, NOT live
-# counters): profiles/r1_ncu_full_final_kernels.json; only valid for the full-size products-shape graph
-NCU_TRAFFIC = {"gat": 128184537000, "spmm_d128": 63515602000}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of round 2 (constants, NOT
+# live counters): profiles/r2_ncu_full_headline_kernels.json; only valid for the full-size products-shape graph
+NCU_TRAFFIC = {"gat": 128187213000, "spmm_d128": 63374651000}
 
 
 def build_workload(args, tfg, device):
@@ -551,8 +551,8 @@ def run_ours(args, rank, world, local_rank):
     d = fams[dominant]
     roofline = {"bound": "hbm", "kernel": d["kernel"], "achieved": d["achieved"], "peak": peak, "unit": "GB/s",
                 "frac": d["frac"], "traffic": d["traffic"],
-                "traffic_source": ("constant copied from the committed ncu --set full capture of round 1 "
-                                   "(profiles/r1_ncu_full_final_kernels.json), not measured in this run") if d["traffic"] else None,
+                "traffic_source": ("constant copied from the committed ncu --set full capture of round 2 "
+                                   "(profiles/r2_ncu_full_headline_kernels.json), not measured in this run") if d["traffic"] else None,
                 "peak_source": peak_src, "algorithmic_bytes": d["algorithmic_bytes_per_step"] / max(d["launches_per_step"], 1),
                 "kernel_ms": d["ms_per_step"] / max(d["launches_per_step"], 1),
                 "launches_per_step": d["launches_per_step"],
