@@ -34,6 +34,29 @@ inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s
 
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize once per (kernel, device) instead of on every launch (the attribute call costs
+// microseconds - invisible next to a 10 ms aggregation, visible on Cora-sized graphs where a forward is a few launches).
+// Only ever raises the limit; safe from several host threads (a repeated set is harmless).
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, size_t bytes) {
+    struct Entry { const void *fn; int dev; size_t bytes; };
+    static Entry table[256];
+    static int used = 0;
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    const void *fn = reinterpret_cast<const void *>(kernel);
+    const int n = used < 256 ? used : 256;
+    for (int i = 0; i < n; ++i)
+        if (table[i].fn == fn && table[i].dev == dev && table[i].bytes >= bytes) return cudaSuccess;
+    err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (err == cudaSuccess && used < 256) {
+        table[used].fn = fn; table[used].dev = dev; table[used].bytes = bytes;
+        ++used;
+    }
+    return err;
+}
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // activation applied in every fused epilogue

@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(256) gat_hub_fixup_kernel(const GatParams p) {
 template <int U, int S>
 static int launch_gat_async(const GatParams &p, cudaStream_t st) {
     const size_t smem = (size_t)kGatAsyncWarps * S * 2 * U * (size_t)(p.H * p.dqk) * 4;
-    TFGK_CUDA(cudaFuncSetAttribute(gat_async_kernel<U, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TFGK_CUDA(ensure_dynamic_smem(gat_async_kernel<U, S>, smem));
     const int64_t n_tasks = p.task_row ? p.n_tasks : ceil_div64(p.N, kGatAsyncRows);
     const unsigned blocks = (unsigned)ceil_div64(n_tasks, kGatAsyncWarps);
     gat_async_kernel<U, S><<<blocks, kGatAsyncWarps * 32, smem, st>>>(p);

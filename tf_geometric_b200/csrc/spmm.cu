@@ -877,10 +877,10 @@ static int launch_spmm_async(const SpmmParams &p, cudaStream_t st) {
     const int64_t n_tasks = p.task_row ? p.n_tasks : ceil_div64(p.n_dst, kAsyncRows);
     const unsigned blocks = (unsigned)ceil_div64(n_tasks, kAsyncWarps);
     if (p.reduce == TFGK_REDUCE_MAX) {
-        TFGK_CUDA(cudaFuncSetAttribute(spmm_async_kernel<NC, true, U, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TFGK_CUDA(ensure_dynamic_smem(spmm_async_kernel<NC, true, U, S>, smem));
         spmm_async_kernel<NC, true, U, S><<<blocks, kAsyncWarps * 32, smem, st>>>(p, row_bytes);
     } else {
-        TFGK_CUDA(cudaFuncSetAttribute(spmm_async_kernel<NC, false, U, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TFGK_CUDA(ensure_dynamic_smem(spmm_async_kernel<NC, false, U, S>, smem));
         spmm_async_kernel<NC, false, U, S><<<blocks, kAsyncWarps * 32, smem, st>>>(p, row_bytes);
     }
     TFGK_LAUNCH_CHECK();
@@ -931,10 +931,10 @@ static int launch_spmm_gather4(const SpmmParams &p, int64_t h_rows, cudaStream_t
     const int64_t n_tasks = p.task_row ? p.n_tasks : ceil_div64(p.n_dst, kAsyncRows);
     const unsigned blocks = (unsigned)ceil_div64(n_tasks, kAsyncWarps);
     if (p.reduce == TFGK_REDUCE_MAX) {
-        TFGK_CUDA(cudaFuncSetAttribute(spmm_gather4_kernel<true, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TFGK_CUDA(ensure_dynamic_smem(spmm_gather4_kernel<true, S>, smem));
         spmm_gather4_kernel<true, S><<<blocks, kAsyncWarps * 32, smem, st>>>(p, row_bytes, tmap);
     } else {
-        TFGK_CUDA(cudaFuncSetAttribute(spmm_gather4_kernel<false, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TFGK_CUDA(ensure_dynamic_smem(spmm_gather4_kernel<false, S>, smem));
         spmm_gather4_kernel<false, S><<<blocks, kAsyncWarps * 32, smem, st>>>(p, row_bytes, tmap);
     }
     TFGK_LAUNCH_CHECK();
@@ -993,10 +993,10 @@ static int launch_spmm_bulk(const SpmmParams &p, cudaStream_t st) {
     const int64_t rows_per_cta = (int64_t)warps * kBulkRowsPerWarp;
     const unsigned blocks = (unsigned)ceil_div64(p.n_dst, rows_per_cta);
     if (p.reduce == TFGK_REDUCE_MAX) {
-        TFGK_CUDA(cudaFuncSetAttribute(spmm_bulk_kernel<NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TFGK_CUDA(ensure_dynamic_smem(spmm_bulk_kernel<NC, true>, smem));
         spmm_bulk_kernel<NC, true><<<blocks, warps * 32, smem, st>>>(p, warps, row_bytes);
     } else {
-        TFGK_CUDA(cudaFuncSetAttribute(spmm_bulk_kernel<NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TFGK_CUDA(ensure_dynamic_smem(spmm_bulk_kernel<NC, false>, smem));
         spmm_bulk_kernel<NC, false><<<blocks, warps * 32, smem, st>>>(p, warps, row_bytes);
     }
     TFGK_LAUNCH_CHECK();

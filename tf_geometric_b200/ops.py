@@ -29,7 +29,10 @@ def default_device():
 
 def as_device(x, dtype=None, device=None):
     """numpy / list / torch (any device) -> contiguous CUDA tensor of `dtype` (reference casting rules are applied
-    by the callers: int32 edge_index, float32 weights/features; data/graph.py:58-86)."""
+    by the callers: int32 edge_index, float32 weights/features; data/graph.py:58-86).
+    A conversion creates a NEW tensor on every call, and the CSR caches are keyed on tensor identity: for the warm path
+    (no re-sort per forward) hand the layers an int32 CUDA edge_index - `Graph.to_device()` produces one - or pass
+    `cache=graph.cache`."""
     if x is None:
         return None
     if not torch.is_tensor(x):
@@ -83,9 +86,10 @@ class Plan(object):
         self._scratch = None
 
     def struct(self, floats_per_slot, device):
+        # the hub-slice scratch is allocated per call (the caching allocator makes that cheap and stream-ordered): a buffer
+        # kept on the plan would be shared by launches on different streams that use the same cached CSR
         need = max(self.n_slots * floats_per_slot, 1)
-        if self._scratch is None or self._scratch.numel() < need:
-            self._scratch = torch.empty((need,), dtype=torch.float32, device=device)
+        self._scratch = torch.empty((need,), dtype=torch.float32, device=device)
         a = self.arrays
         st = _ffi.PlanStruct(self.n_tasks, self.n_hubs, self.n_slots, HUB_CHUNK,
                              a["task_row"].data_ptr(), a["task_nrows"].data_ptr(), a["task_e0"].data_ptr(),
