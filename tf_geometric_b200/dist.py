@@ -249,7 +249,7 @@ class PartitionedGraph(object):
                     events.append(ev)
                 t1.record(side)
             self.pull_events.append((t0, t1))
-        del self.pull_events[:-64]
+            del self.pull_events[:-64]
 
             def project(rows, lo, hi):
                 if hi <= lo:
