@@ -11,7 +11,7 @@ Scope: the gather -> edge-apply -> segment-aggregate path under tfg.nn.gcn / gat
 (SURVEY.md section 8).  All arithmetic runs in libtfgk.so (hand-written CUDA, include/tfgk.h); importing the package
 works without a GPU, calling any operator does not (there is no CPU fallback).
 """
-from . import _ffi, ops, nn, layers, utils
+from . import _ffi, ops, nn, layers, utils, dist, peer
 from .data.graph import Graph, BatchGraph
 from .sparse import SparseMatrix
 from ._rng import set_seed
