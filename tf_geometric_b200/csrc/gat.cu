@@ -11,6 +11,7 @@
 // No tensor cores: the per-edge dot products are 16-wide and the kernel is bound by the gathers.
 #include "common.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 namespace tfgk {
 
@@ -468,6 +469,176 @@ __global__ void __launch_bounds__(kGatAsyncWarps * 32) gat_async_kernel(const Ga
     while (r < r1) finalize_row();
 }
 
+// ---- the same kernel with the neighbour rows fetched by TMA tile::gather4 (north_star: "staged through TMA") ------------------
+// K and V are projected into ONE [N, 2A] buffer (nn/conv/gat.py), so a tensor map over that buffer with a box of 2A columns x 1
+// row lets ONE cp.async.bulk.tensor...tile::gather4 fetch the key AND the value rows of four neighbours (4 x 2A x 4 bytes = 4 KB
+// at A = 128) into the warp's ring stage, completing its mbarrier with the transaction bytes.  Arithmetic, edge order and the
+// online softmax are those of gat_async_kernel: same bits.  Requires V == K + A columns in the same buffer (ldk == ldv).
+struct alignas(64) GatTensorMap { uint64_t opaque[16]; };
+
+__device__ __forceinline__ void gat_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spin > (1u << 28)) __trap();
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(kGatAsyncWarps * 32) gat_gather4_kernel(const GatParams p, const __grid_constant__ GatTensorMap tmap) {
+    constexpr int U = 4, RPC = 32 / U;
+    static_assert(S <= RPC, "index chunk refill assumes the prologue stays inside chunk 0");
+    extern __shared__ __align__(128) uint8_t gat_g4_ring[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int A = p.H * p.dqk;
+    const uint32_t edge_bytes = 2u * (uint32_t)A * 4u;            // [K row | V row] of one neighbour, contiguous in the KV buffer
+    const uint32_t tx_bytes = U * edge_bytes;
+    const uint32_t stage_bytes = (tx_bytes + 127u) & ~127u;
+    uint8_t *my_ring = gat_g4_ring + (size_t)warp * S * stage_bytes;
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(my_ring);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(gat_g4_ring + (size_t)kGatAsyncWarps * S * stage_bytes) + warp * S;
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < S; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * i));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const int64_t task = (int64_t)blockIdx.x * kGatAsyncWarps + warp;
+    int64_t r0, r1, e_begin, e_stop;
+    int slot = -1;
+    if (p.task_row != nullptr) {
+        if (task >= p.n_tasks) return;
+        r0 = p.task_row[task];
+        r1 = r0 + p.task_nrows[task];
+        e_begin = p.task_e0[task];
+        e_stop = p.task_e1[task];
+        slot = p.task_slot[task];
+    } else {
+        r0 = task * kGatAsyncRows;
+        if (r0 >= p.N) return;
+        r1 = min((int64_t)p.N, r0 + kGatAsyncRows);
+        e_begin = p.rowptr[r0];
+        e_stop = p.rowptr[r1];
+    }
+    const int64_t rp_hi = p.rowptr[min(r0 + lane + 1, r1)];
+    const int n_edges = (int)(e_stop - e_begin);
+    const int n_rounds = (n_edges + U - 1) / U;
+    const int lanes_per_head = p.dqk >> 2;
+    const int ccol = lane * 4;
+    const bool cok = ccol < A;
+    const uint32_t row_bytes = (uint32_t)A * 4u;
+
+    int64_t r = r0;
+    int row_end = slot >= 0 ? 0x7fffffff : (int)(__shfl_sync(0xffffffffu, rp_hi, 0) - e_begin);
+    float4 q = cok ? ldg4(p.Q + r * p.ldq + ccol) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 q_next = (cok && r + 1 < r1) ? ldg4(p.Q + (r + 1) * p.ldq + ccol) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float mx = -FLT_MAX, den = 0.0f, a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias && cok) bias = ldg4(p.bias + ccol);
+
+    auto finalize_row = [&]() {
+        if (cok) {
+            const float inv = 1.0f / (den + 1e-8f);
+            float4 o;
+            o.x = apply_act(a0 * inv + bias.x, p.act);
+            o.y = apply_act(a1 * inv + bias.y, p.act);
+            o.z = apply_act(a2 * inv + bias.z, p.act);
+            o.w = apply_act(a3 * inv + bias.w, p.act);
+            *reinterpret_cast<float4 *>(p.out + r * p.ldo + ccol) = o;
+            if (p.stats != nullptr && (lane % lanes_per_head) == 0) {
+                p.stats[r * 2 * p.H + lane / lanes_per_head] = mx;
+                p.stats[r * 2 * p.H + p.H + lane / lanes_per_head] = den + 1e-8f;
+            }
+        }
+        mx = -FLT_MAX; den = 0.0f; a0 = a1 = a2 = a3 = 0.0f;
+        ++r;
+        q = q_next;
+        if (r < r1) {
+            row_end = (int)(__shfl_sync(0xffffffffu, rp_hi, (int)(r - r0)) - e_begin);
+            if (cok && r + 1 < r1) q_next = ldg4(p.Q + (r + 1) * p.ldq + ccol);
+        }
+    };
+    auto load_chunk = [&](int c) {
+        const int e = c * 32 + lane;
+        return e < n_edges ? ld_stream_i32(p.col + e_begin + e) : 0;
+    };
+    auto issue = [&](int g, int ci) {
+        if (g < n_rounds) {
+            const int base = (g % RPC) * U;
+            const int valid = min(U, n_edges - g * U);
+            const int c0 = __shfl_sync(0xffffffffu, ci, base);
+            int c1 = __shfl_sync(0xffffffffu, ci, base + 1), c2 = __shfl_sync(0xffffffffu, ci, base + 2);
+            int c3 = __shfl_sync(0xffffffffu, ci, base + 3);
+            if (valid < 2) c1 = c0;
+            if (valid < 3) c2 = c0;
+            if (valid < 4) c3 = c0;
+            if (lane == 0) {
+                const uint32_t bar = bar0 + 8 * (uint32_t)(g % S);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx_bytes) : "memory");
+                asm volatile(
+                    "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                    ::"r"(ring_addr + (uint32_t)(g % S) * stage_bytes), "l"(&tmap), "r"(0), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+                    : "memory");
+            }
+        }
+    };
+
+    int ca = load_chunk(0), cb = load_chunk(1);
+#pragma unroll
+    for (int g = 0; g < S - 1; ++g) issue(g, ca);
+
+    for (int g = 0; g < n_rounds; ++g) {
+        __syncwarp();                               // every lane has finished reading the stage that is re-armed now
+        {
+            const int gn = g + S - 1;
+            issue(gn, ((gn / RPC) & 1) ? cb : ca);
+        }
+        gat_mbar_wait(bar0 + 8 * (uint32_t)(g % S), (uint32_t)(g / S) & 1u);
+        const uint8_t *sbuf = my_ring + (size_t)(g % S) * stage_bytes;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = g * U + u;
+            if (e < n_edges) {
+                while (e == row_end) finalize_row();
+                float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+                if (cok) {
+                    kk = *reinterpret_cast<const float4 *>(sbuf + (size_t)u * edge_bytes + ccol * 4);
+                    vv = *reinterpret_cast<const float4 *>(sbuf + (size_t)u * edge_bytes + row_bytes + ccol * 4);
+                }
+                float d = q.x * kk.x + q.y * kk.y + q.z * kk.z + q.w * kk.w;
+                for (int off = 1; off < lanes_per_head; off <<= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+                const float s = __fdiv_rn(d, p.scale);
+                const bool up = s > mx;
+                const float t = expf(up ? mx - s : s - mx);
+                const float corr = up ? t : 1.0f, pe = up ? 1.0f : t;
+                mx = up ? s : mx;
+                den = fmaf(den, corr, pe);
+                a0 = fmaf(a0, corr, pe * vv.x);
+                a1 = fmaf(a1, corr, pe * vv.y);
+                a2 = fmaf(a2, corr, pe * vv.z);
+                a3 = fmaf(a3, corr, pe * vv.w);
+            }
+        }
+        if ((g + S) % RPC == 0) {
+            const int dead = (g + S) / RPC - 1;
+            if (dead & 1) cb = load_chunk(dead + 2); else ca = load_chunk(dead + 2);
+        }
+    }
+    if (slot >= 0) {
+        float *dst = p.scratch + (int64_t)slot * (A + 64);
+        if (cok) *reinterpret_cast<float4 *>(dst + ccol) = make_float4(a0, a1, a2, a3);
+        dst[A + lane] = mx;
+        dst[A + 32 + lane] = den;
+        return;
+    }
+    while (r < r1) finalize_row();
+}
+
 // merges the (sums, max, denominator) partials of every hub row with the log-sum-exp rule, in slice order
 __global__ void __launch_bounds__(256) gat_hub_fixup_kernel(const GatParams p) {
     const int lane = threadIdx.x & 31;
@@ -523,7 +694,51 @@ static int launch_gat_async(const GatParams &p, cudaStream_t st) {
     return TFGK_OK;
 }
 
+typedef int (*GatEncodeTiledFn)(void *map, int dtype, uint32_t rank, void *base, const uint64_t *dims, const uint64_t *strides,
+                                const uint32_t *box, const uint32_t *elem_strides, int interleave, int swizzle, int l2promo,
+                                int oob_fill);
+
+template <int S>
+static int launch_gat_gather4(const GatParams &p, cudaStream_t st) {
+    const int A = p.H * p.dqk;
+    if (p.V != p.K + A || p.ldk != p.ldv || 2 * A > 256 || (p.ldk % 4) != 0) return TFGK_ERR_UNSUPPORTED;
+    static GatEncodeTiledFn encode = nullptr;
+    if (encode == nullptr) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        TFGK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (fn == nullptr || qres != cudaDriverEntryPointSuccess) return TFGK_ERR_UNSUPPORTED;
+        encode = reinterpret_cast<GatEncodeTiledFn>(fn);
+    }
+    GatTensorMap tmap;
+    const uint64_t dims[2] = {(uint64_t)(2 * A), (uint64_t)1 << 31};      // rows are bounded by the int32 column ids
+    const uint64_t strides[1] = {(uint64_t)p.ldk * sizeof(float)};
+    const uint32_t box[2] = {(uint32_t)(2 * A), 1u};
+    const uint32_t elem[2] = {1u, 1u};
+    if (encode(&tmap, 7, 2, const_cast<float *>(p.K), dims, strides, box, elem, 0, 0, 2, 0) != 0) return TFGK_ERR_UNSUPPORTED;
+    const size_t stage_pitch = ((size_t)4 * 2 * A * 4 + 127) & ~(size_t)127;
+    const size_t smem = (size_t)kGatAsyncWarps * S * stage_pitch + (size_t)kGatAsyncWarps * S * 8;
+    TFGK_CUDA(ensure_dynamic_smem(gat_gather4_kernel<S>, smem));
+    const int64_t n_tasks = p.task_row ? p.n_tasks : ceil_div64(p.N, kGatAsyncRows);
+    const unsigned blocks = (unsigned)ceil_div64(n_tasks, kGatAsyncWarps);
+    gat_gather4_kernel<S><<<blocks, kGatAsyncWarps * 32, smem, st>>>(p, tmap);
+    TFGK_LAUNCH_CHECK();
+    if (p.task_row && p.n_hubs > 0) {
+        gat_hub_fixup_kernel<<<(unsigned)ceil_div64(p.n_hubs, 8), 256, 0, st>>>(p);
+        TFGK_LAUNCH_CHECK();
+    }
+    return TFGK_OK;
+}
+
 static int dispatch_gat_async(const GatParams &p, cudaStream_t st) {
+    const char *g4 = getenv("TFGK_GAT_IMPL");               // "gather4[:S]": TMA tile::gather4 ring (K|V in one buffer)
+    if (g4 && g4[0] == 'g') {
+        const char *colon = strchr(g4, ':');
+        const int stages = colon ? atoi(colon + 1) : 3;
+        const int rc = stages == 2 ? launch_gat_gather4<2>(p, st) : stages == 4 ? launch_gat_gather4<4>(p, st)
+                                                                              : launch_gat_gather4<3>(p, st);
+        if (rc != TFGK_ERR_UNSUPPORTED) return rc;
+    }
     const char *cfg = getenv("TFGK_GAT_ASYNC_CFG");        // "UxS"; default 2x3
     if (cfg && cfg[0] == '4' && cfg[2] == '2') return launch_gat_async<4, 2>(p, st);
     if (cfg && cfg[0] == '4' && cfg[2] == '3') return launch_gat_async<4, 3>(p, st);
