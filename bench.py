@@ -434,13 +434,13 @@ def build_workload(args, tfg, device):
             gcn = tfg.layers.GCN(UNITS, activation=tfg.nn.relu, seed=2)
             gcn.build_cache_for_graph(graph)                   # normalised adjacency + CSR (one-off, untimed)
             layers.append(lambda xd: gcn([xd, graph.edge_index, graph.edge_weight], cache=graph.cache))
-            kernels["gcn_spmm"] = ("tfgk_spmm_f32", spmm_bytes(UNITS, e_loop, True), "spmm_async_kernel<1,0,4,3> (tfgk_spmm_f32)",
+            kernels["gcn_spmm"] = ("tfgk_spmm_f32", spmm_bytes(UNITS, e_loop, True), "spmm_gather4_kernel<0,3> (tfgk_spmm_f32)",
                                    NCU_TRAFFIC["spmm_d128"] if args.config == "headline" and args.scale == 1.0 else None)
             kernels["gcn_projection"] = ("tfgk_gemm_f32", proj_bytes(UNITS), "gemm_tf32x3_ws_kernel (tfgk_gemm_f32)", None)
         if "gat" in kind:
             gat = tfg.layers.GAT(UNITS, num_heads=HEADS, activation=tfg.nn.relu, seed=3)
             layers.append(lambda xd: gat([xd, graph.edge_index], cache=graph.cache))
-            kernels["gat_fused"] = ("tfgk_gat_fused_f32", gat_bytes, "gat_async_kernel<2,3> (tfgk_gat_fused_f32)",
+            kernels["gat_fused"] = ("tfgk_gat_fused_f32", gat_bytes, "gat_gather4_kernel<2> (tfgk_gat_fused_f32)",
                                     NCU_TRAFFIC["gat"] if args.config == "headline" and args.scale == 1.0 else None)
             kernels["gat_projections"] = ("tfgk_gemm_proj_f32", proj_bytes(3 * UNITS),
                                           "gemm_proj_kernel, Q|K|V in one launch (tfgk_gemm_proj_f32)", None)

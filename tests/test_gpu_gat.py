@@ -141,7 +141,7 @@ def test_gat_tma_gather4_variant_is_bit_identical(stages, monkeypatch):
     q = dev(rs.randn(n, a).astype(np.float32))
     kv = dev(rs.randn(n, 2 * a).astype(np.float32))
     bias = dev(rs.randn(a).astype(np.float32))
-    monkeypatch.delenv("TFGK_GAT_IMPL", raising=False)
+    monkeypatch.setenv("TFGK_GAT_IMPL", "async")
     want = ops.gat_fused(csr, q, kv[:, :a], kv[:, a:], heads, bias=bias, act=ops.ACT_RELU)
     monkeypatch.setenv("TFGK_GAT_IMPL", "gather4:" + stages)
     got = ops.gat_fused(csr, q, kv[:, :a], kv[:, a:], heads, bias=bias, act=ops.ACT_RELU)

@@ -731,10 +731,13 @@ static int launch_gat_gather4(const GatParams &p, cudaStream_t st) {
 }
 
 static int dispatch_gat_async(const GatParams &p, cudaStream_t st) {
-    const char *g4 = getenv("TFGK_GAT_IMPL");               // "gather4[:S]": TMA tile::gather4 ring (K|V in one buffer)
-    if (g4 && g4[0] == 'g') {
-        const char *colon = strchr(g4, ':');
-        const int stages = colon ? atoi(colon + 1) : 3;
+    // default: TMA tile::gather4 ring with two stages whenever K and V sit side by side in one buffer (the layers project them
+    // that way): 18.74 ms against 19.97 ms for the cp.async ring at the products shape, three / four stages lose resident warps
+    // (22.1 / 26.3 ms; profiles/r2_kernel_variants_final.json).  TFGK_GAT_IMPL=async keeps the cp.async ring; "gather4:S" sets S.
+    const char *g4 = getenv("TFGK_GAT_IMPL");
+    if (!(g4 && g4[0] == 'a')) {
+        const char *colon = g4 ? strchr(g4, ':') : nullptr;
+        const int stages = colon ? atoi(colon + 1) : 2;
         const int rc = stages == 2 ? launch_gat_gather4<2>(p, st) : stages == 4 ? launch_gat_gather4<4>(p, st)
                                                                               : launch_gat_gather4<3>(p, st);
         if (rc != TFGK_ERR_UNSUPPORTED) return rc;

@@ -966,10 +966,11 @@ static int dispatch_spmm_async(const SpmmParams &p, cudaStream_t st) {
     return launch_spmm_async<4, 2, 4>(p, st);
 }
 
-// Default kernel by row shape (profiles/r2_kernel_variants.json): rows whose byte length is a multiple of 512 fill every lane of
-// the cp.async ring (one 16-byte LDGSTS per lane per row) and that kernel is ~4% faster there; other widths leave lanes idle
-// (D = 100: 25 of 32) and the TMA gather4 ring, whose copies do not depend on the lane mapping, is ~8% faster.
-static bool spmm_prefers_gather4(int D) { return D >= 36 && D <= 256 && (D % 128) != 0; }
+// Default kernel: the TMA tile::gather4 ring with three stages for every float4-aligned width up to 256 columns
+// (profiles/r2_kernel_variants_final.json: D = 128 9.55 ms against 9.87 ms for the cp.async ring, D = 100 9.51 against 10.24;
+// three stages beat four, six and eight, which cost resident warps).  TFGK_SPMM_IMPL=async keeps the cp.async ring, which is also
+// the fallback when the driver entry point for tensor maps is unavailable.
+static bool spmm_prefers_gather4(int D) { return D >= 32 && D <= 256; }
 
 static int spmm_impl_choice() {
     // 0 = register-staged LDG gather, 1 = TMA bulk gather.  TFGK_SPMM_IMPL overrides (read per call: cheap).
@@ -1087,7 +1088,7 @@ extern "C" int tfgk_spmm_f32(const int64_t *rowptr, const int32_t *col, const fl
             // the ABI does not carry the number of source rows: the tensor map is bounded by the index type instead
             // (column ids were validated against n_cols when the CSR was built)
             const char *cfg = getenv("TFGK_SPMM_GATHER4_STAGES");
-            const int st = cfg ? atoi(cfg) : 4;
+            const int st = cfg ? atoi(cfg) : 3;
             const int rcg = st == 2 ? launch_spmm_gather4<2>(p, (int64_t)1 << 31, as_stream(stream))
                           : st == 3 ? launch_spmm_gather4<3>(p, (int64_t)1 << 31, as_stream(stream))
                           : st == 6 ? launch_spmm_gather4<6>(p, (int64_t)1 << 31, as_stream(stream))

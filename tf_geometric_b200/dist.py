@@ -597,7 +597,7 @@ def bench_papers(args, rank, world, device, metric, config):
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "clocks": clocks, "e2e": None, "gpu_launches": launches,
-                "roofline": {"bound": "hbm", "kernel": "spmm_async_kernel<1,0,4,3> (tfgk_spmm_f32), rank 0 partition",
+                "roofline": {"bound": "hbm", "kernel": "spmm_gather4_kernel<0,3> (tfgk_spmm_f32), rank 0 partition",
                              "achieved": spmm_bytes / (spmm_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": spmm_bytes / (spmm_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                              "algorithmic_bytes": spmm_bytes, "kernel_ms": spmm_ms},
@@ -719,7 +719,7 @@ def bench_partitioned(args, rank, world, device, metric, config):
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-                "roofline": {"bound": "hbm", "kernel": "gat_async_kernel<2,3> (tfgk_gat_fused_f32), rank 0 partition",
+                "roofline": {"bound": "hbm", "kernel": "gat_gather4_kernel<2> (tfgk_gat_fused_f32), rank 0 partition",
                              "achieved": gat_bytes / (gat_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": gat_bytes / (gat_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                              "algorithmic_bytes": gat_bytes, "kernel_ms": gat_ms},

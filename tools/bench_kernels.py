@@ -80,10 +80,9 @@ if os.environ.get("TFGK_BENCH_QUICK"):
     kv = torch.randn((n, 2 * D), generator=gen, device=dev)
     gat_bytes = csr.nnz * (8 * D + 4) + n * (8 * D + 8)
     ref = None
-    for impl in ("", "gather4:2", "gather4:3", "gather4:4"):
-        if impl:
-            os.environ["TFGK_GAT_IMPL"] = impl
-        timed(lambda: ops.gat_fused(csr, q, kv[:, :D], kv[:, D:], B.HEADS), "gat_" + (impl.replace(":", "_") or "async_2x3"), gat_bytes)
+    for impl in ("async", "gather4:2", "gather4:3", "gather4:4"):
+        os.environ["TFGK_GAT_IMPL"] = impl
+        timed(lambda: ops.gat_fused(csr, q, kv[:, :D], kv[:, D:], B.HEADS), "gat_" + impl.replace(":", "_").replace("async", "async_2x3"), gat_bytes)
         got = ops.gat_fused(csr, q, kv[:, :D], kv[:, D:], B.HEADS)
         if ref is None:
             ref = got.clone()

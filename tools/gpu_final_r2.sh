@@ -17,7 +17,7 @@ echo "== train"; timeout 300 python tools/bench_train.py --steps 5 > $O/r2_train
 if [ "$1" == "--ncu" ]; then
   echo "== launch list headline"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/r2_launches_headline.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2> $O/ncu1.err; echo "rc=$?"
   echo "== launch list cfg4"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/r2_launches_cfg4.csv python bench.py --config cfg4 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2> $O/ncu1b.err; echo "rc=$?"
-  echo "== ncu --set full headline kernels"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gat_async_kernel|spmm_async_kernel|gemm_proj_ts_kernel" -s 12 -c 4 -o $O/r2_prof_headline -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2> $O/ncu2.err; echo "rc=$?"
-  echo "== ncu --set full training kernels"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gat_bwd_kernel|spmm_gather4_kernel" -s 4 -c 3 -o $O/r2_prof_train -f python tools/ncu_train.py > /dev/null 2> $O/ncu3.err; echo "rc=$?"
+  echo "== ncu --set full headline kernels"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gat_gather4_kernel|gat_async_kernel|spmm_gather4_kernel|spmm_async_kernel|gemm_proj_ts_kernel" -s 12 -c 4 -o $O/r2_prof_headline -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2> $O/ncu2.err; echo "rc=$?"
+  echo "== ncu --set full training kernels"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gat_bwd_kernel|spmm_gather4_kernel" -s 6 -c 4 -o $O/r2_prof_train -f python tools/ncu_train.py > /dev/null 2> $O/ncu3.err; echo "rc=$?"
   for r in r2_prof_headline r2_prof_train; do python tools/ncu_summary.py $O/$r.ncu-rep > $O/$r.json 2>/dev/null; done
 fi
