@@ -404,7 +404,7 @@ def run_e2e(args, device, x_host, step_fn, n_out_rows, edges_per_layer, barrier=
 TIMED_CALLS = ("tfgk_gat_fused_f32", "tfgk_spmm_f32", "tfgk_gemm_f32", "tfgk_gemm_proj_f32")
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of round 2 (constants, NOT
 # live counters): profiles/r2_ncu_full_headline_kernels.json; only valid for the full-size products-shape graph
-NCU_TRAFFIC = {"gat": 128187213000, "spmm_d128": 63374651000}
+NCU_TRAFFIC = {"gat": 128185916000, "spmm_d128": 63372534000}
 
 
 def build_workload(args, tfg, device):
