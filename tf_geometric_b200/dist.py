@@ -292,9 +292,21 @@ class PartitionedGraph(object):
             c0 += wd
         return outs
 
+    def close(self):
+        """Unmap the peers' buffers and free this rank's published buffers (collective: every rank calls it).  Optional -
+        process exit releases them too."""
+        for ex in self._row_exchanges.values():
+            if ex is not None:
+                ex.close()
+        self._row_exchanges = {}
+        self._work = {}
+
     def share(self, x_local, layers):
         """Publish x_local once and compute, in ONE fused launch sequence, the all-row projections of every layer in
-        `layers` (tfg.layers.GCN / GAT ...).  Pass the result instead of x_local: layer([shared, partitioned_graph])."""
+        `layers` (tfg.layers.GCN / GAT ...).  Pass the result instead of x_local: layer([shared, partitioned_graph]).
+        The result is meant to be consumed by those layers before the next share() / layer call on this graph: when the
+        projected rows are pulled from the peers (input at least as wide as the projections) they live in an exchange buffer
+        that the next exchange overwrites."""
         x_local = ops.as_device(x_local, torch.float32, device=self.edge_index.device)
         shared = SharedRows(x_local, self)
         groups, owners = [], []
