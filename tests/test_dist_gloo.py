@@ -28,7 +28,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, n, seed, renorm, queue):
+def _worker(rank, world, port, n, seed, renorm, queue, exchange=None):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -49,8 +49,10 @@ def _worker(rank, world, port, n, seed, renorm, queue):
         wq, wk, wv = glorot(rs, f, u), glorot(rs, f, u), glorot(rs, f, u)
         bq, bk = rs.randn(u).astype(np.float32) * .1, rs.randn(u).astype(np.float32) * .1
 
-        pg = tdist.PartitionedGraph.from_global(ei, w, n)
+        pg = tdist.PartitionedGraph.from_global(ei, w, n, exchange=exchange)
         p = pg.part
+        if exchange == "p2p":          # 128-row aligned blocks; without CUDA every exchange falls back to the collective
+            assert p.block % 128 == 0
         x_local = x[p.lo:p.hi]
         gcn_local = tdist.gcn_partitioned(pg, x_local, k, b, ops.relu, renorm=renorm)
         gat_local = tdist.gat_partitioned(pg, x_local, wq, bq, ops.relu, wk, bk, ops.relu, wv, b, ops.relu, num_heads=heads)
@@ -78,15 +80,15 @@ def _worker(rank, world, port, n, seed, renorm, queue):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n,renorm", [(101, True), (64, False)])
-def test_partitioned_gcn_and_gat_match_single_process_oracle(n, renorm):
+@pytest.mark.parametrize("n,renorm,exchange", [(101, True, None), (64, False, None), (300, True, "p2p")])
+def test_partitioned_gcn_and_gat_match_single_process_oracle(n, renorm, exchange):
     from oracle import tfg_oracle as o
     from conftest import random_graph, glorot
     world, seed = 2, 5
     ctx = mp.get_context("spawn")
     queue = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, seed, renorm, queue)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, seed, renorm, queue, exchange)) for r in range(world)]
     for p in procs:
         p.start()
     parts = sorted(queue.get(timeout=120) for _ in range(world))
