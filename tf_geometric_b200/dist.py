@@ -13,13 +13,18 @@ tf.distribute.MirroredStrategy, demo/demo_distributed_gcn.py:37-57); this is the
 Per-row edge order is the caller's order, so every output row is bit-identical to the single-GPU result.
 
 Round 2 - how the source rows reach a rank (the exchange step):
-  * "p2p" (default on GPUs of one node): NO collective on the data path.  Every rank publishes its rows of x in a
-    peer-mapped buffer (peer.RowExchange: one device-to-device copy + a device-side flag barrier over NVLink) and the
-    dense projections of ALL rows are computed by one tcgen05 launch whose A tiles are pulled straight from the owning
-    rank's memory (tfgk_gemm_proj_f32 with a_parts): a fused all-gather -> GEMM.  Because x is narrower than what is
-    aggregated (F = 100 against 128 + 256 projected columns in the bench) this moves 3.8x fewer bytes over NVLink than
-    shipping projected rows, and the projections replicated on every rank are cheap tensor-core work hidden under the
-    transfer.  Rows are identical to the ones the owner would compute (row-local arithmetic, same kernel).
+  * "p2p" (default on GPUs of one node): NO collective on the data path.  Every rank publishes rows in a peer-mapped
+    buffer (peer.RowExchange: CUDA IPC mappings set up once; per publication one device-to-device copy and a device-side
+    flag barrier over NVLink) and the other ranks pull them with tfgk_peer_pull (copy engine by default) on a side stream.
+      - input narrower than what is aggregated (the bench: F = 100 against 128 + 256 projected columns): x itself is
+        published and pulled into a local [N, F] table, and tfgk_gemm_proj_f32 projects every block as soon as it has
+        landed - the pull of block j+1 travels while the tensor core works on block j.  3.8x fewer NVLink bytes than
+        shipping projected rows; the projections replicated on every rank are tensor-core work.  Rows are identical to the
+        ones the owner would compute (row-local arithmetic, same kernel).
+      - input at least as wide (config 5): the local rows are projected straight into the published slot and the peers'
+        projected rows are pulled (no replicated GEMM).
+  * "p2p_fused": measured alternative - the projection GEMM's producers cp.async the owners' rows in place (a_parts of
+    tfgk_gemm_proj_f32).  Correct, slower (peer reads bypass the local L2).
   * "collective": the round-1 path - project the local rows, all-gather the projected rows (NCCL on GPUs, gloo in the
     CPU tests); also the fallback when peer mappings cannot be set up.
 tfg.layers.GCN / GAT accept [x_local, partitioned_graph] (or the result of partitioned_graph.share(...)).
@@ -187,8 +192,8 @@ class PartitionedGraph(object):
         """Dense projections of EVERY node's features, which each aggregation kernel then gathers from.
         groups: list of column groups, each a list of (weight [F, n], bias or None, act code); the projections of one
         group are laid side by side in one [padded_nodes, sum n] buffer (e.g. K | V).  Returns the list of buffers.
-        p2p: one fused all-gather -> GEMM launch per four 128-column blocks, A tiles pulled from the owning ranks;
-        collective: local projection + all-gather of the projected rows."""
+        p2p: peers' rows pulled over NVLink peer mappings on a side stream, blocks projected as they land (or, for wide
+        inputs, the peers' projected rows pulled); collective: local projection + all-gather of the projected rows."""
         p = self.part
         dev = x_local.device
         widths = [sum(int(w.shape[1]) for w, _, _ in g) for g in groups]
