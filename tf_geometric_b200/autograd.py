@@ -140,11 +140,16 @@ def _transposed_of_csr(csr, edge_index_used):
 class GatAttention(torch.autograd.Function):
     """y = act(softmax-attention aggregate(Q, K, V) + b) (gat.py:73-120) with gradients for Q, K, V and b.
 
-    forward : tfgk_gat_fused_f32 (coefficients kept for the backward); with attention dropout (gat.py:85) the
-              coefficients are re-aggregated by tfgk_spmm_heads_f32 under a counter-based mask.
-    backward: G = dy * act'(y);  ds = tfgk_gat_softmax_bwd_f32(att, G, V);
-              dQ = sum_e ds K[col] / scale                       forward CSR
-              dK = sum_e ds Q[row] / scale,  dV = sum_e a' G[row] transposed CSR (gather instead of scatter-add)
+    Without attention dropout (the default path):
+      forward : tfgk_gat_fused_stats_f32 keeps (max, denominator) per (row, head) - no [E', H] coefficient table;
+      backward: tfgk_gat_bwd_prepare/dst/src_f32 recompute the coefficients from those two numbers (dQ over the forward
+                CSR, dK and dV over the transposed CSR: gathers, never scatter-adds).
+    With attention dropout (gat.py:85), averaged heads, hub-row plans or shapes the streaming kernel does not take:
+      forward : tfgk_gat_fused_f32 with the coefficients kept; under dropout they are re-aggregated by
+                tfgk_spmm_heads_f32 with a counter-based mask;
+      backward: G = dy * act'(y);  ds = tfgk_gat_softmax_bwd_f32(att, G, V);
+                dQ = sum_e ds K[col] / scale                       forward CSR
+                dK = sum_e ds Q[row] / scale,  dV = sum_e a' G[row] transposed CSR
     The mask is regenerated from (seed, edge, head) in every kernel, never stored."""
 
     @staticmethod

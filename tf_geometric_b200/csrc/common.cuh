@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <float.h>
+#include <mutex>
 #include "tfgk.h"
 
 namespace tfgk {
@@ -42,9 +43,11 @@ inline cudaError_t ensure_dynamic_smem(Kernel kernel, size_t bytes) {
     struct Entry { const void *fn; int dev; size_t bytes; };
     static Entry table[256];
     static int used = 0;
+    static std::mutex guard;                  // launches may come from several host threads
     int dev = 0;
     cudaError_t err = cudaGetDevice(&dev);
     if (err != cudaSuccess) return err;
+    std::lock_guard<std::mutex> lock(guard);
     const void *fn = reinterpret_cast<const void *>(kernel);
     const int n = used < 256 ? used : 256;
     for (int i = 0; i < n; ++i)

@@ -617,7 +617,7 @@ extern "C" int tfgk_gemm_tc_f32(const float *A, int64_t lda, const float *B, int
         const tc::SmemPlanDeep LD(p.un, K);
         if (LD.ring >= 3 && (2u * LD.b_bytes) % 1024u == 0) {
 #define TFGK_LAUNCH_DEEP(RR)                                                                                              \
-            TFGK_CUDA(cudaFuncSetAttribute(tc::gemm_tf32x3_deep_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LD.total)); \
+            TFGK_CUDA(ensure_dynamic_smem(tc::gemm_tf32x3_deep_kernel<RR>, LD.total)); \
             tc::gemm_tf32x3_deep_kernel<RR><<<grid, tc::kWsThreads, LD.total, as_stream(stream)>>>(p)
             if (LD.ring == 5) { TFGK_LAUNCH_DEEP(5); } else if (LD.ring == 4) { TFGK_LAUNCH_DEEP(4); } else { TFGK_LAUNCH_DEEP(3); }
 #undef TFGK_LAUNCH_DEEP
@@ -627,20 +627,20 @@ extern "C" int tfgk_gemm_tc_f32(const float *A, int64_t lda, const float *B, int
     }
     if (!(impl && impl[0] == 's')) {          // default: warp-specialised; "sync" selects the __syncthreads variant
         if (L.stages == 3) {
-            TFGK_CUDA(cudaFuncSetAttribute(tc::gemm_tf32x3_ws_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+            TFGK_CUDA(ensure_dynamic_smem(tc::gemm_tf32x3_ws_kernel<3>, L.total));
             tc::gemm_tf32x3_ws_kernel<3><<<grid, tc::kWsThreads, L.total, as_stream(stream)>>>(p);
         } else {
-            TFGK_CUDA(cudaFuncSetAttribute(tc::gemm_tf32x3_ws_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+            TFGK_CUDA(ensure_dynamic_smem(tc::gemm_tf32x3_ws_kernel<2>, L.total));
             tc::gemm_tf32x3_ws_kernel<2><<<grid, tc::kWsThreads, L.total, as_stream(stream)>>>(p);
         }
         TFGK_LAUNCH_CHECK();
         return TFGK_OK;
     }
     if (L.stages == 3) {
-        TFGK_CUDA(cudaFuncSetAttribute(tc::gemm_tf32x3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+        TFGK_CUDA(ensure_dynamic_smem(tc::gemm_tf32x3_kernel<3>, L.total));
         tc::gemm_tf32x3_kernel<3><<<grid, tc::kThreads, L.total, as_stream(stream)>>>(p);
     } else {
-        TFGK_CUDA(cudaFuncSetAttribute(tc::gemm_tf32x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+        TFGK_CUDA(ensure_dynamic_smem(tc::gemm_tf32x3_kernel<2>, L.total));
         tc::gemm_tf32x3_kernel<2><<<grid, tc::kThreads, L.total, as_stream(stream)>>>(p);
     }
     TFGK_LAUNCH_CHECK();
