@@ -235,6 +235,25 @@ def test_golden_reference_execution_files_match_oracle():
         replay_with_oracle(f, data)
 
 
+def test_fixture_generator_shim_is_independent_of_the_oracle():
+    """The ref_exec_* fixtures pin the oracle only if the TF / tf_sparse stand-ins that executed the reference were written
+    without it: tools/ref_shim must not import (or name) the checker, and loading it must not pull `oracle` into the
+    interpreter.  Checked in a fresh interpreter."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shim = os.path.join(root, "tools", "ref_shim")
+    for name in os.listdir(shim):
+        if name.endswith(".py"):
+            text = open(os.path.join(shim, name)).read()
+            assert "import oracle" not in text and "from oracle" not in text and "tfg_oracle" not in text, name
+    code = ("import sys; sys.path.insert(0, {!r}); import ref_shim; "
+            "bad = [m for m in sys.modules if m == 'oracle' or m.startswith('oracle.') or m.startswith('tf_geometric_b200')]; "
+            "print(bad); sys.exit(1 if bad else 0)").format(os.path.join(root, "tools"))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root)
+    assert res.returncode == 0, res.stdout + res.stderr
+
+
 def test_philox_known_answers_and_uniform_draws():
     """Philox4x32-10 against the Random123 known-answer vectors (counter, key -> output); the kernels in
     tf_geometric_b200/csrc/rng.cuh implement the same function and are compared with the oracle bit for bit on the GPU."""
