@@ -3,9 +3,10 @@
 
 One process per GPU.  Every rank allocates a buffer with tfgk_peer_alloc (cudaMalloc, so it can be exported), the
 64-byte CUDA IPC handles travel through torch.distributed (host side, once), and every rank maps the other ranks'
-buffers.  After that the data path uses no collective at all: kernels read the owning rank's memory over NVLink
-(tfgk_gemm_proj_f32 with `a_parts`) and ranks synchronise with tfgk_peer_barrier, a device-side flag barrier on the
-stream.  torch only sees these buffers as tensors created over the raw pointer (no torch allocation behind them).
+buffers.  After that the data path uses no collective at all: ranks pull the owning rank's rows over NVLink with
+tfgk_peer_pull (copy engine or a copy kernel; tfgk_gemm_proj_f32 can also read them in place through `a_parts`) and
+synchronise with tfgk_peer_barrier, a device-side flag barrier on the stream.  torch only sees these buffers as tensors
+created over the raw pointer (no torch allocation behind them).
 """
 import ctypes
 
@@ -82,8 +83,9 @@ class RowExchange(object):
     Two slots of [block, width] floats per rank alternate between publications.  publish(x_local) copies the rows into
     the current slot and runs the device-side barrier; after it, slot_ptrs() are the addresses (one per rank) a kernel
     later on this stream may read.  The barrier of publication g also certifies that every rank has finished reading
-    publication g-1 (the reads were enqueued on the same stream before the barrier), so the slot of g-2 can be
-    overwritten by g without further hand-shakes.  All calls must come from the same stream.
+    publication g-1 (the reads were enqueued on the same stream before the barrier - or on a side stream the publishing
+    stream has waited for, as dist.PartitionedGraph does with its pull stream), so the slot of g-2 can be overwritten by
+    g without further hand-shakes.  next_slot / commit / publish must come from the same stream.
     """
 
     FLAG_BYTES = 256
