@@ -393,3 +393,42 @@ def test_sparse_features_and_column_splits():
         assert torch.equal(part, full), splits
     with pytest.raises(ValueError):
         tfg.nn.gcn(dev(dense), tfg.SparseMatrix(eid, None, [n, n]), dev(k), dev(b), num_or_size_splits=3)
+
+
+def test_training_with_sparse_features_matches_dense_features():
+    """demo_gcn.py / demo_gat.py train on tf.SparseTensor features: the weight gradients with a sparse x (projection and
+    its transpose on the aggregation kernel) equal the ones the dense training path gives (that path is checked against
+    float64 autograd in test_gpu_train)."""
+    rs = np.random.RandomState(21)
+    n, f, u, heads = 500, 240, 16, 4
+    dense = ((rs.rand(n, f) < 0.06) * rs.rand(n, f)).astype(np.float32)
+    dense[7] = 0.0
+    ei = random_graph(n, 4000, seed=5, symmetric=True, isolated=1)
+    eid = dev(ei, torch.int32)
+    nz = np.nonzero(dense)
+    xs = tfg.SparseMatrix(np.stack(nz).astype(np.int32), dense[nz], [n, f])
+    names = ("k", "b", "wq", "bq", "wk", "bk", "wv")
+    init = {"k": glorot(rs, f, u), "b": rs.randn(u).astype(np.float32), "wq": glorot(rs, f, u), "wk": glorot(rs, f, u),
+            "wv": glorot(rs, f, u), "bq": rs.randn(u).astype(np.float32) * .1, "bk": rs.randn(u).astype(np.float32) * .1}
+    gout = dev(rs.randn(n, u).astype(np.float32))
+
+    def grads(x):
+        p = {k_: dev(init[k_]).requires_grad_(True) for k_ in names}
+        y1 = tfg.nn.gcn(x, tfg.SparseMatrix(eid, None, [n, n]), p["k"], p["b"], tfg.nn.relu)
+        y2 = tfg.nn.gat(x, eid, p["wq"], p["bq"], tfg.nn.relu, p["wk"], p["bk"], tfg.nn.relu, p["wv"], p["b"], tfg.nn.relu,
+                        num_heads=heads)
+        assert y1.requires_grad and y2.requires_grad
+        ((y1 + y2) * gout).sum().backward()
+        return host(y1), host(y2), {k_: host(p[k_].grad) for k_ in names}
+
+    s1, s2, gs = grads(xs)
+    d1, d2, gd = grads(dev(dense))
+    assert_close(s1, d1, rtol=1e-4, atol_scale=1e-4, what="gcn forward, sparse features, training path")
+    assert_close(s2, d2, rtol=1e-4, atol_scale=1e-4, what="gat forward, sparse features, training path")
+    for k_ in names:
+        assert np.abs(gd[k_]).sum() > 0, k_
+        assert_close(gs[k_], gd[k_], rtol=1e-3, atol_scale=2e-4, what="d " + k_ + " with sparse features")
+    layer = tfg.layers.GCN(u, activation=tfg.nn.relu, seed=4, trainable=True)
+    out = layer([xs, eid], training=True)
+    out.sum().backward()
+    assert all(p_.grad is not None and float(p_.grad.abs().sum()) > 0 for n_, p_ in layer.named_parameters() if "bias" not in n_)

@@ -356,12 +356,18 @@ def _spmm64(index, value, h, n):
 
 
 @pytest.mark.parametrize("name", ["sgc", "ssgc", "tagcn", "gin", "le_conv", "chebynet", "gcn_graph_sage",
-                                  "mean_pool_graph_sage"])
+                                  "mean_pool_graph_sage", "max_pool_graph_sage"])
 def test_conv_training_gradients_match_autodiff(name):
     """Loss gradients of the remaining convolutions against float64 torch autograd over the reference's op sequence."""
     rs = np.random.RandomState(sum(map(ord, name)))
     n, f, u = 320, 9, 6
     ei = random_graph(n, 2400, seed=len(name), symmetric=True, isolated=1)
+    if name == "max_pool_graph_sage":
+        # every node needs an in-edge here: an empty max is float32 lowest (reference semantics, asserted in
+        # test_gpu_models), which overflows in the projection that follows and says nothing about gradients
+        ring = np.arange(n, dtype=ei.dtype)
+        ei = np.concatenate([ei[:, :ei.shape[1] // 2], np.stack([ring, np.roll(ring, 1)]),
+                             ei[:, ei.shape[1] // 2:], np.stack([np.roll(ring, 1), ring])], axis=1)
     w = (rs.rand(ei.shape[1]) + 0.2).astype(np.float32)
     half = ei.shape[1] // 2
     w[half:] = w[:half]                                             # symmetric weights (chebynet's Laplacian)
@@ -448,6 +454,18 @@ def test_conv_training_gradients_match_autodiff(name):
         ai, av = normed(renorm=False, weights=np.ones_like(w))     # quirks: weights -> ones, cache=None -> renorm=False
         run(lambda xd, p: tfg.nn.gcn_graph_sage(xd, eid, wd, p["k"], p["b"], relu),
             lambda x64, p: torch.relu(_spmm64(ai, av, x64, n) @ p["k"] + p["b"]), grad_x=True)
+    elif name == "max_pool_graph_sage":
+        P.update(ws=glorot(rs, f, u), wm=glorot(rs, f, 8), wn=glorot(rs, 8, u), bm=rs.randn(8).astype(np.float32),
+                 b=rs.randn(2 * u).astype(np.float32))
+        row64 = torch.from_numpy(ei[0].astype(np.int64)).unsqueeze(1).expand(-1, 8)
+        col64 = torch.from_numpy(ei[1].astype(np.int64))
+
+        def ref(x64, p):
+            h_node = torch.relu(x64 @ p["wm"] + p["bm"])
+            red = torch.zeros((n, 8), dtype=torch.float64).scatter_reduce(0, row64, h_node[col64], "amax", include_self=False)
+            return torch.relu(torch.cat([x64 @ p["ws"], red @ p["wn"]], dim=1) + p["b"])
+        run(lambda xd, p: tfg.nn.max_pool_graph_sage(xd, eid, wd, p["ws"], p["wm"], p["wn"], p["bm"], p["b"], relu), ref,
+            grad_x=True)
     else:
         P.update(ws=glorot(rs, f, u), wm=glorot(rs, f, 8), wn=glorot(rs, 8, u), bm=rs.randn(8).astype(np.float32),
                  b=rs.randn(2 * u).astype(np.float32))
@@ -474,6 +492,7 @@ def test_every_trainable_layer_gets_gradients():
         (L.SumGraphSage(8, concat=False, seed=1, trainable=True), [xd, eid, wd]),
         (L.GCNGraphSage(8, seed=1, trainable=True), [xd, eid, wd]),
         (L.MeanPoolGraphSage(8, seed=1, trainable=True), [xd, eid, wd]),
+        (L.MaxPoolGraphSage(8, seed=1, trainable=True), [xd, eid, wd]),
         (L.APPNP([12, 5], k=3, seed=1, trainable=True), [xd, eid, wd]),
         (L.SGC(6, k=2, seed=1, trainable=True), [xd, eid, wd]),
         (L.SSGC([12, 5], k=3, seed=1, trainable=True), [xd, eid, wd]),
@@ -491,8 +510,6 @@ def test_every_trainable_layer_gets_gradients():
             assert p.grad is not None and torch.isfinite(p.grad).all(), "{}.{}".format(type(layer).__name__, pname)
             if "bias" not in pname:
                 assert float(p.grad.abs().sum()) > 0, "{}.{}".format(type(layer).__name__, pname)
-    with pytest.raises(NotImplementedError):
-        L.MaxPoolGraphSage(8, seed=1, trainable=True)([xd, eid, wd])
 
 
 def test_every_pool_layer_passes_gradients():

@@ -88,6 +88,7 @@ def test_model_paths(fake):
     test_gpu_models.test_appnp(10, 0.1)
     test_gpu_models.test_appnp(0, 0.1)
     test_gpu_models.test_sparse_features_and_column_splits()
+    test_gpu_models.test_training_with_sparse_features_matches_dense_features()
     test_gpu_models.test_graph_sage_forward_backward("mean", False, True)
     test_gpu_models.test_graph_sage_forward_backward("mean", True, False)
     test_gpu_models.test_graph_sage_forward_backward("sum", True, True)
@@ -149,7 +150,8 @@ def test_pooling_family_on_the_fake_backend(fake):
 
 
 def test_remaining_convs_train_on_the_fake_backend(fake):
-    for name in ("sgc", "ssgc", "tagcn", "gin", "le_conv", "chebynet", "gcn_graph_sage", "mean_pool_graph_sage"):
+    for name in ("sgc", "ssgc", "tagcn", "gin", "le_conv", "chebynet", "gcn_graph_sage", "mean_pool_graph_sage",
+                 "max_pool_graph_sage"):
         test_gpu_train.test_conv_training_gradients_match_autodiff(name)
     test_gpu_train.test_every_trainable_layer_gets_gradients()
 

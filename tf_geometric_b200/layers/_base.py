@@ -18,7 +18,7 @@ class Layer(torch.nn.Module):
         self.built = False
         self._seed = kwargs.pop("seed", None)
         # Keras weights are trainable by default; here weights only require grad when asked, so that plain forward calls
-        # take the fused inference kernels.  Backward passes exist for every convolution except max_pool_graph_sage (autograd.py).
+        # take the fused inference kernels.  Backward passes exist for every convolution (autograd.py).
         self._trainable = bool(kwargs.pop("trainable", False))
 
     def add_weight(self, name, shape, initializer="glorot_uniform", regularizer=None, device=None):

@@ -50,7 +50,11 @@ def gat(x, edge_index,
     drop_rate = float(edge_drop_rate) if training else 0.0
     if x_sparse is not None:
         if drop_rate > 0.0 or autograd.needs_grad(query_kernel, query_bias, key_kernel, key_bias, kernel, bias):
-            raise NotImplementedError("training with sparse features: pass x.to_dense()")
+            if return_attention:
+                raise NotImplementedError("return_attention is an inference-path extension")
+            return _gat_training(x_sparse, csr, edge_index_used, query_kernel, query_bias, query_activation, key_kernel,
+                                 key_bias, key_activation, kernel, bias, activation, num_heads, split_value_heads, drop_rate,
+                                 _rng.resolve(seed) if drop_rate > 0.0 else 0)
         q_act, q_left = ops.activation_code(query_activation)
         k_act, k_left = ops.activation_code(key_activation)
         f32 = lambda t: None if t is None else ops.as_device(t, torch.float32, device=dev)     # noqa: E731
@@ -106,14 +110,15 @@ def gat(x, edge_index,
 def _gat_training(x, csr, edge_index_used, query_kernel, query_bias, query_activation, key_kernel, key_bias,
                   key_activation, kernel, bias, activation, num_heads, split_value_heads, drop_rate, seed):
     """The same layer behind autograd Functions (demo/demo_gat.py trains through tf.GradientTape): dense projections
-    with dX/dW/db GEMMs, then GatAttention."""
-    dev = x.device
+    with dX/dW/db GEMMs (sparse features: the aggregation kernel over x's pattern and its transpose), then GatAttention."""
+    sparse_x = as_sparse_features(x)
+    dev = csr.col.device
 
     def dense(w, b, act):
         code, left = ops.activation_code(act)
         w = ops.as_device(w, torch.float32, device=dev)
         b = None if b is None else ops.as_device(b, torch.float32, device=dev)
-        y = autograd.Dense.apply(x, w, b, code)
+        y = autograd.Dense.apply(x, w, b, code) if sparse_x is None else autograd.SparseMatmul.apply(w, b, sparse_x, code)
         return left(y) if left is not None else y
 
     Q = dense(query_kernel, query_bias, query_activation)

@@ -114,7 +114,8 @@ def gcn(x, sparse_adj, kernel, bias=None, activation=None,
     :param kernel: [num_features, units] or None (propagate x itself)
     :param bias: [units] or None
     :param activation: callable or None; relu is fused into the aggregation epilogue
-    :param num_or_size_splits: accepted for parity; the fused kernel has no [E, D] temporary to bound
+    :param num_or_size_splits: column chunks of the propagation (gcn.py:274-280): one launch per chunk into slices of one
+        output, same bits (the fused kernel has no [E, D] temporary to bound, so this is an API-parity feature)
     :return: [num_nodes, units]
     """
     normed = gcn_norm_adj(sparse_adj, norm=norm, add_self_loop=add_self_loop, sym=sym, renorm=renorm,
@@ -128,8 +129,10 @@ def gcn(x, sparse_adj, kernel, bias=None, activation=None,
         if kernel is None:
             raise ValueError("a sparse feature matrix needs a kernel (reference gcn.py:266-272)")
         if autograd.needs_grad(kernel, bias):
-            raise NotImplementedError("training with sparse features: pass x.to_dense() (the backward of the sparse "
-                                      "projection is not built)")
+            # training (demo/demo_gcn.py:60-75): dW = x^T dH is the same kernel over the transposed pattern of x
+            h = autograd.propagate(x_sparse, ops.as_device(kernel, torch.float32, device=dev))
+            h = autograd.SparseMatmul.apply(h, bias, normed, act_code)
+            return leftover(h) if leftover is not None else h
         h = project_features(x_sparse, kernel)
         h = normed.matmul(h, num_or_size_splits=num_or_size_splits, bias=bias, act=act_code)
         return leftover(h) if leftover is not None else h

@@ -139,11 +139,15 @@ def _pool_sage(reduce, x, edge_index, edge_weight, self_kernel, neighbor_mlp_ker
     x = ops.as_device(x, torch.float32, device=dev)
     num_nodes = x.shape[0]
     if autograd.needs_grad(x, self_kernel, neighbor_mlp_kernel, neighbor_kernel, neighbor_mlp_bias, bias):
-        if reduce != "mean":
-            raise NotImplementedError("max_pool_graph_sage has no backward kernel (the max reduce keeps no argmax)")
         f32 = lambda t: None if t is None else ops.as_device(t, torch.float32, device=dev)   # noqa: E731
         h_node = autograd.dense(x, f32(neighbor_mlp_kernel), f32(neighbor_mlp_bias), activation)
-        reduced = autograd.NeighborAggregate.apply(h_node, edge_index, None, "mean", num_nodes)
+        if reduce == "mean":
+            reduced = autograd.NeighborAggregate.apply(h_node, edge_index, None, "mean", num_nodes)
+        else:
+            # training only: the per-edge messages are materialised like the reference does (graph_sage.py:262-270), so that
+            # the max can route its gradient to the selected neighbours (ties share it, TF's UnsortedSegmentMax gradient)
+            messages = autograd.TakeRows.apply(h_node, edge_index[1].contiguous())
+            reduced = autograd.SegmentReduce.apply(messages, edge_index[0].contiguous(), num_nodes, "max")
         return _project_pair_autograd(x, reduced, f32(self_kernel), f32(neighbor_kernel), f32(bias), activation, concat,
                                       normalize)
     csr, _ = _structure.csr_for_edge_index(edge_index, num_nodes)
