@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 # coding=utf-8
 """Secondary workload of SURVEY.md 8d: an RMAT(0.57, 0.19, 0.19, 0.05) graph of ogbn-products size (skewed degrees).
-Times K1 and K3 alone and reports the degree skew; development tool (hub rows are not split yet)."""
+Times K1 and K3 alone and reports the degree skew; development tool (hub rows run through the work plan of DESIGN.md section 4:
+profiles/r1_rmat_{before,after}_hub_split.json)."""
 import json
 import os
 import sys
