@@ -74,6 +74,15 @@ def _worker(rank, world, port, n, seed, renorm, queue, exchange=None):
                                       gat_l.key_bias, ops.relu, gat_l.kernel, gat_l.bias, ops.relu, num_heads=heads))
         for got in (alone, together):
             assert np.array_equal(got[0].numpy(), want[0].numpy()) and np.array_equal(got[1].numpy(), want[1].numpy())
+        # the partitioned path is forward-only: a trainable layer must fail loudly instead of losing its gradients silently,
+        # and still runs for inference under no_grad
+        trainable = tfg.layers.GCN(u, activation=ops.relu, renorm=renorm, seed=2, trainable=True)
+        with pytest.raises(NotImplementedError):
+            trainable([xl, pg])
+        with pytest.raises(NotImplementedError):
+            pg.share(xl, [trainable])
+        with torch.no_grad():
+            assert np.array_equal(trainable([xl, pg]).numpy(), want[0].numpy())
         queue.put((rank, p.lo, p.hi, gcn_local.numpy(), gat_local.numpy()))
         dist.barrier()
     finally:

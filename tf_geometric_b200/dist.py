@@ -320,6 +320,7 @@ class PartitionedGraph(object):
             for key, group in layer.partitioned_projections():
                 owners.append(key)
                 groups.append(group)
+        _forward_only("PartitionedGraph.share", x_local, *[t for group in groups for w, b, _ in group for t in (w, b)])
         if groups:
             for key, buf in zip(owners, self.project_all_rows(x_local, groups)):
                 shared.projected[key] = buf
@@ -382,6 +383,15 @@ class SharedRows(object):
         return self.projected.get(tuple(id(w) for w in weights))
 
 
+def _forward_only(what, *tensors):
+    """The partitioned path has no backward pass: fail loudly rather than return rows without a grad_fn (a trainable
+    layer would silently receive no gradient)."""
+    from . import autograd
+    if autograd.needs_grad(*[t.x if isinstance(t, SharedRows) else t for t in tensors]):
+        raise NotImplementedError("{}: the partitioned (multi-GPU) path is forward-only; call it under torch.no_grad() "
+                                  "(or with layers created without trainable=True)".format(what))
+
+
 def _unwrap(x_local, dev):
     if isinstance(x_local, SharedRows):
         return x_local.x, x_local
@@ -391,6 +401,7 @@ def _unwrap(x_local, dev):
 def gcn_partitioned(pg, x_local, kernel, bias=None, activation=None, renorm=True, improved=False):
     """tfg.nn.gcn on a PartitionedGraph: returns this rank's rows of act(norm(A) (x W) + b)."""
     dev = pg.edge_index.device
+    _forward_only("gcn_partitioned", x_local, kernel, bias)
     x_local, shared = _unwrap(x_local, dev)
     csr, value_csr = pg.gcn_normed(renorm=renorm, improved=improved)
     h_full = shared.find(kernel) if shared is not None and kernel is not None else None
@@ -410,6 +421,7 @@ def gat_partitioned(pg, x_local, query_kernel, query_bias, query_activation, key
     """tfg.nn.gat (split_value_heads=True) on a PartitionedGraph: Q stays local, K and V travel in ONE all-gather of a
     [n_local, A + U] buffer that both projections write into directly."""
     dev = pg.edge_index.device
+    _forward_only("gat_partitioned", x_local, query_kernel, query_bias, key_kernel, key_bias, kernel, bias)
     x_local, shared = _unwrap(x_local, dev)
     f32 = lambda t: None if t is None else ops.as_device(t, torch.float32, device=dev)   # noqa: E731
     q_act, q_left = ops.activation_code(query_activation)
@@ -436,6 +448,7 @@ def gcn_gat_overlapped(pg, x_local, gcn_kernel, gcn_bias, gcn_activation,
     stream, and the GCN aggregation runs while K|V is still travelling.  Results are identical to calling
     gcn_partitioned / gat_partitioned one after the other (relu query/key activations)."""
     dev = pg.edge_index.device
+    _forward_only("gcn_gat_overlapped", x_local, gcn_kernel, gcn_bias, query_kernel, query_bias, key_kernel, key_bias, kernel, bias)
     x_local = ops.as_device(x_local, torch.float32, device=dev)
     f32 = lambda t: None if t is None else ops.as_device(t, torch.float32, device=dev)   # noqa: E731
     csr, value_csr = pg.gcn_normed()
