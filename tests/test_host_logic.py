@@ -158,3 +158,27 @@ def test_remaining_convs_train_on_the_fake_backend(fake):
 
 def test_pooling_passes_gradients_on_the_fake_backend(fake):
     test_gpu_train.test_every_pool_layer_passes_gradients()
+
+
+def test_sparse_matrix_product_is_differentiable(fake):
+    """`A @ h` in a user's own training loop (tf_sparse products sit under tf.GradientTape in the reference's demos): the
+    gradient reaches h and the bias; epilogue forms without a backward raise instead of cutting the graph."""
+    rs = np.random.RandomState(4)
+    n, m, d = 40, 30, 6
+    index = np.stack([rs.randint(0, n, 200), rs.randint(0, m, 200)]).astype(np.int32)
+    value = rs.rand(200).astype(np.float32)
+    a = tfg.SparseMatrix(index, value, [n, m])
+    h = torch.from_numpy(rs.randn(m, d).astype(np.float32)).requires_grad_(True)
+    g = torch.from_numpy(rs.randn(n, d).astype(np.float32))
+    y = a @ h
+    assert y.requires_grad
+    (y * g).sum().backward()
+    dense = torch.zeros(n, m, dtype=torch.float64)
+    dense.index_put_((torch.from_numpy(index[0]).long(), torch.from_numpy(index[1]).long()), torch.from_numpy(value).double(),
+                     accumulate=True)
+    np.testing.assert_allclose(y.detach().numpy(), (dense @ h.detach().double()).numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(h.grad.numpy(), (dense.t() @ g.double()).numpy(), rtol=1e-5, atol=1e-5)
+    with pytest.raises(NotImplementedError):
+        a.matmul(h, alpha=2.0)
+    with torch.no_grad():
+        assert not (a @ h).requires_grad

@@ -115,6 +115,13 @@ class SparseMatrix(object):
         reference's split -> matmul -> concat; the fused kernel has no [E, D] temporary to bound, so the results are the
         same bits with or without it."""
         h = ops.as_device(h, torch.float32, device=self.index.device)
+        from . import autograd
+        if autograd.needs_grad(h, epilogue.get("bias")):
+            # `A @ h` inside a user's training loop (tf_sparse products are differentiable under tf.GradientTape): the same
+            # kernel behind autograd (dh = A^T g over the transposed structure); column chunks change no bit, so none here
+            if h.dim() != 2 or set(epilogue) - {"bias", "act"}:
+                raise NotImplementedError("SparseMatrix.matmul: gradients are built for act(A @ h + bias) with a 2-D h")
+            return autograd.propagate(self, h, epilogue.get("bias"), epilogue.get("act", ops.ACT_NONE))
         if num_or_size_splits is None or h.dim() != 2:
             return ops.spmm(self.csr, self.value_csr, h, reduce="sum", **epilogue)
         d = h.shape[1]
